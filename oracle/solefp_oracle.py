@@ -1,0 +1,276 @@
+"""NumPy restatement of the reference's SolEFP central-mode evaluation.
+
+TEST INFRASTRUCTURE -- never imported by the product (slv_b200/).
+
+Follows solvshift/solefp.py:1011-1629 (``EFP._eval_mode_central``), solvshift/slvpar.py:641-734
+(``Frag.sup``), solvshift/src/efprot.f (rotations), solvshift/src/solpol2.f:3-115 (``MOLLST``).
+The multipole electrostatics (``sdmtpm/sdmtpe/dmtcor``), the dispersion shift
+(``sdisp6/tdisp6``) and the Kabsch superimposer live in the un-vendored dependency
+``libbbg`` (>= 1.1.0, github.com/globulion/libbbg; no lockfile pins it): their published
+algorithm is restated from SURVEY.md Appendix A and anchored on the reference call sites
+solefp.py:1175-1190, 1434-1435, slvpar.py:646-652 and on the golden vector
+examples/1_small-clusters/f.
+
+Everything here works with full (unreduced) Cartesian tensors and einsum, i.e. a formulation
+independent of the reduced-storage CUDA kernels it checks.
+"""
+import numpy as np
+
+BohrToAngstrom = 0.529177249
+HartreePerHbarToCmRec = 219474.63067
+
+# reduced-storage index maps (efprot.f:312-320)
+_Q_IDX = [(0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2)]
+_O_IDX = [(0, 0, 0), (1, 1, 1), (2, 2, 2), (0, 0, 1), (0, 0, 2), (0, 1, 1), (1, 1, 2), (0, 2, 2), (1, 2, 2), (0, 1, 2)]
+
+
+def quad_full(q):
+    """[...,6] reduced -> [...,3,3] symmetric."""
+    q = np.asarray(q)
+    out = np.zeros(q.shape[:-1] + (3, 3))
+    for k, (a, b) in enumerate(_Q_IDX):
+        out[..., a, b] = q[..., k]
+        out[..., b, a] = q[..., k]
+    return out
+
+
+def oct_full(o):
+    """[...,10] reduced -> [...,3,3,3] fully symmetric."""
+    import itertools
+    o = np.asarray(o)
+    out = np.zeros(o.shape[:-1] + (3, 3, 3))
+    for k, abc in enumerate(_O_IDX):
+        for perm in set(itertools.permutations(abc)):
+            out[(Ellipsis,) + perm] = o[..., k]
+    return out
+
+
+def quad_reduced(Q):
+    return np.stack([Q[..., a, b] for a, b in _Q_IDX], axis=-1)
+
+
+def oct_reduced(O):
+    return np.stack([O[..., a, b, c] for a, b, c in _O_IDX], axis=-1)
+
+
+def traceless_full(Q, O):
+    """Buckingham traceless forms (efprot.f:1256-1292)."""
+    d = np.eye(3)
+    trq = np.einsum('...aa->...', Q)
+    Th = 1.5 * Q - 0.5 * trq[..., None, None] * d
+    t = np.einsum('...abb->...a', O)
+    Om = 2.5 * O - 0.5 * (np.einsum('...a,bc->...abc', t, d) + np.einsum('...b,ac->...abc', t, d)
+                          + np.einsum('...c,ab->...abc', t, d))
+    return Th, Om
+
+
+# --------------------------------------------------------------------------- Kabsch
+def kabsch(ref, target, supl=None):
+    """Biopython-style SVDSuperimposer as used through libbbg (slvpar.py:641-679):
+    rotate/translate the parameter geometry <ref> onto <target> using atoms <supl>.
+    Row-vector convention x' = x.rot + transl.  One-atom fragments: identity + shift
+    (slvpar.py:668-671).  Returns rot, transl, rms."""
+    ref = np.asarray(ref, float); target = np.asarray(target, float)
+    if len(target) == 1:
+        return np.eye(3), (target - ref).reshape(3), 0.0
+    if supl is not None:
+        coords = ref[supl]; reference = target[supl]
+    else:
+        coords = ref; reference = target
+    av1 = coords.mean(0); av2 = reference.mean(0)
+    c = coords - av1; r = reference - av2
+    a = c.T @ r
+    u, d, vt = np.linalg.svd(a)
+    rot = (vt.T @ u.T).T
+    if np.linalg.det(rot) < 0:
+        vt[2] = -vt[2]
+        rot = (vt.T @ u.T).T
+    tran = av2 - av1 @ rot
+    diff = coords @ rot + tran - reference
+    rms = np.sqrt((diff * diff).sum() / len(coords))
+    return rot, tran, rms
+
+
+def reorder_xyz(xyz, reord):
+    """solefp.py:1633-1645: row i of the result is xyz[reord[i]], zeros where reord[i] < 0."""
+    out = np.zeros((len(reord), 3))
+    for i, I in enumerate(reord):
+        if I > -1:
+            out[i] = xyz[I]
+    return out
+
+
+def mollst(rc, rm_list, ccut, pcut, ecut):
+    """MOLLST (solpol2.f:3-115): unweighted centre of the solute vs unweighted centre of each
+    solvent molecule; in layer iff distance < cut (strict)."""
+    c0 = rc.sum(0) / float(len(rc))
+    icm, ipm, iem = [], [], []
+    for xyz in rm_list:
+        c = xyz.sum(0) / float(len(xyz))
+        d = c0 - c
+        rr = np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+        icm.append(rr < ccut); ipm.append(rr < pcut); iem.append(rr < ecut)
+    return np.array(icm, bool), np.array(ipm, bool), np.array(iem, bool)
+
+
+# --------------------------------------------------------------------------- rotation of parameters
+def sup_params(par, rot, transl):
+    """Frag.sup body (slvpar.py:680-733): returns a new dict with every tensor transformed.
+    Multipoles rotate as mu' = mu.R, Q' = R^T Q R, O'_ijk = O_abc R_ai R_bj R_ck (efprot.f:297-301);
+    polarisabilities alpha' = R^T alpha R (slvpar.py:707-722)."""
+    R = np.asarray(rot); t = np.asarray(transl)
+    out = dict(par)
+    for k in ('pos', 'lmoc', 'rpol', 'rdma'):
+        if k in par:
+            out[k] = par[k] @ R + t
+    for k in ('lmoc1', 'lvec'):
+        if k in par:
+            out[k] = par[k] @ R
+    for sfx in ('', '1', '2'):
+        if 'dmad' + sfx in par:
+            out['dmad' + sfx] = par['dmad' + sfx] @ R
+            Q = quad_full(par['dmaq' + sfx]); O = oct_full(par['dmao' + sfx])
+            out['dmaq' + sfx] = quad_reduced(np.einsum('...ab,ai,bj->...ij', Q, R, R))
+            out['dmao' + sfx] = oct_reduced(np.einsum('...abc,ai,bj,ck->...ijk', O, R, R, R))
+    for k in ('dpol', 'dpol1', 'dpoli', 'dpoli1'):
+        if k in par:
+            out[k] = np.einsum('ai,...ab,bj->...ij', R, par[k], R)
+    return out
+
+
+def _lab_moments(par, sfx=''):
+    """q, mu, Theta(full, traceless), Omega(full, traceless) for suffix '', '1' or '2'."""
+    q = par['dmac' + sfx]; mu = par['dmad' + sfx]
+    Th, Om = traceless_full(quad_full(par['dmaq' + sfx]), oct_full(par['dmao' + sfx]))
+    return q, mu, Th, Om
+
+
+# --------------------------------------------------------------------------- electrostatics
+def _T_tensors(R):
+    """Interaction tensors of 1/R up to rank 3 for R[...,3]."""
+    d = np.eye(3)
+    r2 = (R * R).sum(-1); r = np.sqrt(r2)
+    T0 = 1.0 / r
+    T1 = -R / r[..., None] ** 3
+    T2 = (3.0 * np.einsum('...a,...b->...ab', R, R) - r2[..., None, None] * d) / r[..., None, None] ** 5
+    RRR = np.einsum('...a,...b,...c->...abc', R, R, R)
+    Rd = (np.einsum('...a,bc->...abc', R, d) + np.einsum('...b,ac->...abc', R, d) + np.einsum('...c,ab->...abc', R, d))
+    T3 = -(15.0 * RRR - 3.0 * r2[..., None, None, None] * Rd) / r[..., None, None, None] ** 7
+    return T0, T1, T2, T3
+
+
+def emtp_r4(rA, qA, muA, ThA, OmA, rB, qB, muB, ThB, OmB):
+    """Multipole-multipole interaction energy between site sets A and B, orders R^-1..R^-4
+    only (the truncation ``sdmtpm`` applies: q-q; q-mu; q-Theta + mu-mu; q-Omega + mu-Theta).
+    Moment arrays of A may carry leading batch axes before the site axis."""
+    R = rB[None, :, :] - rA[:, None, :]                      # [nA,nB,3]
+    T0, T1, T2, T3 = _T_tensors(R)
+    e = np.einsum('...i,ij,j->...', qA, T0, qB)
+    e = e + np.einsum('...i,ija,ja->...', qA, T1, muB) - np.einsum('...ia,ija,j->...', muA, T1, qB)
+    e = e + (np.einsum('...i,ijab,jab->...', qA, T2, ThB) + np.einsum('...iab,ijab,j->...', ThA, T2, qB)) / 3.0 \
+          - np.einsum('...ia,ijab,jb->...', muA, T2, muB)
+    e = e + (np.einsum('...i,ijabc,jabc->...', qA, T3, OmB) - np.einsum('...iabc,ijabc,j->...', OmA, T3, qB)) / 15.0 \
+          - np.einsum('...ia,ijabc,jbc->...', muA, T3, ThB) / 3.0 + np.einsum('...iab,ijabc,jc->...', ThA, T3, muB) / 3.0
+    return e
+
+
+def mode_weights(parc, mode):
+    """w_m = g_mjj/(M_m w_m^2), den = 2 M_j w_j  (mode is 1-based, as in the reference API)."""
+    gijj = parc['gijk'][:, mode - 1, mode - 1]
+    w = gijj / (parc['redmass'] * parc['freq'] ** 2)
+    den = 2.0 * parc['redmass'][mode - 1] * parc['freq'][mode - 1]
+    return w, den
+
+
+def elect_shifts(parc, solv, mode, ea=True, corr=True):
+    """ele_mea, ele_ea, cor_mea, cor_ea (a.u.) and fi_el[nmodes] for an already superimposed
+    solute <parc> and list of superimposed solvent dicts <solv> (solefp.py:1167-1190)."""
+    w, den = mode_weights(parc, mode)
+    nmodes = len(w)
+    if len(solv) == 0:
+        return 0.0, 0.0, 0.0, 0.0, np.zeros(nmodes)
+    rB = np.concatenate([s['rdma'] for s in solv])
+    qB = np.concatenate([s['dmac'] for s in solv])
+    muB = np.concatenate([s['dmad'] for s in solv])
+    QB = np.concatenate([quad_full(s['dmaq']) for s in solv])
+    OB = np.concatenate([oct_full(s['dmao']) for s in solv])
+    ThB, OmB = traceless_full(QB, OB)
+    rA = parc['rdma']
+    q1, mu1, Th1, Om1 = _lab_moments(parc, '1')             # [nmodes, ndma, ...]
+    fi = emtp_r4(rA, q1, mu1, Th1, Om1, rB, qB, muB, ThB, OmB)
+    mea = -(w * fi).sum() / den
+    eav = 0.0
+    if ea:
+        m2 = list(parc['mode']).index(mode - 1)
+        q2 = parc['dmac2'][m2]; mu2 = parc['dmad2'][m2]
+        Th2, Om2 = traceless_full(quad_full(parc['dmaq2'][m2]), oct_full(parc['dmao2'][m2]))
+        eav = emtp_r4(rA, q2, mu2, Th2, Om2, rB, qB, muB, ThB, OmB) / den
+    cmea = cea = 0.0
+    if corr:
+        # gradient of the potential of the solvent CHARGES at the solute sites (= atoms)
+        R = rA[:, None, :] - rB[None, :, :]
+        r3 = ((R * R).sum(-1)) ** 1.5
+        G = -(qB[None, :, None] * R / r3[..., None]).sum(1)         # grad V at each solute site
+        L = parc['lvec']                                            # [nmodes, natoms, 3]
+        qA = parc['dmac']
+        per_mode = np.einsum('x,mxa,xa->m', qA, L, G)
+        cmea = -(w * per_mode).sum() / den
+        cea = 2.0 * np.einsum('x,xa,xa->', parc['dmac1'][mode - 1], L[mode - 1], G) / den
+    return mea, eav, cmea, cea, fi
+
+
+# --------------------------------------------------------------------------- dispersion
+_GL12 = np.array([
+    [0.0471753363865118, -0.9815606342467192], [0.1069393259953184, -0.9041172563704749],
+    [0.1600783285433462, -0.7699026741943047], [0.2031674267230659, -0.5873179542866175],
+    [0.2334925365383548, -0.3678314989981802], [0.2491470458134028, -0.1252334085114689],
+    [0.2491470458134028, 0.1252334085114689], [0.2334925365383548, 0.3678314989981802],
+    [0.2031674267230659, 0.5873179542866175], [0.1600783285433462, 0.7699026741943047],
+    [0.1069393259953184, 0.9041172563704749], [0.0471753363865118, 0.9815606342467192]])
+
+
+def gl12_weights(v=0.3):
+    """slvpar.py:989-1019."""
+    return 2.0 * v * _GL12[:, 0] / (1.0 - _GL12[:, 1]) ** 2
+
+
+def _disp_energy(ri, ai, rj, aj, W):
+    """E_iso, E_ani for solute LMO set (ri [n,3], ai [n,12,3,3]) vs solvent (rj, aj).
+    ani: -(1/2pi) sum W_k T_ab aj_cb T_cd ai_da ; iso: -(3/pi) sum W_k abar_i abar_j / R^6."""
+    R = ri[:, None, :] - rj[None, :, :]
+    r2 = (R * R).sum(-1)
+    T = (3.0 * np.einsum('ija,ijb->ijab', R, R) - r2[..., None, None] * np.eye(3)) / r2[..., None, None] ** 2.5
+    ani = -np.einsum('k,ijab,jkcb,ijcd,ikda->', W, T, aj, T, ai) / (2.0 * np.pi)
+    abi = np.einsum('ikaa->ik', ai) / 3.0; abj = np.einsum('jkaa->jk', aj) / 3.0
+    iso = -(3.0 / np.pi) * np.einsum('k,ik,jk,ij->', W, abi, abj, 1.0 / r2 ** 3)
+    return iso, ani
+
+
+def disp_shifts(parc, solv, mode, h=None):
+    """dis_mea_iso, dis_mea (a.u.): -sum_m w_m dE/dQ_m / den with dE/dQ_m acting on the solute
+    polarisabilities (dpoli1) and LMO centroids (lmoc1) (solefp.py:1427-1435).
+    The centroid derivative is taken analytically through the linear pre-contraction
+    u_i = sum_m w_m lmoc1_m and a complex-step-free central difference is NOT used: the
+    directional derivative is evaluated exactly by differentiating T."""
+    w, den = mode_weights(parc, mode)
+    if len(solv) == 0:
+        return 0.0, 0.0
+    W = gl12_weights()
+    ri = parc['rpol']; ai = parc['dpoli']
+    rj = np.concatenate([s['rpol'] for s in solv]); aj = np.concatenate([s['dpoli'] for s in solv])
+    A1 = np.tensordot(w, parc['dpoli1'], (0, 0))                 # [npol,12,3,3]
+    u = np.tensordot(w, parc['lmoc1'], (0, 0))                   # [npol,3]
+    # (1) polarisability-derivative part: E is linear in ai
+    iso1, ani1 = _disp_energy(ri, A1, rj, aj, W)
+    # (2) centroid part: d/de E(ri + e u) at e=0, analytic
+    R = ri[:, None, :] - rj[None, :, :]
+    r2 = (R * R).sum(-1); Ru = np.einsum('ija,ia->ij', R, u)
+    d = np.eye(3)
+    T = (3.0 * np.einsum('ija,ijb->ijab', R, R) - r2[..., None, None] * d) / r2[..., None, None] ** 2.5
+    dT = (3.0 * (np.einsum('ia,ijb->ijab', u, R) + np.einsum('ija,ib->ijab', R, u)) - 2.0 * Ru[..., None, None] * d) \
+        / r2[..., None, None] ** 2.5 - 5.0 * Ru[..., None, None] * T / r2[..., None, None]
+    ani2 = -(np.einsum('k,ijab,jkcb,ijcd,ikda->', W, dT, aj, T, ai)
+             + np.einsum('k,ijab,jkcb,ijcd,ikda->', W, T, aj, dT, ai)) / (2.0 * np.pi)
+    abi = np.einsum('ikaa->ik', ai) / 3.0; abj = np.einsum('jkaa->jk', aj) / 3.0
+    iso2 = -(3.0 / np.pi) * np.einsum('k,ik,jk,ij->', W, abi, abj, -6.0 * Ru / r2 ** 4)
+    return -(iso1 + iso2) / den, -(ani1 + ani2) / den
