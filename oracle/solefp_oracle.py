@@ -274,3 +274,136 @@ def disp_shifts(parc, solv, mode, h=None):
     abi = np.einsum('ikaa->ik', ai) / 3.0; abj = np.einsum('jkaa->jk', aj) / 3.0
     iso2 = -(3.0 / np.pi) * np.einsum('k,ik,jk,ij->', W, abi, abj, -6.0 * Ru / r2 ** 4)
     return -(iso1 + iso2) / den, -(ani1 + ani2) / den
+
+
+# --------------------------------------------------------------------------- polarisation
+def _field_traceless(R, q, mu, Th, Om, oct_fac):
+    """Field at displacement R = P - r_site of a site with Buckingham-traceless moments:
+    qR/R^3 + 3(mu.R)R/R^5 - mu/R^3 + 5(R Th R)R/R^7 - 2 Th R/R^5 + oct_fac (Om RRR) R/R^9 - 3 (Om RR)/R^7.
+    oct_fac = 7 is the physical value; FFFFFF uses 5 (solpol2.f:1425).  Shapes: R [...,3],
+    moments broadcastable against the leading axes of R."""
+    r2 = (R * R).sum(-1); ri = 1.0 / np.sqrt(r2)
+    r3 = ri ** 3; r5 = r3 * ri * ri; r7 = r5 * ri * ri; r9 = r7 * ri * ri
+    mR = (mu * R).sum(-1)
+    ThR = np.einsum('...ab,...b->...a', Th, R); RThR = (ThR * R).sum(-1)
+    OmRR = np.einsum('...abc,...b,...c->...a', Om, R, R); OmRRR = (OmRR * R).sum(-1)
+    return (q * r3)[..., None] * R + (3.0 * mR * r5)[..., None] * R - r3[..., None] * mu \
+        + (5.0 * RThR * r7)[..., None] * R - 2.0 * r5[..., None] * ThR \
+        + (oct_fac * OmRRR * r9)[..., None] * R - 3.0 * r7[..., None] * OmRR
+
+
+def _dfield_traceless(R, v, q, mu, Th, Om):
+    """Directional derivative along v (of the field point) of the PHYSICAL field (oct factor 7),
+    with the reference's one slip reproduced: in the auxiliary sum SUM2 = Om_abc v_a R_b R_c the term
+    O_xzz v_z R_x R_z is counted once instead of twice (solpol2.f:466-483 and 959-976)."""
+    r2 = (R * R).sum(-1); ri2 = 1.0 / r2; ri = np.sqrt(ri2)
+    r3 = ri ** 3; r5 = r3 * ri2; r7 = r5 * ri2; r9 = r7 * ri2
+    Rv = (R * v).sum(-1)
+    mR = (mu * R).sum(-1); mv = (mu * v).sum(-1)
+    ThR = np.einsum('...ab,...b->...a', Th, R); Thv = np.einsum('...ab,...b->...a', Th, v)
+    RThR = (ThR * R).sum(-1); vThR = (ThR * v).sum(-1)
+    OmRR = np.einsum('...abc,...b,...c->...a', Om, R, R); OmRRR = (OmRR * R).sum(-1)
+    OmvR = np.einsum('...abc,...b,...c->...a', Om, v, R)
+    sum2 = (OmRR * v).sum(-1) - Om[..., 0, 2, 2] * v[..., 2] * R[..., 0] * R[..., 2]
+    e = lambda s: s[..., None]
+    out = e(q * r3) * (v - e(3.0 * Rv * ri2) * R)
+    out = out + e(3.0 * r5) * (e(mR) * v + e(mv) * R - e(5.0 * ri2 * mR * Rv) * R + e(Rv) * mu)
+    out = out + e(r5) * (e(5.0 * ri2) * (e(2.0 * Rv) * ThR + e(2.0 * vThR) * R + e(RThR) * v) - 2.0 * Thv
+                         - e(35.0 * Rv * RThR * ri2 * ri2) * R)
+    out = out + e(7.0 * r9) * (e(OmRRR) * v - e(9.0 * ri2 * OmRRR * Rv) * R + e(3.0 * sum2) * R + e(3.0 * Rv) * OmRR) \
+        - e(6.0 * r7) * OmvR
+    return out
+
+
+def pol_system(parc, solv):
+    """Fields FLDS and matrix D of FFFFFF (solpol2.f:1270-1511) for solute + solvent list.
+    Returns F [N,3], D [3N,3N], centres [N,3], molecule id per centre, polinv [N,3,3]."""
+    PAR = [parc] + list(solv)
+    rp = np.concatenate([p['rpol'] for p in PAR]); molp = np.concatenate([[k] * p['npol'] for k, p in enumerate(PAR)])
+    rd = np.concatenate([p['rdma'] for p in PAR]); mold = np.concatenate([[k] * p['ndma'] for k, p in enumerate(PAR)])
+    q = np.concatenate([p['dmac'] for p in PAR]); mu = np.concatenate([p['dmad'] for p in PAR])
+    Th, Om = traceless_full(np.concatenate([quad_full(p['dmaq']) for p in PAR]),
+                            np.concatenate([oct_full(p['dmao']) for p in PAR]))
+    pol = np.concatenate([p['dpol'] for p in PAR]); polinv = np.linalg.inv(pol)
+    N = len(rp)
+    R = rp[:, None, :] - rd[None, :, :]
+    Fij = _field_traceless(R, q[None], mu[None], Th[None], Om[None], 5.0)
+    Fij = np.where((molp[:, None] != mold[None, :])[..., None], Fij, 0.0)
+    F = Fij.sum(1)
+    Rp = rp[:, None, :] - rp[None, :, :]
+    r2 = (Rp * Rp).sum(-1); np.fill_diagonal(r2, 1.0)
+    T = np.eye(3) / r2[..., None, None] ** 1.5 - 3.0 * np.einsum('ija,ijb->ijab', Rp, Rp) / r2[..., None, None] ** 2.5
+    T = np.where((molp[:, None] != molp[None, :])[..., None, None], T, 0.0)
+    D = T.transpose(0, 2, 1, 3).reshape(3 * N, 3 * N).copy()
+    for i in range(N):
+        D[3 * i:3 * i + 3, 3 * i:3 * i + 3] = polinv[i]
+    return F, D, rp, molp, polinv
+
+
+def pol_shift(parc, solv, mode, literal_gemm=False):
+    """pol_mea (a.u.), fi_pol[nmodes], dipind, avec -- SFTPLI + AAAAAA (solpol2.f:118-239, 242-1150).
+    literal_gemm=True forms D^-1 dD_m D^-1 with two dense products per mode exactly like the
+    reference (solpol2.f:1124-1129); otherwise the same vectors come from mat-vecs."""
+    w, den = mode_weights(parc, mode)
+    g = w / den
+    nmodes = len(w)
+    if len(solv) == 0:
+        return 0.0, np.zeros(nmodes), None, None
+    F, D, rp, molp, polinv = pol_system(parc, solv)
+    N = len(rp); npc = parc['npol']; ndc = parc['ndma']
+    assert ndc == parc['natoms'], 'AAAAAA indexes lvec/dma1 by DMTP site: needs ndma == natoms (solpol2.f:738-741, 873-876)'
+    Dinv = np.linalg.inv(D)
+    Fv = F.reshape(3 * N)
+    dipind = Dinv @ Fv
+    mat1 = Dinv + Dinv.T
+    # solvent data
+    rdB = np.concatenate([p['rdma'] for p in solv]); qB = np.concatenate([p['dmac'] for p in solv])
+    muB = np.concatenate([p['dmad'] for p in solv])
+    ThB, OmB = traceless_full(np.concatenate([quad_full(p['dmaq']) for p in solv]),
+                              np.concatenate([oct_full(p['dmao']) for p in solv]))
+    # solute data
+    rdA = parc['rdma']; qA = parc['dmac']; muA = parc['dmad']
+    ThA, OmA = traceless_full(quad_full(parc['dmaq']), oct_full(parc['dmao']))
+    q1 = parc['dmac1']; mu1 = parc['dmad1']
+    Th1, Om1 = traceless_full(quad_full(parc['dmaq1']), oct_full(parc['dmao1']))
+    rpA = rp[:npc]; rpB = rp[npc:]
+    R_AB = rpA[:, None, :] - rdB[None, :, :]                  # solute centres <- solvent sites
+    R_pp = rpA[:, None, :] - rpB[None, :, :]                  # solute centres vs solvent centres
+    r2pp = (R_pp * R_pp).sum(-1)
+    R_BA = rpB[:, None, :] - rdA[None, :, :]                  # solvent centres <- solute sites
+    avec = np.zeros(3 * N); fi = np.zeros(nmodes)
+    for m in range(nmodes):
+        dD = np.zeros((3 * N, 3 * N)); dF = np.zeros((N, 3))
+        r1 = parc['lmoc1'][m]                                  # [npc,3]
+        for i in range(npc):
+            dD[3 * i:3 * i + 3, 3 * i:3 * i + 3] = -polinv[i] @ parc['dpol1'][m, i] @ polinv[i]
+        # field derivative at solute centres (they move by r1)
+        v = np.broadcast_to(r1[:, None, :], R_AB.shape)
+        dF[:npc] = _dfield_traceless(R_AB, v, qB[None], muB[None], ThB[None], OmB[None]).sum(1)
+        # D-matrix derivative, solute-solvent blocks: HALF of dT/dr_i . r1 (solpol2.f:699-706), mirrored
+        R1R = np.einsum('ija,ia->ij', R_pp, r1)
+        blk = R1R[..., None, None] * (np.eye(3) - 5.0 * np.einsum('ija,ijb->ijab', R_pp, R_pp) / r2pp[..., None, None]) \
+            + np.einsum('ija,ib->ijab', R_pp, r1) + np.einsum('ia,ijb->ijab', r1, R_pp)
+        blk = -blk * (1.5 / r2pp ** 2.5)[..., None, None]
+        nB = N - npc
+        off = blk.transpose(0, 2, 1, 3).reshape(3 * npc, 3 * nB)
+        dD[:3 * npc, 3 * npc:] = off
+        dD[3 * npc:, :3 * npc] = blk.transpose(1, 2, 0, 3).reshape(3 * nB, 3 * npc)
+        # field derivative at solvent centres: solute sites move by lvec_m and carry dma1_m
+        L = parc['lvec'][m]                                    # [natoms(=ndma),3]
+        vL = np.broadcast_to(L[None, :, :], R_BA.shape)
+        moving = _dfield_traceless(R_BA, vL, qA[None], muA[None], ThA[None], OmA[None])
+        deriv = _field_traceless(R_BA, q1[m][None], mu1[m][None], Th1[m][None], Om1[m][None], 7.0)
+        dF[npc:] = (deriv - moving).sum(1)
+        dFv = dF.reshape(3 * N)
+        if literal_gemm:
+            mat3 = Dinv @ (dD @ Dinv)
+            vec1 = mat3.T @ Fv
+        else:
+            vec1 = Dinv.T @ (dD.T @ (Dinv.T @ Fv))
+        vec2 = mat1.T @ dFv
+        mivec = vec1 - vec2
+        avec += g[m] * mivec
+        fi[m] = 0.5 * Fv @ mivec
+    shift = -0.5 * Fv @ avec
+    return shift, fi, dipind.reshape(N, 3), avec.reshape(N, 3)
