@@ -407,3 +407,46 @@ def pol_shift(parc, solv, mode, literal_gemm=False):
         fi[m] = 0.5 * Fv @ mivec
     shift = -0.5 * Fv @ avec
     return shift, fi, dipind.reshape(N, 3), avec.reshape(N, 3)
+
+
+# --------------------------------------------------------------------------- one frame, all terms
+def eval_frame(pos, ind, nmol, pars, supl, reord, mode, ccut=1e10, pcut=1e10, ecut=1e10,
+               elect=True, ea=True, corr=True, pol=False, disp=False, rep=False, rep_fn=None):
+    """EFP.set + EFP.eval(0) for one frame in central mode (solefp.py:223-277, 738-787, 1011-1629).
+    pars: list of parameter dicts (Frag.get()); returns a dict of a.u. terms + rms values."""
+    ind = np.asarray(ind, int); nmol = np.asarray(nmol, int)
+    off = np.concatenate([[0], np.cumsum(nmol)])
+    xyz = [pos[off[i]:off[i + 1]] for i in range(len(ind))]
+    icm, ipm, iem = mollst(xyz[0], xyz[1:], ccut, pcut, ecut)
+
+    def sup(i):
+        t = ind[i]; p = pars[t]
+        ro = reord[t] if reord is not None and reord[t] is not None else np.arange(p['natoms'])
+        sl = supl[t] if supl is not None else None
+        r, tr, rms = kabsch(p['pos'], reorder_xyz(xyz[i], ro), sl)
+        return sup_params(p, r, tr), rms
+
+    parc, rms_c = sup(0)
+    out = dict(ele_mea=0.0, ele_ea=0.0, cor_mea=0.0, cor_ea=0.0, pol_mea=0.0, rep_mea=0.0, dis_mea=0.0, dis_mea_iso=0.0)
+    lay_c = [sup(i + 1) for i in np.nonzero(icm)[0]]
+    rms_s = [r for _, r in lay_c]
+    out['rms_c'] = rms_c
+    out['rms_smax'] = max(rms_s) if rms_s else 0.0
+    out['rms_ave'] = (rms_c + sum(rms_s)) / (len(rms_s) + 1.0)
+    out['n_elect'] = int(icm.sum()); out['n_pol'] = int(ipm.sum()); out['n_rep'] = int(iem.sum())
+    if elect:
+        m, e, cm, ce, fi = elect_shifts(parc, [p for p, _ in lay_c], mode, ea=ea, corr=corr)
+        out.update(ele_mea=m, ele_ea=e, cor_mea=cm, cor_ea=ce, fi_el=fi)
+        lay_p = None
+        if pol or disp:
+            lay_p = [sup(i + 1)[0] for i in np.nonzero(ipm)[0]]
+        if pol:
+            sh, fip, dip, av = pol_shift(parc, lay_p, mode)
+            out.update(pol_mea=sh, fi_pol=fip, dipind=dip, avec=av)
+        if disp:
+            iso, ani = disp_shifts(parc, lay_p, mode)
+            out.update(dis_mea=ani, dis_mea_iso=iso)
+    if rep:
+        lay_e = [sup(i + 1)[0] for i in np.nonzero(iem)[0]]
+        out['rep_mea'] = rep_fn(parc, lay_e, mode) if lay_e else 0.0
+    return out

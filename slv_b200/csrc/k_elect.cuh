@@ -1,0 +1,176 @@
+// k_elect.cuh -- kernel A: one CTA per MD frame.
+//   * MOLLST cut-off test per solvent instance (solvshift/src/solpol2.f:3-115)
+//   * Kabsch superimposition of the solute and of every solvent instance inside any cut-off
+//     (Frag.sup, solvshift/slvpar.py:641-679) -- once per instance, not once per layer
+//   * rotation of the instance's distributed multipoles into the lab frame (ROTDMA, efprot.f:286-741)
+//   * solute-solvent multipole electrostatic shift through R^-4 with the mode-contracted SolCAMM
+//     moment sets (libbbg sdmtpm/sdmtpe, call sites solvshift/solefp.py:1175-1182) and the
+//     charge-only potential-gradient corrections (dmtcor rf2/rk2, solefp.py:1186-1190)
+//   * compacted hand-over list (instance, flags, rot, transl) for the pol/disp/rep kernels
+// Coordinates are read exactly once from HBM; rotated multipoles are never materialised.
+#pragma once
+#include "slv_common.cuh"
+
+namespace slv {
+
+constexpr int ELECT_THREADS = 256;
+constexpr int SOLROW = 52;   // doubles per solute site in shared memory: pos3, smea20, sea20, cmea3, cea3 (+3 pad)
+
+__global__ void __launch_bounds__(ELECT_THREADS)
+k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, FrameLists fl, double *__restrict__ out) {
+  extern __shared__ double sm[];
+  double *s_sol = sm;                                   // [ndma_c][SOLROW]
+  __shared__ double s_xf[16];                           // solute rot(9) transl(3) rms, centroid(3)
+  __shared__ double s_red[32];
+  __shared__ int s_cnt[ELECT_THREADS / 32 + 1];
+  __shared__ int s_base;
+
+  const int fi = blockIdx.x;                            // frame within chunk
+  const double *x = coords + (size_t)(frame0 + fi) * p.natoms_total * 3;
+  const int *tm0 = tmeta(p, p.inst_type[0]);
+  const int ndmac = tm0[SLVGPU_M_NDMA];
+  const int a0c = p.inst_atom0[0], natc_md = p.inst_atom0[1] - a0c;
+
+  if (threadIdx.x == 0) {
+    double rot[9], tr[3], rms;
+    fit_instance(p, tm0, x + a0c * 3, rot, tr, rms);
+    double c[3] = {0, 0, 0};
+    for (int k = 0; k < natc_md; ++k) { c[0] += x[(a0c + k) * 3]; c[1] += x[(a0c + k) * 3 + 1]; c[2] += x[(a0c + k) * 3 + 2]; }
+    const double inv = 1.0 / (double)natc_md;
+#pragma unroll
+    for (int d = 0; d < 9; ++d) s_xf[d] = rot[d];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { s_xf[9 + d] = tr[d]; s_xf[13 + d] = c[d] * inv; }
+    s_xf[12] = rms;
+    double *sx = fl.sol_xf + (size_t)fi * 12;
+#pragma unroll
+    for (int d = 0; d < 9; ++d) sx[d] = rot[d];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) sx[9 + d] = tr[d];
+    s_base = 0;
+  }
+  __syncthreads();
+
+  // solute site rows in the lab frame
+  if ((p.flags & SLVGPU_ELECT) && threadIdx.x < ndmac) {
+    const int s = threadIdx.x;
+    double R[9];
+#pragma unroll
+    for (int d = 0; d < 9; ++d) R[d] = s_xf[d];
+    double *row = s_sol + s * SOLROW;
+    double y[3];
+    rot_vec(R, p.dtab + tm0[SLVGPU_M_O_RDMA] + s * 3, y);
+    row[0] = y[0] + s_xf[9]; row[1] = y[1] + s_xf[10]; row[2] = y[2] + s_xf[11];
+    double m[20];
+    rot_mom20(R, p.dtab + p.sol_meta[SLVGPU_S_SMEA] + s * 20, m); fold20(m);
+#pragma unroll
+    for (int k = 0; k < 20; ++k) row[3 + k] = m[k];
+    rot_mom20(R, p.dtab + p.sol_meta[SLVGPU_S_SEA] + s * 20, m); fold20(m);
+#pragma unroll
+    for (int k = 0; k < 20; ++k) row[23 + k] = m[k];
+    rot_vec(R, p.dtab + p.sol_meta[SLVGPU_S_CMEA] + s * 3, y);
+    row[43] = y[0]; row[44] = y[1]; row[45] = y[2];
+    rot_vec(R, p.dtab + p.sol_meta[SLVGPU_S_CEA] + s * 3, y);
+    row[46] = y[0]; row[47] = y[1]; row[48] = y[2];
+  }
+  __syncthreads();
+
+  const double cx = s_xf[13], cy = s_xf[14], cz = s_xf[15];
+  double e_mea = 0.0, e_ea = 0.0, c_mea = 0.0, c_ea = 0.0, rms_sum = 0.0, rms_max = 0.0;
+  int n_c = 0, n_p = 0, n_e = 0;
+  const int nsolv = p.ninst - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int base = 0; base < nsolv; base += blockDim.x) {
+    const int i = base + threadIdx.x + 1;                // instance index
+    int flag = 0;
+    double rot[9], tr[3], rms = 0.0;
+    if (i < p.ninst) {
+      const int a0 = p.inst_atom0[i], nat = p.inst_atom0[i + 1] - a0;
+      const double *xi = x + (size_t)a0 * 3;
+      double mx = 0, my = 0, mz = 0;
+      for (int k = 0; k < nat; ++k) { mx += xi[k * 3]; my += xi[k * 3 + 1]; mz += xi[k * 3 + 2]; }
+      const double dn = (double)nat;
+      mx /= dn; my /= dn; mz /= dn;
+      const double dx = cx - mx, dy = cy - my, dz = cz - mz;
+      const double rr = sqrt(dx * dx + dy * dy + dz * dz);
+      flag = (rr < p.ccut ? 4 : 0) | (rr < p.pcut ? 1 : 0) | (rr < p.ecut ? 2 : 0);
+      if (flag) {
+        const int *tm = tmeta(p, p.inst_type[i]);
+        fit_instance(p, tm, xi, rot, tr, rms);
+        if (flag & 4) {
+          ++n_c; rms_sum += rms; rms_max = fmax(rms_max, rms);
+          if (p.flags & SLVGPU_ELECT) {
+            const int nd = tm[SLVGPU_M_NDMA];
+            const double *rd = p.dtab + tm[SLVGPU_M_O_RDMA], *mom = p.dtab + tm[SLVGPU_M_O_MOM];
+            for (int s = 0; s < nd; ++s) {
+              double rB[3], mB[20];
+              rot_vec(rot, rd + s * 3, rB);
+              rB[0] += tr[0]; rB[1] += tr[1]; rB[2] += tr[2];
+              rot_mom20(rot, mom + s * 20, mB);
+              for (int a = 0; a < ndmac; ++a) {
+                const double *row = s_sol + a * SOLROW;
+                double P[23];
+                pair_potentials(row, rB, mB, P);
+                double e1 = 0.0, e2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 20; ++k) { e1 += row[3 + k] * P[k]; e2 += row[23 + k] * P[k]; }
+                e_mea += e1; e_ea += e2;
+                c_mea += row[43] * P[20] + row[44] * P[21] + row[45] * P[22];
+                c_ea += row[46] * P[20] + row[47] * P[21] + row[48] * P[22];
+              }
+            }
+          }
+        }
+        if (flag & 1) ++n_p;
+        if (flag & 2) ++n_e;
+      }
+    }
+    // ordered compaction of the instances the later kernels need (inside pcut or ecut)
+    const int keep = (flag & 3) != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_cnt[w];
+    off += __popc(bal & ((1u << lane) - 1u));
+    if (keep && off < p.list_cap) {
+      const size_t e = (size_t)fi * p.list_cap + off;
+      fl.list_inst[e] = i; fl.list_flag[e] = flag & 3;
+      double *xf = fl.list_xf + e * 12;
+#pragma unroll
+      for (int d = 0; d < 9; ++d) xf[d] = rot[d];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) xf[9 + d] = tr[d];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_cnt[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+
+  e_mea = block_sum(e_mea, s_red); e_ea = block_sum(e_ea, s_red);
+  c_mea = block_sum(c_mea, s_red); c_ea = block_sum(c_ea, s_red);
+  rms_sum = block_sum(rms_sum, s_red); rms_max = block_max(rms_max, s_red);
+  const double dn_c = block_sum((double)n_c, s_red), dn_p = block_sum((double)n_p, s_red), dn_e = block_sum((double)n_e, s_red);
+  if (threadIdx.x == 0) {
+    double *o = out + (size_t)(frame0 + fi) * SLVGPU_NOUT;
+    const bool el = (p.flags & SLVGPU_ELECT) != 0;
+    o[SLVGPU_ELE_MEA] = el ? e_mea : 0.0;
+    o[SLVGPU_ELE_EA] = (el && (p.flags & SLVGPU_EA)) ? e_ea : 0.0;
+    o[SLVGPU_COR_MEA] = (el && (p.flags & SLVGPU_CORR)) ? c_mea : 0.0;
+    o[SLVGPU_COR_EA] = (el && (p.flags & SLVGPU_CORR)) ? c_ea : 0.0;
+    o[SLVGPU_POL_MEA] = 0.0; o[SLVGPU_REP_MEA] = 0.0; o[SLVGPU_DIS_MEA] = 0.0; o[SLVGPU_DIS_ISO] = 0.0;
+    o[SLVGPU_RMS_C] = s_xf[12];
+    o[SLVGPU_RMS_SMAX] = rms_max;
+    o[SLVGPU_RMS_AVE] = (s_xf[12] + rms_sum) / (dn_c + 1.0);
+    o[SLVGPU_N_ELECT] = dn_c; o[SLVGPU_N_POL] = dn_p; o[SLVGPU_N_REP] = dn_e;
+    o[SLVGPU_POL_ITERS] = 0.0; o[SLVGPU_POL_RESID] = 0.0;
+    fl.nlist[fi] = s_base < p.list_cap ? s_base : p.list_cap;
+  }
+}
+
+}  // namespace slv

@@ -1,0 +1,295 @@
+// k_pol.cuh -- kernel C: polarisation (induced-dipole) frequency shift.  Persistent CTAs, one MD frame at
+// a time per CTA, scratch tables in an L2-resident per-CTA workspace.
+//
+// Reference: SFTPLI + FFFFFF + AAAAAA (solvshift/src/solpol2.f:118-239, 1270-1511, 242-1150) build the dense
+// matrix D (alpha^-1 blocks, dipole tensor T between centres of different molecules), invert it by LU and do
+// two NDIM^3 DGEMMs per normal mode.  Algebraically, with x = D^-1 F and y = D^-T F,
+//      SHIFT = -1/2 [ y^T dD x - (x + y) . dF ],   dD = sum_m g_m dD_m,  dF = sum_m g_m dF_m,
+// where dD has entries only in the solute rows/columns and dF is a sum over (solute, solvent) pairs, both
+// linear in the mode-derivative parameters -- which the plan pre-contracts.  So the work is: the fields F,
+// two linear solves, and O(N) pair contractions.  The solves are matrix-free block-Jacobi sweeps
+//      x <- alpha (F - T x),   y <- alpha^T (F - T y)
+// that share every T_ij evaluation; T is rebuilt from the centre coordinates each sweep (no N^2 storage).
+// The reference's quirks are reproduced: octupole field prefactor 5 in F (solpol2.f:1425), 1/2 on the
+// solute-solvent dT blocks (699-706), the SUM2 slip in the field derivatives (466-483, 959-976).
+#pragma once
+#include "slv_common.cuh"
+
+namespace slv {
+
+constexpr int POL_THREADS = 512;
+constexpr int POL_TILE = 128;
+constexpr int SITE_ROW = 24;     // pos3, mom20, molecule id
+
+struct PolWork {                 // per-CTA workspace (device pointers already offset per CTA by the kernel)
+  double *cent_pos;   // [cent_cap][3]
+  double *cent_alpha; // [cent_cap][9]
+  double *fld;        // [cent_cap][3]
+  double *xy;         // [2 buffers][cent_cap][6]  x(3), y(3)
+  double *site;       // [site_cap][SITE_ROW]
+  int *cent_mol;      // [cent_cap]
+  int *ent_coff;      // [list_cap] first centre of a list entry
+  int *ent_soff;      // [list_cap] first site of a list entry
+};
+
+__global__ void __launch_bounds__(POL_THREADS)
+k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, double *__restrict__ out, int *__restrict__ status,
+      double *__restrict__ detail /* optional [nframes][cent_cap][9]: dipind, flds, rpol */) {
+  __shared__ double s_red[32];
+  __shared__ double s_tile[POL_TILE * 10];
+  __shared__ int s_tmol[POL_TILE];
+  __shared__ int s_n[4];
+  extern __shared__ double sm[];    // solute tables for the contraction phase
+
+  PolWork wk = wk0;
+  {
+    const size_t cb = blockIdx.x;
+    const size_t cc = (size_t)p.cent_cap;
+    wk.cent_pos += cb * cc * 3; wk.cent_alpha += cb * cc * 9; wk.fld += cb * cc * 3; wk.xy += cb * cc * 12;
+    wk.site += cb * (size_t)p.site_cap * SITE_ROW; wk.cent_mol += cb * cc;
+    wk.ent_coff += cb * (size_t)p.list_cap; wk.ent_soff += cb * (size_t)p.list_cap;
+  }
+  const int *tm0 = tmeta(p, p.inst_type[0]);
+  const int npolc = tm0[SLVGPU_M_NPOL], ndmac = tm0[SLVGPU_M_NDMA];
+  const int tid = threadIdx.x, NT = blockDim.x;
+
+  for (int fi = blockIdx.x; fi < nframes; fi += gridDim.x) {
+    const int nl = fl.nlist[fi];
+    const size_t lbase = (size_t)fi * p.list_cap;
+    // ---- (a) offsets of every pol-layer entry, then the lab-frame centre and site tables
+    if (tid == 0) {
+      int nc = npolc, ns = ndmac;
+      for (int e = 0; e < nl; ++e) {
+        wk.ent_coff[e] = nc; wk.ent_soff[e] = ns;
+        if (fl.list_flag[lbase + e] & 1) {
+          const int *tm = tmeta(p, p.inst_type[fl.list_inst[lbase + e]]);
+          nc += tm[SLVGPU_M_NPOL]; ns += tm[SLVGPU_M_NDMA];
+        }
+      }
+      s_n[0] = nc; s_n[1] = ns;
+    }
+    __syncthreads();
+    const int ncent = s_n[0], nsite = s_n[1];
+    if (ncent > p.cent_cap || nsite > p.site_cap || ncent == npolc) {
+      if (tid == 0 && ncent != npolc) status[frame0 + fi] |= SLVGPU_ST_OVERFLOW;
+      __syncthreads();
+      continue;
+    }
+    for (int e = tid - 1; e < nl; e += NT) {          // e == -1 is the solute
+      const int *tm; double R[9], t[3]; int c0, s0, mol;
+      if (e < 0) {
+        tm = tm0; const double *sx = fl.sol_xf + (size_t)fi * 12;
+        for (int d = 0; d < 9; ++d) R[d] = sx[d];
+        for (int d = 0; d < 3; ++d) t[d] = sx[9 + d];
+        c0 = 0; s0 = 0; mol = 0;
+      } else {
+        if (!(fl.list_flag[lbase + e] & 1)) continue;
+        tm = tmeta(p, p.inst_type[fl.list_inst[lbase + e]]);
+        const double *xf = fl.list_xf + (lbase + e) * 12;
+        for (int d = 0; d < 9; ++d) R[d] = xf[d];
+        for (int d = 0; d < 3; ++d) t[d] = xf[9 + d];
+        c0 = wk.ent_coff[e]; s0 = wk.ent_soff[e]; mol = e + 1;
+      }
+      const int np_ = tm[SLVGPU_M_NPOL], nd = tm[SLVGPU_M_NDMA];
+      for (int l = 0; l < np_; ++l) {
+        double y[3], a[9];
+        rot_vec(R, p.dtab + tm[SLVGPU_M_O_RPOL] + l * 3, y);
+        rot_mat(R, p.dtab + tm[SLVGPU_M_O_POL] + l * 9, a);
+        for (int d = 0; d < 3; ++d) wk.cent_pos[(size_t)(c0 + l) * 3 + d] = y[d] + t[d];
+        for (int d = 0; d < 9; ++d) wk.cent_alpha[(size_t)(c0 + l) * 9 + d] = a[d];
+        wk.cent_mol[c0 + l] = mol;
+      }
+      for (int s = 0; s < nd; ++s) {
+        double y[3], m[20];
+        rot_vec(R, p.dtab + tm[SLVGPU_M_O_RDMA] + s * 3, y);
+        rot_mom20(R, p.dtab + tm[SLVGPU_M_O_MOM] + s * 20, m);
+        double *row = wk.site + (size_t)(s0 + s) * SITE_ROW;
+        for (int d = 0; d < 3; ++d) row[d] = y[d] + t[d];
+        for (int d = 0; d < 20; ++d) row[3 + d] = m[d];
+        row[23] = (double)mol;
+      }
+    }
+    __syncthreads();
+
+    // ---- (b) fields at every centre from the multipoles of all OTHER molecules (FFFFFF)
+    for (int c = tid; c < ncent; c += NT) {
+      const double rc[3] = {wk.cent_pos[(size_t)c * 3], wk.cent_pos[(size_t)c * 3 + 1], wk.cent_pos[(size_t)c * 3 + 2]};
+      const int mc = wk.cent_mol[c];
+      double F[3] = {0, 0, 0};
+      for (int s = 0; s < nsite; ++s) {
+        const double *row = wk.site + (size_t)s * SITE_ROW;
+        if ((int)row[23] == mc) continue;
+        const double R[3] = {rc[0] - row[0], rc[1] - row[1], rc[2] - row[2]};
+        site_field(R, row + 3, 5.0, F);
+      }
+      const double *a = wk.cent_alpha + (size_t)c * 9;
+      wk.fld[(size_t)c * 3] = F[0]; wk.fld[(size_t)c * 3 + 1] = F[1]; wk.fld[(size_t)c * 3 + 2] = F[2];
+      double *v = wk.xy + (size_t)c * 6;               // buffer 0: x0 = alpha F, y0 = alpha^T F
+      for (int i = 0; i < 3; ++i) {
+        v[i] = a[i * 3] * F[0] + a[i * 3 + 1] * F[1] + a[i * 3 + 2] * F[2];
+        v[3 + i] = a[i] * F[0] + a[3 + i] * F[1] + a[6 + i] * F[2];
+      }
+    }
+    __syncthreads();
+
+    // ---- (c) block-Jacobi sweeps for x and y together
+    int cur = 0, iters = 0;
+    double resid = 1.0;
+    const size_t bstride = (size_t)p.cent_cap * 6;
+    for (; iters < p.pol_maxit; ++iters) {
+      const double *vin = wk.xy + cur * bstride;
+      double *vout = wk.xy + (cur ^ 1) * bstride;
+      double dmax = 0.0, vmax = 0.0;
+      for (int c0 = 0; c0 < ncent; c0 += NT) {
+        const int c = c0 + tid;
+        const bool act = c < ncent;
+        double rc[3] = {0, 0, 0}; int mc = -1;
+        if (act) { rc[0] = wk.cent_pos[(size_t)c * 3]; rc[1] = wk.cent_pos[(size_t)c * 3 + 1]; rc[2] = wk.cent_pos[(size_t)c * 3 + 2]; mc = wk.cent_mol[c]; }
+        double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0};
+        for (int j0 = 0; j0 < ncent; j0 += POL_TILE) {
+          __syncthreads();
+          if (tid < POL_TILE) {
+            const int j = j0 + tid;
+            if (j < ncent) {
+              double *tt = s_tile + tid * 10;
+              tt[0] = wk.cent_pos[(size_t)j * 3]; tt[1] = wk.cent_pos[(size_t)j * 3 + 1]; tt[2] = wk.cent_pos[(size_t)j * 3 + 2];
+              const double *vj = vin + (size_t)j * 6;
+              for (int d = 0; d < 6; ++d) tt[3 + d] = vj[d];
+              s_tmol[tid] = wk.cent_mol[j];
+            } else s_tmol[tid] = -2;
+          }
+          __syncthreads();
+          if (act) {
+            const int jn = min(POL_TILE, ncent - j0);
+            for (int jj = 0; jj < jn; ++jj) {
+              if (s_tmol[jj] == mc) continue;
+              const double *tt = s_tile + jj * 10;
+              const double Rx = rc[0] - tt[0], Ry = rc[1] - tt[1], Rz = rc[2] - tt[2];
+              const double r2 = Rx * Rx + Ry * Ry + Rz * Rz;
+              const double u = rsqrt64(r2), u2 = u * u, u3 = u2 * u, t5 = 3.0 * u3 * u2;
+              const double Rxj = Rx * tt[3] + Ry * tt[4] + Rz * tt[5];
+              const double Ryj = Rx * tt[6] + Ry * tt[7] + Rz * tt[8];
+              const double fx = t5 * Rxj, fy = t5 * Ryj;
+              ax[0] += u3 * tt[3] - fx * Rx; ax[1] += u3 * tt[4] - fx * Ry; ax[2] += u3 * tt[5] - fx * Rz;
+              ay[0] += u3 * tt[6] - fy * Rx; ay[1] += u3 * tt[7] - fy * Ry; ay[2] += u3 * tt[8] - fy * Rz;
+            }
+          }
+        }
+        if (act) {
+          const double *a = wk.cent_alpha + (size_t)c * 9;
+          const double *F = wk.fld + (size_t)c * 3;
+          const double bx[3] = {F[0] - ax[0], F[1] - ax[1], F[2] - ax[2]}, by[3] = {F[0] - ay[0], F[1] - ay[1], F[2] - ay[2]};
+          const double *vo = vin + (size_t)c * 6;
+          double *vn = vout + (size_t)c * 6;
+          for (int i = 0; i < 3; ++i) {
+            const double xn = a[i * 3] * bx[0] + a[i * 3 + 1] * bx[1] + a[i * 3 + 2] * bx[2];
+            const double yn = a[i] * by[0] + a[3 + i] * by[1] + a[6 + i] * by[2];
+            dmax = fmax(dmax, fmax(fabs(xn - vo[i]), fabs(yn - vo[3 + i])));
+            vmax = fmax(vmax, fmax(fabs(xn), fabs(yn)));
+            vn[i] = xn; vn[3 + i] = yn;
+          }
+        }
+      }
+      dmax = block_max(dmax, s_red);
+      vmax = block_max(vmax, s_red);
+      cur ^= 1;
+      resid = vmax > 0.0 ? dmax / vmax : 0.0;
+      if (!(resid > p.pol_tol)) { ++iters; break; }
+    }
+    __syncthreads();
+    const double *vxy = wk.xy + cur * bstride;
+
+    // ---- (d) contractions with the solute rows: y^T dD x - (x+y).dF
+    // solute tables in shared memory: centres [npolc][21]: pos3 r1(3) G(9) x3 y3 ; sites [ndmac][46]: pos3 mom20 dma1(20) L3
+    double *s_c = sm, *s_s = sm + (size_t)npolc * 21;
+    {
+      const double *sx = fl.sol_xf + (size_t)fi * 12;
+      double R[9];
+      for (int d = 0; d < 9; ++d) R[d] = sx[d];
+      for (int i = tid; i < npolc; i += NT) {
+        double *row = s_c + (size_t)i * 21;
+        for (int d = 0; d < 3; ++d) row[d] = wk.cent_pos[(size_t)i * 3 + d];
+        rot_vec(R, p.dtab + p.sol_meta[SLVGPU_S_LMOC1] + i * 3, row + 3);
+        rot_mat(R, p.dtab + p.sol_meta[SLVGPU_S_DPOL1] + i * 9, row + 6);
+        for (int d = 0; d < 6; ++d) row[15 + d] = vxy[(size_t)i * 6 + d];
+      }
+      for (int a = tid; a < ndmac; a += NT) {
+        double *row = s_s + (size_t)a * 46;
+        const double *src = wk.site + (size_t)a * SITE_ROW;
+        for (int d = 0; d < 23; ++d) row[d] = src[d];
+        rot_mom20(R, p.dtab + p.sol_meta[SLVGPU_S_DMA1] + a * 20, row + 23);
+        rot_vec(R, p.dtab + p.sol_meta[SLVGPU_S_LVEC] + a * 3, row + 43);
+      }
+    }
+    __syncthreads();
+    double acc = 0.0;
+    // term A: solute diagonal blocks  y_i^T G_i x_i,  G = -alpha^-1 (sum_m g_m alpha1_m) alpha^-1
+    for (int i = tid; i < npolc; i += NT) {
+      const double *row = s_c + (size_t)i * 21, *G = row + 6, *xi = row + 15, *yi = row + 18;
+      for (int a = 0; a < 3; ++a) acc += yi[a] * (G[a * 3] * xi[0] + G[a * 3 + 1] * xi[1] + G[a * 3 + 2] * xi[2]);
+    }
+    // terms B and C2: one thread per solvent centre j
+    for (int j = npolc + tid; j < ncent; j += NT) {
+      const double rj[3] = {wk.cent_pos[(size_t)j * 3], wk.cent_pos[(size_t)j * 3 + 1], wk.cent_pos[(size_t)j * 3 + 2]};
+      const double *vj = vxy + (size_t)j * 6;
+      const double xj[3] = {vj[0], vj[1], vj[2]}, yj[3] = {vj[3], vj[4], vj[5]};
+      for (int i = 0; i < npolc; ++i) {
+        const double *row = s_c + (size_t)i * 21, *r1 = row + 3, *xi = row + 15, *yi = row + 18;
+        const double R[3] = {row[0] - rj[0], row[1] - rj[1], row[2] - rj[2]};
+        const double r2 = R[0] * R[0] + R[1] * R[1] + R[2] * R[2];
+        const double u = rsqrt64(r2), u2 = u * u, u5 = u2 * u2 * u;
+        const double R1R = R[0] * r1[0] + R[1] * r1[1] + R[2] * r1[2];
+        const double Ryi = R[0] * yi[0] + R[1] * yi[1] + R[2] * yi[2], Rxj = R[0] * xj[0] + R[1] * xj[1] + R[2] * xj[2];
+        const double Ryj = R[0] * yj[0] + R[1] * yj[1] + R[2] * yj[2], Rxi = R[0] * xi[0] + R[1] * xi[1] + R[2] * xi[2];
+        const double yixj = yi[0] * xj[0] + yi[1] * xj[1] + yi[2] * xj[2], yjxi = yj[0] * xi[0] + yj[1] * xi[1] + yj[2] * xi[2];
+        const double r1xj = r1[0] * xj[0] + r1[1] * xj[1] + r1[2] * xj[2], r1yi = r1[0] * yi[0] + r1[1] * yi[1] + r1[2] * yi[2];
+        const double r1xi = r1[0] * xi[0] + r1[1] * xi[1] + r1[2] * xi[2], r1yj = r1[0] * yj[0] + r1[1] * yj[1] + r1[2] * yj[2];
+        const double b1 = R1R * (yixj - 5.0 * u2 * Ryi * Rxj) + Ryi * r1xj + r1yi * Rxj;
+        const double b2 = R1R * (yjxi - 5.0 * u2 * Ryj * Rxi) + Ryj * r1xi + r1yj * Rxi;
+        acc += -1.5 * u5 * (b1 + b2);
+      }
+      double dF[3] = {0, 0, 0};
+      for (int a = 0; a < ndmac; ++a) {
+        const double *row = s_s + (size_t)a * 46;
+        const double R[3] = {rj[0] - row[0], rj[1] - row[1], rj[2] - row[2]};
+        site_field(R, row + 23, 7.0, dF);
+        site_dfield(R, row + 43, row + 3, -1.0, dF);
+      }
+      acc -= (xj[0] + yj[0]) * dF[0] + (xj[1] + yj[1]) * dF[1] + (xj[2] + yj[2]) * dF[2];
+    }
+    // term C1: one thread per solvent site s, field derivative at the solute centres moving by r1
+    for (int s = ndmac + tid; s < nsite; s += NT) {
+      const double *srow = wk.site + (size_t)s * SITE_ROW;
+      double m[20];
+      for (int d = 0; d < 20; ++d) m[d] = srow[3 + d];
+      const double rs[3] = {srow[0], srow[1], srow[2]};
+      for (int i = 0; i < npolc; ++i) {
+        const double *row = s_c + (size_t)i * 21;
+        const double R[3] = {row[0] - rs[0], row[1] - rs[1], row[2] - rs[2]};
+        double dF[3] = {0, 0, 0};
+        site_dfield(R, row + 3, m, 1.0, dF);
+        acc -= (row[15] + row[18]) * dF[0] + (row[16] + row[19]) * dF[1] + (row[17] + row[20]) * dF[2];
+      }
+    }
+    acc = block_sum(acc, s_red);
+    if (tid == 0) {
+      double *o = out + (size_t)(frame0 + fi) * SLVGPU_NOUT;
+      o[SLVGPU_POL_MEA] = -0.5 * acc;
+      o[SLVGPU_POL_ITERS] = (double)iters;
+      o[SLVGPU_POL_RESID] = resid;
+      if (resid > p.pol_tol) status[frame0 + fi] |= SLVGPU_ST_POL_NOCONV;
+    }
+    if (detail) {
+      double *dd = detail + (size_t)fi * p.cent_cap * 9;
+      for (int c = tid; c < ncent; c += NT)
+        for (int d = 0; d < 3; ++d) {
+          dd[(size_t)c * 9 + d] = vxy[(size_t)c * 6 + d];
+          dd[(size_t)c * 9 + 3 + d] = wk.fld[(size_t)c * 3 + d];
+          dd[(size_t)c * 9 + 6 + d] = wk.cent_pos[(size_t)c * 3 + d];
+        }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace slv

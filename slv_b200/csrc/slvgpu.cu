@@ -1,0 +1,384 @@
+// slvgpu.cu -- C ABI (include/slvgpu.h) over the sm_100a kernels of the SolEFP frequency-shift path.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC slvgpu.cu -o libslvgpu.so
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/slvgpu.h"
+#include "k_disp.cuh"
+#include "k_elect.cuh"
+#include "k_pol.cuh"
+#include "k_rep.cuh"
+#include "k_util.cuh"
+
+using namespace slv;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(SLVGPU_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));               \
+  } while (0)
+
+struct slvgpu_plan {
+  DevPlan dp;
+  int max_chunk = 0, sm_count = 0, pol_ctas = 0, rep_ctas = 0;
+  int ndmac = 0, npolc = 0, nmosc = 0, nbasc = 0, natc = 0;
+  int max_nmos = 0, max_nbas = 0, max_nat = 0;
+  std::vector<void *> allocs;
+  FrameLists fl{};
+  PolWork pw{};
+  RepWork rw{};
+  double *d_detail = nullptr;
+  int detail_frames = 0;
+  int want_detail = 0;
+  double *d_stage_coords = nullptr, *d_stage_out = nullptr; int *d_stage_status = nullptr;
+  int64_t stage_frames = 0;
+  int64_t last_launches = 0;
+  cudaStream_t own_stream = nullptr;
+};
+
+template <class T>
+static int dalloc(slvgpu_plan *pl, T **ptr, size_t n) {
+  void *q = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  if (e != cudaSuccess) return fail(SLVGPU_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  pl->allocs.push_back(q);
+  *ptr = (T *)q;
+  return 0;
+}
+template <class T>
+static int upload(slvgpu_plan *pl, const T **dptr, const T *h, size_t n) {
+  T *q = nullptr;
+  int rc = dalloc(pl, &q, n);
+  if (rc) return rc;
+  if (n) CK(cudaMemcpy(q, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  *dptr = q;
+  return 0;
+}
+
+extern "C" const char *slvgpu_last_error(void) { return g_err.c_str(); }
+extern "C" const char *slvgpu_version(void) { return "slvgpu 0.1 (sm_100a)"; }
+
+extern "C" void slvgpu_plan_destroy(slvgpu_plan *pl) {
+  if (!pl) return;
+  for (void *q : pl->allocs) cudaFree(q);
+  if (pl->d_stage_coords) cudaFree(pl->d_stage_coords);
+  if (pl->d_stage_out) cudaFree(pl->d_stage_out);
+  if (pl->d_stage_status) cudaFree(pl->d_stage_status);
+  if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
+  delete pl;
+}
+
+extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) {
+  if (!d || !out) return fail(SLVGPU_EINVAL, "null argument");
+  if (d->ntypes < 1 || d->ninst < 1 || d->natoms_total < 1) return fail(SLVGPU_EINVAL, "empty plan");
+  if (!d->type_meta || !d->sol_meta || !d->itab || !d->dtab || !d->inst_type || !d->inst_atom0)
+    return fail(SLVGPU_EINVAL, "null table pointer");
+  for (int i = 0; i < d->ninst; ++i)
+    if (d->inst_type[i] < 0 || d->inst_type[i] >= d->ntypes) return fail(SLVGPU_EINVAL, "instance type out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SLVGPU_ECUDA, "no CUDA device: this library has no CPU path");
+  slvgpu_plan *pl = new slvgpu_plan();
+  DevPlan &p = pl->dp;
+  memset(&p, 0, sizeof(p));
+  p.ntypes = d->ntypes; p.ninst = d->ninst; p.natoms_total = d->natoms_total; p.flags = d->flags;
+  p.ccut = d->ccut; p.pcut = d->pcut; p.ecut = d->ecut;
+  p.pol_maxit = d->pol_maxit > 0 ? d->pol_maxit : 200;
+  p.pol_tol = d->pol_tol > 0 ? d->pol_tol : 1e-13;
+  int rc = 0;
+#define TRY(x) do { rc = (x); if (rc) { slvgpu_plan_destroy(pl); return rc; } } while (0)
+  TRY(upload(pl, &p.type_meta, d->type_meta, (size_t)d->ntypes * SLVGPU_NMETA));
+  TRY(upload(pl, &p.sol_meta, d->sol_meta, (size_t)SLVGPU_NSOL));
+  TRY(upload(pl, &p.itab, d->itab, (size_t)d->n_itab));
+  TRY(upload(pl, &p.dtab, d->dtab, (size_t)d->n_dtab));
+  TRY(upload(pl, &p.inst_type, d->inst_type, (size_t)d->ninst));
+  TRY(upload(pl, &p.inst_atom0, d->inst_atom0, (size_t)d->ninst + 1));
+  // Gauss-Legendre weights of the imaginary-frequency quadrature (solvshift/slvpar.py:1000-1019), v = 0.3
+  {
+    static const double w12[12] = {0.0471753363865118, 0.1069393259953184, 0.1600783285433462, 0.2031674267230659,
+                                   0.2334925365383548, 0.2491470458134028, 0.2491470458134028, 0.2334925365383548,
+                                   0.2031674267230659, 0.1600783285433462, 0.1069393259953184, 0.0471753363865118};
+    static const double t12[12] = {-0.9815606342467192, -0.9041172563704749, -0.7699026741943047, -0.5873179542866175,
+                                   -0.3678314989981802, -0.1252334085114689, 0.1252334085114689, 0.3678314989981802,
+                                   0.5873179542866175, 0.7699026741943047, 0.9041172563704749, 0.9815606342467192};
+    for (int k = 0; k < 12; ++k) p.glw[k] = 2.0 * 0.3 * w12[k] / ((1.0 - t12[k]) * (1.0 - t12[k]));
+  }
+  // sizes
+  long tot_npol = 0, tot_ndma = 0;
+  p.max_npol = 0; p.max_ndma = 0;
+  for (int t = 0; t < d->ntypes; ++t) {
+    const int32_t *tm = d->type_meta + (size_t)t * SLVGPU_NMETA;
+    if (tm[SLVGPU_M_NPOL] > p.max_npol) p.max_npol = tm[SLVGPU_M_NPOL];
+    if (tm[SLVGPU_M_NDMA] > p.max_ndma) p.max_ndma = tm[SLVGPU_M_NDMA];
+    if (tm[SLVGPU_M_NMOS] > pl->max_nmos) pl->max_nmos = tm[SLVGPU_M_NMOS];
+    if (tm[SLVGPU_M_NBASIS] > pl->max_nbas) pl->max_nbas = tm[SLVGPU_M_NBASIS];
+    if (tm[SLVGPU_M_NATOMS] > pl->max_nat) pl->max_nat = tm[SLVGPU_M_NATOMS];
+  }
+  for (int i = 0; i < d->ninst; ++i) {
+    const int32_t *tm = d->type_meta + (size_t)d->inst_type[i] * SLVGPU_NMETA;
+    tot_npol += tm[SLVGPU_M_NPOL]; tot_ndma += tm[SLVGPU_M_NDMA];
+  }
+  const int32_t *tm0 = d->type_meta + (size_t)d->inst_type[0] * SLVGPU_NMETA;
+  pl->ndmac = tm0[SLVGPU_M_NDMA]; pl->npolc = tm0[SLVGPU_M_NPOL]; pl->nmosc = tm0[SLVGPU_M_NMOS];
+  pl->nbasc = tm0[SLVGPU_M_NBASIS]; pl->natc = tm0[SLVGPU_M_NATOMS];
+  if ((d->flags & SLVGPU_POL) && pl->ndmac != pl->natc) {
+    slvgpu_plan_destroy(pl);
+    return fail(SLVGPU_EINVAL, "polarisation shift needs ndma == natoms on the solute (solpol2.f:738-741, 873-876)");
+  }
+  p.list_cap = d->ninst > 1 ? d->ninst - 1 : 1;
+  p.cent_cap = (int)tot_npol; p.site_cap = (int)tot_ndma;
+  if (d->pol_cent_cap > 0 && d->pol_cent_cap < p.cent_cap) {
+    p.cent_cap = d->pol_cent_cap > pl->npolc ? d->pol_cent_cap : pl->npolc + 1;
+    // sites scale with centres through the fragment types; bound by the worst ratio
+    double ratio = 1.0;
+    for (int t = 0; t < d->ntypes; ++t) {
+      const int32_t *tm = d->type_meta + (size_t)t * SLVGPU_NMETA;
+      if (tm[SLVGPU_M_NPOL] > 0) ratio = fmax(ratio, (double)tm[SLVGPU_M_NDMA] / tm[SLVGPU_M_NPOL]);
+    }
+    long sc = (long)(p.cent_cap * ratio) + pl->ndmac + 8;
+    p.site_cap = (int)(sc < tot_ndma ? sc : tot_ndma);
+  }
+  cudaDeviceProp prop;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaGetDeviceProperties(&prop, dev);
+  pl->sm_count = prop.multiProcessorCount;
+  pl->max_chunk = d->max_chunk > 0 ? d->max_chunk : 1024;
+  pl->want_detail = d->want_detail;
+  const size_t ch = (size_t)pl->max_chunk;
+  TRY(dalloc(pl, &pl->fl.sol_xf, ch * 12));
+  TRY(dalloc(pl, &pl->fl.nlist, ch));
+  TRY(dalloc(pl, &pl->fl.list_inst, ch * p.list_cap));
+  TRY(dalloc(pl, &pl->fl.list_flag, ch * p.list_cap));
+  TRY(dalloc(pl, &pl->fl.list_xf, ch * p.list_cap * 12));
+  if (d->flags & SLVGPU_POL) {
+    pl->pol_ctas = pl->sm_count;        // one persistent CTA per SM (512 threads, ~6 KB static smem + solute tables)
+    const size_t nc = (size_t)pl->pol_ctas, cc = (size_t)p.cent_cap;
+    TRY(dalloc(pl, &pl->pw.cent_pos, nc * cc * 3));
+    TRY(dalloc(pl, &pl->pw.cent_alpha, nc * cc * 9));
+    TRY(dalloc(pl, &pl->pw.fld, nc * cc * 3));
+    TRY(dalloc(pl, &pl->pw.xy, nc * cc * 12));
+    TRY(dalloc(pl, &pl->pw.site, nc * (size_t)p.site_cap * SITE_ROW));
+    TRY(dalloc(pl, &pl->pw.cent_mol, nc * cc));
+    TRY(dalloc(pl, &pl->pw.ent_coff, nc * (size_t)p.list_cap));
+    TRY(dalloc(pl, &pl->pw.ent_soff, nc * (size_t)p.list_cap));
+    if (pl->want_detail) {
+      pl->detail_frames = pl->max_chunk;
+      TRY(dalloc(pl, &pl->d_detail, (size_t)pl->detail_frames * cc * 9));
+    }
+  }
+  if (d->flags & SLVGPU_REP) TRY(rep_alloc(pl->rw, pl->allocs, g_err, pl->sm_count, pl->nmosc, pl->nbasc, pl->max_nmos, pl->max_nbas, &pl->rep_ctas));
+#undef TRY
+  // opt in to large dynamic shared memory where needed
+  cudaFuncSetAttribute(k_frame_elect, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_disp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_pol, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_rep, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  *out = pl;
+  return 0;
+}
+
+__global__ void k_status(const double *__restrict__ out, int *__restrict__ status, int64_t n) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const double *o = out + f * SLVGPU_NOUT;
+  bool bad = false;
+  for (int k = 0; k < 8; ++k) bad |= !isfinite(o[k]);
+  if (bad) status[f] |= SLVGPU_ST_NONFINITE;
+}
+
+extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64_t nframes, double *d_out,
+                                  int32_t *d_status, void *stream_) {
+  if (!pl || !d_coords || !d_out || !d_status) return fail(SLVGPU_EINVAL, "null argument");
+  if (nframes < 0) return fail(SLVGPU_EINVAL, "negative frame count");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const DevPlan &p = pl->dp;
+  pl->last_launches = 0;
+  if (nframes == 0) return 0;
+  CK(cudaMemsetAsync(d_status, 0, (size_t)nframes * sizeof(int32_t), st));
+  const size_t sm_el = (size_t)pl->ndmac * SOLROW * sizeof(double);
+  const size_t sm_di = ((size_t)pl->npolc * DISP_SOLROW + 108 * DISP_THREADS) * sizeof(double);
+  const size_t sm_po = ((size_t)pl->npolc * 21 + (size_t)pl->ndmac * 46) * sizeof(double);
+  for (int64_t f0 = 0; f0 < nframes; f0 += pl->max_chunk) {
+    const int nf = (int)((nframes - f0) < pl->max_chunk ? (nframes - f0) : pl->max_chunk);
+    k_frame_elect<<<nf, ELECT_THREADS, sm_el, st>>>(p, d_coords, (int)f0, pl->fl, d_out);
+    ++pl->last_launches;
+    if ((p.flags & SLVGPU_DISP) && p.ninst > 1) {
+      k_disp<<<nf, DISP_THREADS, sm_di, st>>>(p, (int)f0, pl->fl, d_out);
+      ++pl->last_launches;
+    }
+    if ((p.flags & SLVGPU_POL) && p.ninst > 1) {
+      const int g = nf < pl->pol_ctas ? nf : pl->pol_ctas;
+      k_pol<<<g, POL_THREADS, sm_po, st>>>(p, (int)f0, nf, pl->fl, pl->pw, d_out, d_status, pl->d_detail);
+      ++pl->last_launches;
+    }
+    if ((p.flags & SLVGPU_REP) && p.ninst > 1) {
+      const int g = nf < pl->rep_ctas ? nf : pl->rep_ctas;
+      k_rep<<<g, REP_THREADS, rep_smem_bytes(pl->nmosc, pl->max_nmos, pl->natc, pl->max_nat), st>>>(p, (int)f0, nf, pl->fl, pl->rw, d_out);
+      ++pl->last_launches;
+    }
+  }
+  k_status<<<(unsigned)((nframes + 255) / 256), 256, 0, st>>>(d_out, d_status, nframes);
+  ++pl->last_launches;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, int64_t nframes, double *h_out,
+                                       int32_t *h_status) {
+  if (!pl || !h_coords || !h_out || !h_status) return fail(SLVGPU_EINVAL, "null argument");
+  if (nframes <= 0) return nframes == 0 ? 0 : fail(SLVGPU_EINVAL, "negative frame count");
+  const DevPlan &p = pl->dp;
+  if (!pl->own_stream) CK(cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking));
+  if (pl->stage_frames < nframes) {
+    if (pl->d_stage_coords) { cudaFree(pl->d_stage_coords); cudaFree(pl->d_stage_out); cudaFree(pl->d_stage_status); }
+    pl->d_stage_coords = nullptr; pl->d_stage_out = nullptr; pl->d_stage_status = nullptr; pl->stage_frames = 0;
+    CK(cudaMalloc(&pl->d_stage_coords, (size_t)nframes * p.natoms_total * 3 * sizeof(double)));
+    CK(cudaMalloc(&pl->d_stage_out, (size_t)nframes * SLVGPU_NOUT * sizeof(double)));
+    CK(cudaMalloc(&pl->d_stage_status, (size_t)nframes * sizeof(int32_t)));
+    pl->stage_frames = nframes;
+  }
+  cudaStream_t st = pl->own_stream;
+  CK(cudaMemcpyAsync(pl->d_stage_coords, h_coords, (size_t)nframes * p.natoms_total * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = slvgpu_eval_frames(pl, pl->d_stage_coords, nframes, pl->d_stage_out, pl->d_stage_status, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_out, pl->d_stage_out, (size_t)nframes * SLVGPU_NOUT * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_status, pl->d_stage_status, (size_t)nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int64_t slvgpu_last_launches(const slvgpu_plan *pl) { return pl ? pl->last_launches : 0; }
+
+extern "C" int slvgpu_get_pol_detail(slvgpu_plan *pl, int64_t frame, double *h_dipind, double *h_flds, double *h_rpol,
+                                     int32_t max_centres) {
+  if (!pl || !pl->d_detail) return fail(SLVGPU_EINVAL, "plan was created without want_detail / pol");
+  if (frame < 0 || frame >= pl->detail_frames) return fail(SLVGPU_EINVAL, "frame outside the last chunk");
+  const int cc = pl->dp.cent_cap;
+  std::vector<double> buf((size_t)cc * 9);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(buf.data(), pl->d_detail + (size_t)frame * cc * 9, buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  const int n = max_centres < cc ? max_centres : cc;
+  for (int c = 0; c < n; ++c)
+    for (int d = 0; d < 3; ++d) {
+      if (h_dipind) h_dipind[c * 3 + d] = buf[(size_t)c * 9 + d];
+      if (h_flds) h_flds[c * 3 + d] = buf[(size_t)c * 9 + 3 + d];
+      if (h_rpol) h_rpol[c * 3 + d] = buf[(size_t)c * 9 + 6 + d];
+    }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------ Frag utilities
+template <class F>
+static int roundtrip(double *h, size_t n, F launch) {
+  double *d = nullptr;
+  CK(cudaMalloc(&d, n * sizeof(double)));
+  cudaError_t e = cudaMemcpy(d, h, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) { launch(d); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cudaMemcpy(h, d, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(SLVGPU_ECUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int slvgpu_kabsch(const double *h_ref, const double *h_target, int32_t n, double *h_rot, double *h_transl,
+                             double *h_rms) {
+  if (!h_ref || !h_target || n < 1 || !h_rot || !h_transl || !h_rms) return fail(SLVGPU_EINVAL, "bad argument");
+  std::vector<double> buf((size_t)n * 6 + 13);
+  memcpy(buf.data(), h_ref, (size_t)n * 3 * sizeof(double));
+  memcpy(buf.data() + (size_t)n * 3, h_target, (size_t)n * 3 * sizeof(double));
+  int rc = roundtrip(buf.data(), buf.size(), [&](double *d) { k_kabsch_one<<<1, 32>>>(d, d + (size_t)n * 3, n, d + (size_t)n * 6); });
+  if (rc) return rc;
+  memcpy(h_rot, buf.data() + (size_t)n * 6, 9 * sizeof(double));
+  memcpy(h_transl, buf.data() + (size_t)n * 6 + 9, 3 * sizeof(double));
+  *h_rms = buf[(size_t)n * 6 + 12];
+  return 0;
+}
+
+static int with_rot(const double *h_rot, double **d_rot) {
+  CK(cudaMalloc(d_rot, 12 * sizeof(double)));
+  CK(cudaMemcpy(*d_rot, h_rot, 9 * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int slvgpu_rotate_dma(double *h_dip, double *h_qad, double *h_oct, int64_t n, const double *h_rot) {
+  if (n <= 0) return 0;
+  if (!h_dip || !h_qad || !h_oct || !h_rot) return fail(SLVGPU_EINVAL, "null argument");
+  std::vector<double> buf((size_t)n * 19);
+  for (int64_t i = 0; i < n; ++i) {
+    memcpy(&buf[i * 19], h_dip + i * 3, 3 * sizeof(double));
+    memcpy(&buf[i * 19 + 3], h_qad + i * 6, 6 * sizeof(double));
+    memcpy(&buf[i * 19 + 9], h_oct + i * 10, 10 * sizeof(double));
+  }
+  double *d_rot = nullptr;
+  int rc = with_rot(h_rot, &d_rot);
+  if (rc) return rc;
+  rc = roundtrip(buf.data(), buf.size(), [&](double *d) { k_rot_dma<<<(unsigned)((n + 127) / 128), 128>>>(d, n, d_rot); });
+  cudaFree(d_rot);
+  if (rc) return rc;
+  for (int64_t i = 0; i < n; ++i) {
+    memcpy(h_dip + i * 3, &buf[i * 19], 3 * sizeof(double));
+    memcpy(h_qad + i * 6, &buf[i * 19 + 3], 6 * sizeof(double));
+    memcpy(h_oct + i * 10, &buf[i * 19 + 9], 10 * sizeof(double));
+  }
+  return 0;
+}
+
+extern "C" int slvgpu_rotate_pol(double *h_pol, int64_t n, const double *h_rot) {
+  if (n <= 0) return 0;
+  if (!h_pol || !h_rot) return fail(SLVGPU_EINVAL, "null argument");
+  double *d_rot = nullptr;
+  int rc = with_rot(h_rot, &d_rot);
+  if (rc) return rc;
+  rc = roundtrip(h_pol, (size_t)n * 9, [&](double *d) { k_rot_pol<<<(unsigned)((n + 127) / 128), 128>>>(d, n, d_rot); });
+  cudaFree(d_rot);
+  return rc;
+}
+
+extern "C" int slvgpu_rotate_vec(double *h_vec, int64_t n, const double *h_rot, const double *h_transl) {
+  if (n <= 0) return 0;
+  if (!h_vec || !h_rot) return fail(SLVGPU_EINVAL, "null argument");
+  double *d_rot = nullptr;
+  int rc = with_rot(h_rot, &d_rot);
+  if (rc) return rc;
+  double t[3] = {0, 0, 0};
+  if (h_transl) memcpy(t, h_transl, sizeof(t));
+  cudaMemcpy(d_rot + 9, t, sizeof(t), cudaMemcpyHostToDevice);
+  rc = roundtrip(h_vec, (size_t)n * 3, [&](double *d) { k_rot_vec<<<(unsigned)((n + 127) / 128), 128>>>(d, n, d_rot); });
+  cudaFree(d_rot);
+  return rc;
+}
+
+extern "C" int slvgpu_rotate_vecl(double *h_vec, int64_t nrows, int32_t nbasis, const int32_t *h_typ, const double *h_rot) {
+  if (nrows <= 0 || nbasis <= 0) return 0;
+  if (!h_vec || !h_typ || !h_rot) return fail(SLVGPU_EINVAL, "null argument");
+  // shell starts: the first function of each p triple / d sextet
+  std::vector<int> start;
+  for (int k = 0; k < nbasis;) {
+    if (h_typ[k] == 1) { start.push_back(k); start.push_back(1); k += 3; }
+    else if (h_typ[k] == 2) { start.push_back(k); start.push_back(2); k += 6; }
+    else ++k;
+  }
+  if (start.empty()) return 0;
+  double *d_rot = nullptr; int *d_start = nullptr;
+  int rc = with_rot(h_rot, &d_rot);
+  if (rc) return rc;
+  CK(cudaMalloc(&d_start, start.size() * sizeof(int)));
+  CK(cudaMemcpy(d_start, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice));
+  const int nsh = (int)start.size() / 2;
+  rc = roundtrip(h_vec, (size_t)nrows * nbasis, [&](double *d) {
+    const int64_t work = nrows * nsh;
+    k_rot_vecl<<<(unsigned)((work + 127) / 128), 128>>>(d, nrows, nbasis, d_start, nsh, d_rot);
+  });
+  cudaFree(d_rot); cudaFree(d_start);
+  return rc;
+}

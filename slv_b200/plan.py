@@ -1,0 +1,210 @@
+"""Static plan compilation (host, once per trajectory layout).
+
+Turns the arguments of ``EFP.set`` (ind, nmol, bsm, supl, reord -- solvshift/solefp.py:223-277, produced
+by ``MDInput.get``, solvshift/md.py:82-92) into the flat device tables of include/slvgpu.h and pre-contracts
+every normal-mode sum of the reference: with g_m = g_mjj / (M_m w_m^2) / (2 M_j w_j),
+
+  SolCAMM (mechanical)  s_mea = -sum_m g_m dma1_m              (slvpar.py:1049-1056)
+  SolCAMM (electronic)  s_ea  = dma2_j / (2 M_j w_j)           (slvpar.py:1058-1064)
+  corrections           c_mea = -q_x sum_m g_m L^m_x ,  c_ea = 2 q1^j_x L^j_x / (2 M_j w_j)
+  dispersion            sum_m g_m dpoli1_m, sum_m g_m lmoc1_m
+  polarisation          -alpha^-1 (sum_m g_m dpol1_m) alpha^-1, sum_m g_m lmoc1_m, sum_m g_m lvec_m, sum_m g_m dma1_m
+  exchange-repulsion    sum_m g_m fock1_m, sum_m g_m vecl1_m, sum_m g_m lmoc1_m, sum_m g_m lvec_m
+
+so that one pass over the solute-solvent pairs replaces the reference's (nmodes + 1) passes
+(libbbg sdmtpm / solpol2.f AAAAAA / shftex.f CALCIJ+CALCFI all loop over the modes).  Pure data
+re-indexing and parameter algebra on frame-invariant inputs; nothing per-frame happens here.
+"""
+import ctypes
+
+import numpy
+
+from . import _lib
+from .slvpar import traceless
+
+
+class _Tab(object):
+    def __init__(self, dtype):
+        self.chunks = []; self.n = 0; self.dtype = dtype
+
+    def add(self, a):
+        a = numpy.ascontiguousarray(a, self.dtype).ravel()
+        off = self.n
+        self.chunks.append(a); self.n += a.size
+        return off
+
+    def get(self):
+        if not self.chunks:
+            return numpy.zeros(1, self.dtype)
+        return numpy.concatenate(self.chunks)
+
+
+def mom20(q, d, Q, O):
+    """[n,20] rows: charge, dipole, traceless quadrupole (6), traceless octupole (10)."""
+    qt, ot = traceless(Q, O)
+    return numpy.concatenate([numpy.asarray(q, numpy.float64)[..., None], d, qt, ot], axis=-1)
+
+
+def mode_weights(par, mode):
+    gijj = par['gijk'][:, mode - 1, mode - 1]
+    den = 2.0 * par['redmass'][mode - 1] * par['freq'][mode - 1]
+    return gijj / (par['redmass'] * par['freq'] ** 2) / den, den
+
+
+class Plan(object):
+    """Device-resident evaluation plan (owns the slvgpu_plan handle)."""
+
+    def __init__(self, ind, nmol, bsm, supl, reord, mode, flags, ccut, pcut, ecut,
+                 max_chunk=1024, pol_maxit=200, pol_tol=1e-13, pol_cent_cap=0, want_detail=False):
+        ind = numpy.asarray(ind, int); nmol = numpy.asarray(nmol, int)
+        assert len(ind) == len(nmol) and len(ind) >= 1
+        self.ninst = len(ind)
+        self.natoms_total = int(nmol.sum())
+        self.flags = 0
+        for k, v in flags.items():
+            if v:
+                self.flags |= _lib.FLAG[k]
+        dt, it = _Tab(numpy.float64), _Tab(numpy.int32)
+        ntypes = len(bsm)
+        meta = numpy.full((ntypes, _lib.NMETA), -1, numpy.int32)
+        M = _lib.M
+        pars = [b.get() for b in bsm]
+        need_rep = bool(self.flags & _lib.FLAG['rep'])
+        for t, par in enumerate(pars):
+            nat = int(par['natoms'])
+            sl = supl[t] if supl is not None and supl[t] is not None else numpy.arange(nat)
+            ro = reord[t] if reord is not None and reord[t] is not None else numpy.arange(nat)
+            sl = numpy.asarray(sl, int); ro = numpy.asarray(ro, int)
+            assert len(ro) == nat, 'reorder list of fragment %d must have natoms entries' % t
+            m = meta[t]
+            m[M['NATOMS']] = nat; m[M['NDMA']] = par.get('ndma', 0) or 0; m[M['NPOL']] = par.get('npol', 0) or 0
+            m[M['NMOS']] = par.get('nmos', 0) or 0; m[M['NBASIS']] = par.get('nbasis', 0) or 0
+            m[M['NSUPL']] = len(sl)
+            m[M['IO_SUPL']] = it.add(sl); m[M['IO_REORD']] = it.add(ro)
+            m[M['O_POS']] = dt.add(par['pos'])
+            if 'rdma' in par:
+                m[M['O_RDMA']] = dt.add(par['rdma'])
+                m[M['O_MOM']] = dt.add(mom20(par['dmac'], par['dmad'], par['dmaq'], par['dmao']))
+            if 'rpol' in par and 'dpol' in par:
+                m[M['O_RPOL']] = dt.add(par['rpol'])
+                m[M['O_POL']] = dt.add(par['dpol'])
+                m[M['O_POLINV']] = dt.add(numpy.linalg.inv(par['dpol']))
+            else:
+                m[M['NPOL']] = 0
+            if 'dpoli' in par:
+                m[M['O_DPOLI']] = dt.add(par['dpoli'])
+            if need_rep and 'vecl' in par:
+                from .basis import BasisSet
+                bfs = BasisSet(par['atno'], par['pos'])
+                assert len(bfs) == par['nbasis'], 'basis size mismatch for fragment type %d' % t
+                m[M['O_LMOC']] = dt.add(par['lmoc']); m[M['O_FOCK']] = dt.add(par['fock'])
+                m[M['O_VECL']] = dt.add(par['vecl']); m[M['O_ZNUC']] = dt.add(numpy.asarray(par['atno'], float))
+                m[M['IO_BFC']] = it.add(bfs.center); m[M['IO_BFL']] = it.add(bfs.powers); m[M['IO_BFNP']] = it.add(bfs.nprim)
+                m[M['O_BFEXP']] = dt.add(bfs.exps); m[M['O_BFCOEF']] = dt.add(bfs.coefs)
+        # ---- solute: mode-contracted tables
+        sol = numpy.full(_lib.NSOL, -1, numpy.int32)
+        S = _lib.S
+        pc = pars[int(ind[0])]
+        self.mode = mode
+        if mode is not None and 'gijk' in pc:
+            g, den = mode_weights(pc, mode)
+            j = mode - 1
+            dma1 = mom20(pc['dmac1'], pc['dmad1'], pc['dmaq1'], pc['dmao1'])          # [nmodes, ndma, 20]
+            gd = numpy.tensordot(g, dma1, (0, 0))
+            sol[S['SMEA']] = dt.add(-gd)
+            sol[S['DMA1']] = dt.add(gd)
+            if 'mode' in pc and (mode - 1) in list(pc['mode']):
+                m2 = list(pc['mode']).index(mode - 1)
+                sol[S['SEA']] = dt.add(mom20(pc['dmac2'][m2], pc['dmad2'][m2], pc['dmaq2'][m2], pc['dmao2'][m2]) / den)
+            else:
+                assert not (self.flags & _lib.FLAG['ea']) or not (self.flags & _lib.FLAG['elect']), \
+                    " The second derivatives wrt mode %d are not evaluated for %s!" % (mode, pc.get('name'))
+                sol[S['SEA']] = dt.add(numpy.zeros_like(gd))
+            gL = numpy.tensordot(g, pc['lvec'], (0, 0))                                 # [natoms,3]
+            nd = int(pc['ndma']); nat = int(pc['natoms']); n = min(nd, nat)
+            cm = numpy.zeros((nd, 3)); ce = numpy.zeros((nd, 3))
+            cm[:n] = -pc['dmac'][:n, None] * gL[:n]
+            ce[:n] = 2.0 * pc['dmac1'][j][:n, None] * pc['lvec'][j][:n] / den
+            sol[S['CMEA']] = dt.add(cm); sol[S['CEA']] = dt.add(ce)
+            sol[S['LVEC']] = dt.add(gL)
+            if 'lmoc1' in pc:
+                sol[S['LMOC1']] = dt.add(numpy.tensordot(g, pc['lmoc1'], (0, 0)))
+            if 'dpoli1' in pc:
+                sol[S['DPOLI1']] = dt.add(numpy.tensordot(g, pc['dpoli1'], (0, 0)))
+            if 'dpol1' in pc:
+                ainv = numpy.linalg.inv(pc['dpol'])
+                a1 = numpy.tensordot(g, pc['dpol1'], (0, 0))
+                sol[S['DPOL1']] = dt.add(-numpy.einsum('iab,ibc,icd->iad', ainv, a1, ainv))
+            if need_rep:
+                sol[S['FOCK1']] = dt.add(numpy.tensordot(g, pc['fock1'], (0, 0)))
+                sol[S['VECL1']] = dt.add(numpy.tensordot(g, pc['vecl1'], (0, 0)))
+        self._keep = dict(meta=meta, sol=sol, itab=it.get(), dtab=dt.get(),
+                          inst_type=numpy.ascontiguousarray(ind, numpy.int32),
+                          inst_atom0=numpy.ascontiguousarray(numpy.concatenate([[0], numpy.cumsum(nmol)]), numpy.int32))
+        k = self._keep
+        d = _lib.PlanDesc()
+        d.ntypes = ntypes; d.ninst = self.ninst; d.natoms_total = self.natoms_total; d.flags = self.flags
+        d.ccut = float(ccut); d.pcut = float(pcut); d.ecut = float(ecut)
+        d.type_meta = k['meta'].ctypes.data; d.sol_meta = k['sol'].ctypes.data
+        d.itab = k['itab'].ctypes.data; d.n_itab = k['itab'].size
+        d.dtab = k['dtab'].ctypes.data; d.n_dtab = k['dtab'].size
+        d.inst_type = k['inst_type'].ctypes.data; d.inst_atom0 = k['inst_atom0'].ctypes.data
+        d.max_chunk = int(max_chunk); d.pol_maxit = int(pol_maxit); d.pol_tol = float(pol_tol)
+        d.pol_cent_cap = int(pol_cent_cap); d.want_detail = int(bool(want_detail))
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib.slvgpu_plan_create(ctypes.byref(d), ctypes.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            _lib.lib.slvgpu_plan_destroy(h)
+            self._h = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def eval_device(self, coords, out=None, status=None, stream=None):
+        """coords: CUDA torch tensor [nframes, natoms_total, 3] float64.  Returns (out[nframes,16], status)."""
+        import torch
+        assert coords.is_cuda and coords.dtype == torch.float64 and coords.is_contiguous()
+        nf = coords.shape[0]
+        assert coords.shape[1] == self.natoms_total and coords.shape[2] == 3
+        if out is None:
+            out = torch.empty((nf, _lib.NOUT), dtype=torch.float64, device=coords.device)
+        if status is None:
+            status = torch.empty((nf,), dtype=torch.int32, device=coords.device)
+        st = torch.cuda.current_stream(coords.device).cuda_stream if stream is None else stream
+        _lib.check(_lib.lib.slvgpu_eval_frames(self._h, coords.data_ptr(), nf, out.data_ptr(), status.data_ptr(), st))
+        return out, status
+
+    def eval_host(self, coords, out=None, status=None):
+        """coords: numpy or pinned CPU torch tensor [nframes, natoms_total, 3] float64 (host buffers;
+        the H2D / D2H copies happen inside the call)."""
+        if hasattr(coords, 'data_ptr'):
+            nf = coords.shape[0]; cptr = coords.data_ptr()
+            assert coords.is_contiguous()
+        else:
+            coords = numpy.ascontiguousarray(coords, numpy.float64)
+            nf = coords.shape[0]; cptr = coords.ctypes.data
+        if out is None:
+            out = numpy.empty((nf, _lib.NOUT), numpy.float64)
+        if status is None:
+            status = numpy.empty((nf,), numpy.int32)
+        optr = out.data_ptr() if hasattr(out, 'data_ptr') else out.ctypes.data
+        sptr = status.data_ptr() if hasattr(status, 'data_ptr') else status.ctypes.data
+        _lib.check(_lib.lib.slvgpu_eval_frames_host(self._h, cptr, nf, optr, sptr))
+        return out, status
+
+    def last_launches(self):
+        return int(_lib.lib.slvgpu_last_launches(self._h))
+
+    def pol_detail(self, frame=0, max_centres=None):
+        n = max_centres or 1 << 20
+        k = self._keep
+        tot = int(sum(k['meta'][t][_lib.M['NPOL']] for t in k['inst_type']))
+        n = min(n, tot)
+        dip = numpy.zeros((n, 3)); fld = numpy.zeros((n, 3)); rp = numpy.zeros((n, 3))
+        got = _lib.check(_lib.lib.slvgpu_get_pol_detail(self._h, frame, dip.ctypes.data, fld.ctypes.data, rp.ctypes.data, n))
+        return dip[:got], fld[:got], rp[:got]

@@ -1,0 +1,266 @@
+"""SolEFP frequency-shift solver -- the ``solvshift.solefp.EFP`` surface on the B200.
+
+Same constructor keywords, ``set`` / ``eval`` / ``get_shifts`` / ``get_rms*`` calls and shift
+dictionary as the reference (solvshift/solefp.py:52-83, 223-277, 93-149, 299-313, 608-634, 679-718,
+1565-1614); the arithmetic of one frame -- cut-off lists (MOLLST), superimposition of every fragment
+(Frag.sup), multipole electrostatics and corrections (libbbg sdmtpm/sdmtpe/dmtcor), polarisation
+(solpol2.f SFTPLI), dispersion (sdisp6/tdisp6), exchange-repulsion (shftex.f) -- runs in CUDA kernels
+behind the C ABI of include/slvgpu.h.  ``eval_frames`` is the batched entry the MD frame loop
+(util/slv_md-run_nopp:116-155, 202-209) maps onto: whole trajectories in one call.
+
+There is no CPU arithmetic path: without the CUDA library / a GPU every evaluation raises.
+"""
+import numpy
+
+from . import _lib
+from .plan import Plan
+from .units import UNITS
+
+__all__ = ['EFP']
+
+SHIFT_TERMS = {
+    'ele_mea': 'SolCAMM (mechanical anharmonicity)',
+    'ele_ea': 'SolCAMM (electronic anharmonicity)',
+    'cor_mea': 'Corrections to SolCAMM (mechanical anharmonicity)',
+    'cor_ea': 'Corrections to SolCAMM (electronic anharmonicity)',
+    'pol_mea': 'Induction (mechanical anharmonicity)',
+    'pol_ea': 'Induction (electronic anharmonicity)',
+    'rep_mea': 'Exchange-Repulsion (mechanical anharmonicity)',
+    'rep_ea': 'Exchange-Repulsion (electronic anharmonicity)',
+    'dis_mea': 'Dispersion (anisotropic, mechanical anharmonicity)',
+    'dis_ea': 'Dispersion (anisotropic, electronic anharmonicity)',
+    'total': 'SolEFP (SolCAMM+Corrections, Induction, Exchange-Repulsion, anisotropic Dispersion)',
+    'total_ele': 'SolCAMM+Corrections, Induction and anisotropic Dispersion (mechanical + electronic anharmonicity)',
+    'total_mea': 'All mechanical anharmonicity terms',
+    'total_ea': 'All electronic anharmonicity terms',
+    'solcamm': 'SolCAMM (mechanical + electronic anharmonicity)',
+    'total_cor': 'Corrections (mechanical + electronic anharmonicity)',
+    'pol_add_mea': 'Induction under additive approximation (mechanical anharmonicity)',
+    'pol_add_ea': 'Induction under additive approximation (electronic anharmonicity)',
+    'dis_mea_iso': 'Dispersion (isotropic, mechanical anharmonicity)',
+    'ele_tot': 'SolCAMM+Corrections (mechanical + electronic anharmonicity)',
+    'pol_tot': 'Polarization (mechanical + electronic anharmonicity)',
+    'rep_tot': 'Exchange-Repulsion (mechanical + electronic anharmonicity)',
+    'dis_tot': 'Dispersion (anisotropic, mechanical + electronic anharmonicity)',
+    'ele_env_mea': 'SolCAMM:DMA[non-EFP Environment]: mechanical anharmonicity ',
+    'ele_env_ea': 'SolCAMM:DMA[non-EFP Environment]: electronic anharmonicity ',
+    'cor_env_mea': 'Corrections:DMA[non-EFP Environment]: electronic anharmonicity ',
+    'tot_env': 'SolCAMM+Corrections:DMA[non-EFP Environment]: mechanical + electronic anharmonicity',
+    'total+env': 'SolEFP + DMA[non-EFP Environment] (total+tot_env terms)',
+}
+
+# columns of the MD report (util/slv_md-run_nopp:127-153, 182-190)
+REPORT_KEYS = ['solcamm', 'ele_mea', 'ele_ea', 'cor_mea', 'cor_ea', 'pol_mea', 'pol_ea', 'rep_mea', 'rep_ea',
+               'dis_mea', 'dis_ea', 'dis_mea_iso', 'total']
+
+
+def shifts_from_rows(rows, cunit):
+    """Assemble the reference's shift terms (solefp.py:1565-1614) from device output rows [n,16].
+    Returns a dict of arrays of length n."""
+    O = _lib.OUT
+    c = UNITS.HartreePerHbarToCmRec if cunit else 1.0
+    r = numpy.asarray(rows, numpy.float64)
+    z = numpy.zeros(len(r))
+    s = {}
+    s['ele_mea'] = r[:, O['ele_mea']] * c; s['ele_ea'] = r[:, O['ele_ea']] * c
+    s['cor_mea'] = r[:, O['cor_mea']] * c; s['cor_ea'] = r[:, O['cor_ea']] * c
+    s['pol_mea'] = r[:, O['pol_mea']] * c; s['pol_ea'] = z.copy()
+    s['rep_mea'] = r[:, O['rep_mea']] * c; s['rep_ea'] = z.copy()
+    s['dis_mea'] = r[:, O['dis_mea']] * c; s['dis_ea'] = z.copy()
+    s['dis_mea_iso'] = r[:, O['dis_mea_iso']] * c
+    s['ele_tot'] = s['ele_mea'] + s['ele_ea'] + s['cor_mea'] + s['cor_ea']
+    s['pol_tot'] = s['pol_mea'] + s['pol_ea']
+    s['rep_tot'] = s['rep_mea'] + s['rep_ea']
+    s['dis_tot'] = s['dis_mea'] + s['dis_ea']
+    s['total'] = s['ele_tot'] + s['pol_tot'] + s['dis_tot'] + s['rep_tot']
+    s['total_ele'] = s['total'] - s['rep_mea'] - s['rep_ea']
+    s['total_mea'] = s['ele_mea'] + s['cor_mea'] + s['pol_mea'] + s['rep_mea'] + s['dis_mea']
+    s['total_ea'] = s['ele_ea'] + s['cor_ea'] + s['pol_ea'] + s['rep_ea'] + s['dis_ea']
+    s['solcamm'] = s['ele_mea'] + s['ele_ea']
+    s['total_cor'] = s['cor_mea'] + s['cor_ea']
+    s['pol_add_mea'] = z.copy(); s['pol_add_ea'] = z.copy(); s['pol_add_tot'] = z.copy()
+    return s
+
+
+class EFP(UNITS):
+    """Frequency-shift (central-molecule) mode of the reference's EFP class."""
+
+    def __init__(self, elect=True, pol=False, rep=False, ct=False, disp=False, all=False,
+                 ccut=None, pcut=None, ecut=None, ea=True, corr=False, nlo=False, freq=False,
+                 cunit=False, mode=None):
+        self._cunit = cunit
+        self._ccut = 1.E+10 if ccut is None else ccut
+        self._pcut = 1.E+10 if pcut is None else pcut
+        self._ecut = 1.E+10 if ecut is None else ecut
+        if all:
+            self._elect = self._pol = self._rep = self._disp = True
+            self._corr = False; self._ea = True
+        else:
+            self._elect, self._pol, self._rep, self._disp, self._corr, self._ea = elect, pol, rep, disp, corr, ea
+        if ct:
+            raise NotImplementedError('charge-transfer is not evaluated by the central (frequency shift) mode '
+                                      '(no ct branch in solvshift/solefp.py:1011-1629)')
+        if not freq:
+            raise NotImplementedError('only the frequency-shift (freq=True) mode is on the GPU path; the global '
+                                      'EFP2 interaction-energy mode (solefp.py:905-1009) is out of scope')
+        if mode is None:
+            raise ValueError('freq=True needs mode=<1-based normal mode index>')
+        self._mode = mode
+        self._plan = None; self._plan_key = None
+        self._pos = None
+        self._rows = None; self._status = None
+        self._shift = dict((k, numpy.nan) for k in SHIFT_TERMS)
+        self.shift_terms = SHIFT_TERMS
+        self._rms_central = None; self._rms_solvent_max = None; self._rms_ave = None
+        self._bsm = None; self._supl = None; self._reord = None; self._ind = None; self._nmol = None
+        self.pol_maxit = 200; self.pol_tol = 1e-13; self.max_chunk = 1024; self.pol_cent_cap = 0
+        self.want_detail = False
+
+    def __call__(self, lwrite=False, num=False, step=0.006, theory=0):
+        self.eval(lwrite, num, step, theory)
+
+    # ------------------------------------------------------------------ configuration
+    def set(self, pos, ind, nmol, bsm=None, supl=None, reord=None):
+        """Set coordinates (natoms,3 in Bohr) and the fragment layout (solefp.py:223-277)."""
+        self._ind = numpy.array(ind, int); self._nmol = numpy.array(nmol, int)
+        if bsm is not None:
+            self._bsm = bsm
+        if supl is not None:
+            self._supl = supl
+        if reord is not None:
+            self._reord = reord
+        self._update(pos)
+
+    def set_cut(self, ccut, pcut, ecut):
+        self._ccut, self._pcut, self._ecut = ccut, pcut, ecut
+        self._plan = None
+
+    def set_bsm(self, bsm):
+        self._bsm = bsm; self._plan = None
+
+    def set_pos(self, pos):
+        self._update(pos)
+
+    def _update(self, pos):
+        pos = numpy.ascontiguousarray(pos, numpy.float64)
+        assert pos.ndim == 2 and pos.shape[1] == 3 and len(pos) == int(self._nmol.sum()), \
+            'coordinate array does not match the nmol list'
+        self._pos = pos
+
+    def _flags(self):
+        # in the reference, pol/disp are only reached inside `if self.__eval_elect` (solefp.py:1122-1437)
+        el = bool(self._elect)
+        return dict(elect=el, ea=bool(self._ea) and el, corr=bool(self._corr) and el,
+                    pol=bool(self._pol) and el, disp=bool(self._disp) and el, rep=bool(self._rep))
+
+    def _get_plan(self):
+        key = (tuple(self._ind), tuple(self._nmol), tuple(id(b) for b in self._bsm), self._mode, self._ccut, self._pcut,
+               self._ecut, tuple(sorted(self._flags().items())), self.pol_maxit, self.pol_tol, self.max_chunk,
+               self.pol_cent_cap, self.want_detail,
+               tuple(None if s is None else tuple(s) for s in (self._supl or [])),
+               tuple(None if s is None else tuple(s) for s in (self._reord or [])))
+        if self._plan is None or key != self._plan_key:
+            self._plan = Plan(self._ind, self._nmol, self._bsm, self._supl, self._reord, self._mode, self._flags(),
+                              self._ccut, self._pcut, self._ecut, max_chunk=self.max_chunk, pol_maxit=self.pol_maxit,
+                              pol_tol=self.pol_tol, pol_cent_cap=self.pol_cent_cap, want_detail=self.want_detail)
+            self._plan_key = key
+        return self._plan
+
+    # ------------------------------------------------------------------ evaluation
+    def eval(self, lwrite=False, num=False, step=0.006, theory=0, remove_clashes=False,
+             rcl_algorithm='remove_by_name', include_ions=True, include_polar=True):
+        """Evaluate the shifts of the current frame (solefp.py:93-149)."""
+        if num:
+            raise NotImplementedError('numerical (finite-difference) mode needs the num_0.006/*.frg sets, which are '
+                                      'not part of the parameter library')
+        if remove_clashes:
+            raise NotImplementedError('remove_clashes (biomol path) is not on the GPU path yet')
+        rows, status = self._get_plan().eval_host(self._pos[None])
+        self._store(rows, status)
+        if lwrite:
+            print(self)
+        return
+
+    def eval_frames(self, coords, ind=None, nmol=None, bsm=None, supl=None, reord=None, device=True):
+        """Batched evaluation: coords [nframes, natoms, 3] (Bohr).  A CUDA torch tensor is evaluated in
+        place on the device and CUDA tensors are returned; a host array (numpy / pinned torch) goes
+        through the host entry point.  Returns (rows [nframes,16] in a.u., status [nframes])."""
+        if ind is not None:
+            self._ind = numpy.array(ind, int); self._nmol = numpy.array(nmol, int)
+            if bsm is not None:
+                self._bsm = bsm
+            if supl is not None:
+                self._supl = supl
+            if reord is not None:
+                self._reord = reord
+        plan = self._get_plan()
+        if hasattr(coords, 'is_cuda') and coords.is_cuda:
+            return plan.eval_device(coords)
+        return plan.eval_host(coords)
+
+    def shifts_of(self, rows):
+        """Dictionary of per-frame arrays with the reference's shift keys."""
+        if hasattr(rows, 'cpu'):
+            rows = rows.cpu().numpy()
+        return shifts_from_rows(rows, self._cunit)
+
+    def _store(self, rows, status):
+        self._rows = rows; self._status = status
+        s = shifts_from_rows(rows[:1], self._cunit)
+        for k, v in s.items():
+            self._shift[k] = float(v[0])
+        self._shift['total+env'] = self._shift['total'] + self._shift['tot_env']
+        O = _lib.OUT
+        self._rms_central = float(rows[0, O['rms_c']])
+        self._rms_solvent_max = float(rows[0, O['rms_smax']])
+        self._rms_ave = float(rows[0, O['rms_ave']])
+
+    # ------------------------------------------------------------------ getters
+    def get_shifts(self):
+        return self._shift.copy()
+
+    def get_status(self):
+        return None if self._status is None else int(self._status[0])
+
+    def get_rms(self):
+        return self._rms_central
+
+    def get_rms_sol(self):
+        return self._rms_solvent_max
+
+    def get_rms_ave(self):
+        return self._rms_ave
+
+    def get_rms_max(self):
+        if self._rms_central is not None:
+            return max(self._rms_central, self._rms_solvent_max)
+        return self._rms_solvent_max
+
+    def get_dipind(self):
+        """(induced dipoles, centres) at the polarisable centres inside pcut (solefp.py:307-309)."""
+        n = self._n_pol_centres()
+        dip, fld, rp = self._get_plan().pol_detail(0, n)
+        return dip, rp
+
+    def get_fields(self):
+        n = self._n_pol_centres()
+        dip, fld, rp = self._get_plan().pol_detail(0, n)
+        return fld, rp
+
+    def _n_pol_centres(self):
+        if not self.want_detail:
+            raise RuntimeError('set efp.want_detail = True before eval() to keep fields / induced dipoles')
+        raise NotImplementedError
+
+    def __repr__(self):
+        s = self._shift
+        log = " Electrostatic      frequency shift: %10.2f\n" % s['ele_tot']
+        log += "                MEA           : %10.2f\n" % s['ele_mea']
+        log += "                 EA           : %10.2f\n" % s['ele_ea']
+        log += "               CORR           : %10.2f\n" % s['total_cor']
+        log += " Polarization       frequency shift: %10.2f  %10.2f\n" % (s['pol_tot'], s['pol_add_tot'])
+        log += " Dispersion         frequency shift: %10.2f  %10.2f\n" % (s['dis_mea_iso'], s['dis_mea'])
+        log += " Exchange-repulsion frequency shift: %10.2f\n" % s['rep_tot']
+        log += " ----------------------------------------------- \n"
+        log += " TOTAL FREQUENCY SHIFT             : %10.2f\n" % s['total']
+        return log

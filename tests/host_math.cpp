@@ -1,0 +1,14 @@
+// Host build of slv_b200/csrc/slv_math.cuh for CPU unit checks (tests/test_host_math.py).
+// TEST INFRASTRUCTURE: the product never loads this.
+#include "../slv_b200/csrc/slv_math.cuh"
+extern "C" {
+void hm_kabsch_rot(const double* a, double* rot) { slv::kabsch_rot(a, rot); }
+void hm_rot_mom20(const double* R, const double* m, double* o) { slv::rot_mom20(R, m, o); }
+void hm_rot_mat(const double* R, const double* a, double* o) { slv::rot_mat(R, a, o); }
+void hm_pair_potentials(const double* rA, const double* rB, const double* mB, double* P) { slv::pair_potentials(rA, rB, mB, P); }
+void hm_fold20(double* s) { slv::fold20(s); }
+}
+extern "C" {
+void hm_site_field(const double* R, const double* m, double f, double* F) { slv::site_field(R, m, f, F); }
+void hm_site_dfield(const double* R, const double* v, const double* m, double sg, double* F) { slv::site_dfield(R, v, m, sg, F); }
+}

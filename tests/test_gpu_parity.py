@@ -1,0 +1,136 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle, on the reference's golden
+cluster, its 21-point scan, and seeded synthetic clusters.  Bit-exactness is not expected for FP64
+sums in a different order; the bar is BASELINE.json's: 1e-6 cm^-1 absolute per frame."""
+import numpy as np
+import pytest
+
+from tests.util import scan_geometries, SCAN_SUPL, SCAN_REORD
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6          # cm^-1, north_star tolerance
+TERMS = ('ele_mea', 'ele_ea', 'cor_mea', 'cor_ea', 'pol_mea', 'dis_mea', 'dis_mea_iso')
+
+
+def _efp(**kw):
+    from slv_b200.solefp import EFP
+    args = dict(elect=True, pol=True, disp=True, corr=True, freq=True, mode=8, cunit=True)
+    args.update(kw)
+    return EFP(**args)
+
+
+def test_golden_vector_f(frags, golden):
+    """examples/1_small-clusters/f: every term except rep against the stored dict."""
+    efp = _efp()
+    xyz = scan_geometries(golden, 1)[0]
+    efp.set(xyz, [0, 1], [12, 3], (frags('nma'), frags('water')), SCAN_SUPL, SCAN_REORD)
+    efp.eval(0)
+    s = efp.get_shifts()
+    for k in ('ele_mea', 'ele_ea', 'cor_mea', 'cor_ea', 'pol_mea', 'dis_mea', 'dis_mea_iso', 'ele_tot', 'solcamm', 'total_cor'):
+        assert abs(s[k] - golden['f'][k]) < 2e-9 * max(1.0, abs(golden['f'][k])) + 1e-8, (k, s[k], golden['f'][k])
+    assert efp.get_status() == 0
+
+
+def test_golden_scan_dat(frags, golden):
+    """examples/1_small-clusters/dat column 2 (ele_tot, 2 decimals) over the 21 rotated geometries, batched."""
+    efp = _efp(pol=False, disp=False)
+    X = np.array(scan_geometries(golden))
+    rows, status = efp.eval_frames(X, [0, 1], [12, 3], (frags('nma'), frags('water')), SCAN_SUPL, SCAN_REORD)
+    s = efp.shifts_of(rows)
+    for i, (tot, ele) in enumerate(golden['dat']):
+        assert abs(round(s['ele_tot'][i], 2) - ele) < 0.011, (i, s['ele_tot'][i], ele)
+    assert int(status.max()) == 0
+
+
+@pytest.mark.parametrize('solute,mode,nw,seed', [('nma', 8, 6, 11), ('nma-d7', 8, 40, 12), ('mescn', 4, 25, 13)])
+def test_synthetic_cluster_vs_oracle(frags, solute, mode, nw, seed):
+    import torch
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O
+    sol, wat = frags(solute), frags('water')
+    nat = sol.get_natoms()
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos()], np.zeros(nw, int), 4, seed=seed)
+    ind = [0] + [1] * nw; nmol = [nat] + [3] * nw
+    cuts = (20.0, 13.0, 11.0)
+    efp = _efp(mode=mode, ccut=cuts[0], pcut=cuts[1], ecut=cuts[2])
+    rows, status = efp.eval_frames(torch.from_numpy(X).cuda(), ind, nmol, [sol, wat], [None, None], [None, None])
+    got = efp.shifts_of(rows)
+    rows = rows.cpu().numpy()
+    c = O.HartreePerHbarToCmRec
+    for f in range(len(X)):
+        ref = O.eval_frame(X[f], ind, nmol, [sol.get(), wat.get()], [None, None], [None, None], mode, *cuts,
+                           elect=True, ea=True, corr=True, pol=True, disp=True)
+        for k in TERMS:
+            assert abs(got[k][f] - ref[k] * c) < TOL, (f, k, got[k][f], ref[k] * c)
+        assert abs(rows[f, 8] - ref['rms_c']) < 1e-10 and abs(rows[f, 9] - ref['rms_smax']) < 1e-10
+        assert abs(rows[f, 10] - ref['rms_ave']) < 1e-10
+        assert (rows[f, 11], rows[f, 12], rows[f, 13]) == (ref['n_elect'], ref['n_pol'], ref['n_rep'])
+    assert int(status.max()) == 0
+
+
+def test_mixed_solvent_types(frags):
+    """water/DMSO mix (BASELINE config 3 shape, small): type-indexed tables, ragged fragments."""
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O
+    sol, wat, dmso = frags('mescn'), frags('water'), frags('dmso')
+    types = np.array([0, 1, 0, 1, 1, 0, 0, 1, 0, 0, 1, 0])
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos(), dmso.get_pos()], types, 2, seed=3, spacing=8.5)
+    ind = [0] + [1 + t for t in types]; nmol = [7] + [3 if t == 0 else 10 for t in types]
+    efp = _efp(mode=4, ccut=40.0, pcut=17.0, ecut=12.0)
+    rows, status = efp.eval_frames(X, ind, nmol, [sol, wat, dmso], [None] * 3, [None] * 3)
+    got = efp.shifts_of(rows)
+    c = O.HartreePerHbarToCmRec
+    for f in range(len(X)):
+        ref = O.eval_frame(X[f], ind, nmol, [sol.get(), wat.get(), dmso.get()], [None] * 3, [None] * 3, 4, 40.0, 17.0, 12.0,
+                           elect=True, ea=True, corr=True, pol=True, disp=True)
+        for k in TERMS:
+            assert abs(got[k][f] - ref[k] * c) < TOL, (f, k, got[k][f], ref[k] * c)
+
+
+def test_rigid_motion_invariance(frags):
+    """Size-independent property: rotating + translating the whole frame leaves every term unchanged."""
+    from slv_b200 import synth
+    sol, wat = frags('nma-d7'), frags('water')
+    nw = 200
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos()], np.zeros(nw, int), 2, seed=5)
+    R = synth.random_rotations(np.random.default_rng(9), 1)[0]
+    X2 = X @ R + np.array([3.0, -7.0, 11.0])
+    ind = [0] + [1] * nw; nmol = [12] + [3] * nw
+    efp = _efp(ccut=40.0, pcut=17.0, ecut=12.0)
+    a, _ = efp.eval_frames(X, ind, nmol, [sol, wat], [None, None], [None, None])
+    b, _ = efp.eval_frames(X2)
+    sa, sb = efp.shifts_of(a), efp.shifts_of(b)
+    for k in TERMS:
+        assert np.abs(sa[k] - sb[k]).max() < TOL, (k, sa[k], sb[k])
+
+
+def test_empty_layers_and_no_solvent(frags):
+    """Edge cases: every solvent outside every cut-off; and a frame with the solute only."""
+    from slv_b200 import synth
+    sol, wat = frags('nma'), frags('water')
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos()], np.zeros(5, int), 1, seed=2)
+    X[:, 12:] += 500.0
+    efp = _efp(ccut=20.0, pcut=13.0, ecut=11.0)
+    rows, status = efp.eval_frames(X, [0] + [1] * 5, [12] + [3] * 5, [sol, wat], [None, None], [None, None])
+    assert np.all(rows[:, :8] == 0.0) and rows[0, 11] == 0 and int(status[0]) == 0
+    efp2 = _efp()
+    efp2.set(X[0, :12], [0], [12], [sol], [None], [None])
+    efp2.eval(0)
+    s = efp2.get_shifts()
+    assert s['total'] == 0.0 and efp2.get_rms() < 0.1
+
+
+def test_frag_sup_matches_oracle(frags):
+    """Frag.sup (GPU Kabsch + tensor rotation) against the NumPy restatement of slvpar.py:641-734."""
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O
+    w = frags('water').copy()
+    par0 = frags('water').get()
+    R = synth.random_rotations(np.random.default_rng(4), 1)[0]
+    xyz = par0['pos'] @ R + np.array([1.0, 2.0, 3.0])
+    rms = w.sup(xyz)
+    rot, tr, rms_o = O.kabsch(par0['pos'], xyz)
+    ref = O.sup_params(par0, rot, tr)
+    got = w.get()
+    assert abs(rms - rms_o) < 1e-10
+    for k in ('pos', 'rdma', 'rpol', 'lmoc', 'dmad', 'dmaq', 'dmao', 'dpol', 'dpoli'):
+        assert np.abs(got[k] - ref[k]).max() < 1e-12, k
