@@ -7,9 +7,10 @@
 //      SHIFT = -1/2 [ y^T dD x - (x + y) . dF ],   dD = sum_m g_m dD_m,  dF = sum_m g_m dF_m,
 // where dD has entries only in the solute rows/columns and dF is a sum over (solute, solvent) pairs, both
 // linear in the mode-derivative parameters -- which the plan pre-contracts.  So the work is: the fields F,
-// two linear solves, and O(N) pair contractions.  The solves are matrix-free block-Jacobi sweeps
-//      x <- alpha (F - T x),   y <- alpha^T (F - T y)
-// that share every T_ij evaluation; T is rebuilt from the centre coordinates each sweep (no N^2 storage).
+// two linear solves, and O(N) pair contractions.  The two solves are one matrix-free BiCG run on the
+// block-preconditioned operator A = I + alpha T (BiCG solves A x = b and A^T xt = bt together, which is
+// exactly the D / D^T pair needed); every sweep over the centre pairs applies T to both search directions,
+// and T is rebuilt from the centre coordinates each sweep (no N^2 storage).
 // The reference's quirks are reproduced: octupole field prefactor 5 in F (solpol2.f:1425), 1/2 on the
 // solute-solvent dT blocks (699-706), the SUM2 slip in the field derivatives (466-483, 959-976).
 #pragma once
@@ -20,12 +21,13 @@ namespace slv {
 constexpr int POL_THREADS = 512;
 constexpr int POL_TILE = 128;
 constexpr int SITE_ROW = 24;     // pos3, mom20, molecule id
+constexpr int PST = 30;          // BiCG state per centre: x xt r rt p pt u ut q qt (3 each)
 
 struct PolWork {                 // per-CTA workspace (device pointers already offset per CTA by the kernel)
   double *cent_pos;   // [cent_cap][3]
   double *cent_alpha; // [cent_cap][9]
   double *fld;        // [cent_cap][3]
-  double *xy;         // [2 buffers][cent_cap][6]  x(3), y(3)
+  double *xy;         // [cent_cap][PST] BiCG state + [cent_cap][6] final x, y
   double *site;       // [site_cap][SITE_ROW]
   int *cent_mol;      // [cent_cap]
   int *ent_coff;      // [list_cap] first centre of a list entry
@@ -45,7 +47,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
   {
     const size_t cb = blockIdx.x;
     const size_t cc = (size_t)p.cent_cap;
-    wk.cent_pos += cb * cc * 3; wk.cent_alpha += cb * cc * 9; wk.fld += cb * cc * 3; wk.xy += cb * cc * 12;
+    wk.cent_pos += cb * cc * 3; wk.cent_alpha += cb * cc * 9; wk.fld += cb * cc * 3; wk.xy += cb * cc * (PST + 6);
     wk.site += cb * (size_t)p.site_cap * SITE_ROW; wk.cent_mol += cb * cc;
     wk.ent_coff += cb * (size_t)p.list_cap; wk.ent_soff += cb * (size_t)p.list_cap;
   }
@@ -124,80 +126,132 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       }
       const double *a = wk.cent_alpha + (size_t)c * 9;
       wk.fld[(size_t)c * 3] = F[0]; wk.fld[(size_t)c * 3 + 1] = F[1]; wk.fld[(size_t)c * 3 + 2] = F[2];
-      double *v = wk.xy + (size_t)c * 6;               // buffer 0: x0 = alpha F, y0 = alpha^T F
-      for (int i = 0; i < 3; ++i) {
-        v[i] = a[i * 3] * F[0] + a[i * 3 + 1] * F[1] + a[i * 3 + 2] * F[2];
-        v[3 + i] = a[i] * F[0] + a[3 + i] * F[1] + a[6 + i] * F[2];
-      }
+      double *v = wk.xy + (size_t)c * PST;              // state slot 0..2 <- b = alpha F
+      for (int i = 0; i < 3; ++i) v[i] = a[i * 3] * F[0] + a[i * 3 + 1] * F[1] + a[i * 3 + 2] * F[2];
     }
     __syncthreads();
 
-    // ---- (c) block-Jacobi sweeps for x and y together
-    int cur = 0, iters = 0;
+    // ---- (c) BiCG on the block-preconditioned system  A x = alpha F,  A = I + alpha T,  together with the
+    //      transposed system A^T xt = F (xt = alpha^-T y): one sweep over the centre pairs applies T to both
+    //      search directions.  State per centre (PST doubles): x xt r rt p pt u ut q qt.
+    int iters = 0;
     double resid = 1.0;
-    const size_t bstride = (size_t)p.cent_cap * 6;
-    for (; iters < p.pol_maxit; ++iters) {
-      const double *vin = wk.xy + cur * bstride;
-      double *vout = wk.xy + (cur ^ 1) * bstride;
-      double dmax = 0.0, vmax = 0.0;
-      for (int c0 = 0; c0 < ncent; c0 += NT) {
-        const int c = c0 + tid;
-        const bool act = c < ncent;
-        double rc[3] = {0, 0, 0}; int mc = -1;
-        if (act) { rc[0] = wk.cent_pos[(size_t)c * 3]; rc[1] = wk.cent_pos[(size_t)c * 3 + 1]; rc[2] = wk.cent_pos[(size_t)c * 3 + 2]; mc = wk.cent_mol[c]; }
-        double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0};
-        for (int j0 = 0; j0 < ncent; j0 += POL_TILE) {
-          __syncthreads();
-          if (tid < POL_TILE) {
-            const int j = j0 + tid;
-            if (j < ncent) {
-              double *tt = s_tile + tid * 10;
-              tt[0] = wk.cent_pos[(size_t)j * 3]; tt[1] = wk.cent_pos[(size_t)j * 3 + 1]; tt[2] = wk.cent_pos[(size_t)j * 3 + 2];
-              const double *vj = vin + (size_t)j * 6;
-              for (int d = 0; d < 6; ++d) tt[3 + d] = vj[d];
-              s_tmol[tid] = wk.cent_mol[j];
-            } else s_tmol[tid] = -2;
+    double *stt = wk.xy;                                   // [ncent][PST]
+    double *vfin = wk.xy + (size_t)p.cent_cap * PST;        // [ncent][6]  final x, y
+    double rho = 0.0, bnorm = 0.0;
+    {
+      double prho = 0.0, pb = 0.0;
+      for (int c = tid; c < ncent; c += NT) {
+        double *s_ = stt + (size_t)c * PST;
+        const double *F = wk.fld + (size_t)c * 3;
+        for (int i = 0; i < 3; ++i) {
+          const double bi = s_[i];                         // alpha F (written in phase b)
+          s_[6 + i] = bi; s_[12 + i] = bi;                 // r = p = b
+          s_[9 + i] = F[i]; s_[15 + i] = F[i];             // rt = pt = F
+          s_[i] = 0.0; s_[3 + i] = 0.0;                    // x = xt = 0
+          prho += F[i] * bi; pb = fmax(pb, fmax(fabs(bi), fabs(F[i])));
+        }
+      }
+      rho = block_sum(prho, s_red);
+      bnorm = block_max(pb, s_red);
+    }
+    bool broke = false;
+    if (bnorm > 0.0) {
+      for (; iters < p.pol_maxit;) {
+        // u = p, ut = alpha^T pt
+        for (int c = tid; c < ncent; c += NT) {
+          double *s_ = stt + (size_t)c * PST;
+          const double *a = wk.cent_alpha + (size_t)c * 9;
+          for (int i = 0; i < 3; ++i) {
+            s_[18 + i] = s_[12 + i];
+            s_[21 + i] = a[i] * s_[15] + a[3 + i] * s_[16] + a[6 + i] * s_[17];
           }
-          __syncthreads();
-          if (act) {
-            const int jn = min(POL_TILE, ncent - j0);
-            for (int jj = 0; jj < jn; ++jj) {
-              if (s_tmol[jj] == mc) continue;
-              const double *tt = s_tile + jj * 10;
-              const double Rx = rc[0] - tt[0], Ry = rc[1] - tt[1], Rz = rc[2] - tt[2];
-              const double r2 = Rx * Rx + Ry * Ry + Rz * Rz;
-              const double u = rsqrt64(r2), u2 = u * u, u3 = u2 * u, t5 = 3.0 * u3 * u2;
-              const double Rxj = Rx * tt[3] + Ry * tt[4] + Rz * tt[5];
-              const double Ryj = Rx * tt[6] + Ry * tt[7] + Rz * tt[8];
-              const double fx = t5 * Rxj, fy = t5 * Ryj;
-              ax[0] += u3 * tt[3] - fx * Rx; ax[1] += u3 * tt[4] - fx * Ry; ax[2] += u3 * tt[5] - fx * Rz;
-              ay[0] += u3 * tt[6] - fy * Rx; ay[1] += u3 * tt[7] - fy * Ry; ay[2] += u3 * tt[8] - fy * Rz;
+        }
+        double pq = 0.0;
+        for (int c0 = 0; c0 < ncent; c0 += NT) {
+          const int c = c0 + tid;
+          const bool act = c < ncent;
+          double rc[3] = {0, 0, 0}; int mc = -1;
+          if (act) { rc[0] = wk.cent_pos[(size_t)c * 3]; rc[1] = wk.cent_pos[(size_t)c * 3 + 1]; rc[2] = wk.cent_pos[(size_t)c * 3 + 2]; mc = wk.cent_mol[c]; }
+          double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0};
+          for (int j0 = 0; j0 < ncent; j0 += POL_TILE) {
+            __syncthreads();
+            if (tid < POL_TILE) {
+              const int j = j0 + tid;
+              if (j < ncent) {
+                double *tt = s_tile + tid * 10;
+                tt[0] = wk.cent_pos[(size_t)j * 3]; tt[1] = wk.cent_pos[(size_t)j * 3 + 1]; tt[2] = wk.cent_pos[(size_t)j * 3 + 2];
+                const double *vj = stt + (size_t)j * PST + 18;
+                for (int d = 0; d < 6; ++d) tt[3 + d] = vj[d];
+                s_tmol[tid] = wk.cent_mol[j];
+              } else s_tmol[tid] = -2;
+            }
+            __syncthreads();
+            if (act) {
+              const int jn = min(POL_TILE, ncent - j0);
+              for (int jj = 0; jj < jn; ++jj) {
+                if (s_tmol[jj] == mc) continue;
+                const double *tt = s_tile + jj * 10;
+                const double Rx = rc[0] - tt[0], Ry = rc[1] - tt[1], Rz = rc[2] - tt[2];
+                const double r2 = Rx * Rx + Ry * Ry + Rz * Rz;
+                const double u = rsqrt64(r2), u2 = u * u, u3 = u2 * u, t5 = 3.0 * u3 * u2;
+                const double Rxj = Rx * tt[3] + Ry * tt[4] + Rz * tt[5];
+                const double Ryj = Rx * tt[6] + Ry * tt[7] + Rz * tt[8];
+                const double fx = t5 * Rxj, fy = t5 * Ryj;
+                ax[0] += u3 * tt[3] - fx * Rx; ax[1] += u3 * tt[4] - fx * Ry; ax[2] += u3 * tt[5] - fx * Rz;
+                ay[0] += u3 * tt[6] - fy * Rx; ay[1] += u3 * tt[7] - fy * Ry; ay[2] += u3 * tt[8] - fy * Rz;
+              }
+            }
+          }
+          if (act) {      // q = p + alpha (T p), qt = pt + T ut
+            double *s_ = stt + (size_t)c * PST;
+            const double *a = wk.cent_alpha + (size_t)c * 9;
+            for (int i = 0; i < 3; ++i) {
+              const double q = s_[12 + i] + a[i * 3] * ax[0] + a[i * 3 + 1] * ax[1] + a[i * 3 + 2] * ax[2];
+              const double qt = s_[15 + i] + ay[i];
+              pq += s_[15 + i] * q;
+              s_[24 + i] = q; s_[27 + i] = qt;
             }
           }
         }
-        if (act) {
-          const double *a = wk.cent_alpha + (size_t)c * 9;
-          const double *F = wk.fld + (size_t)c * 3;
-          const double bx[3] = {F[0] - ax[0], F[1] - ax[1], F[2] - ax[2]}, by[3] = {F[0] - ay[0], F[1] - ay[1], F[2] - ay[2]};
-          const double *vo = vin + (size_t)c * 6;
-          double *vn = vout + (size_t)c * 6;
+        pq = block_sum(pq, s_red);
+        ++iters;
+        if (!(fabs(pq) > 0.0) || !isfinite(pq)) { broke = true; break; }
+        const double al = rho / pq;
+        double prho = 0.0, pr = 0.0;
+        for (int c = tid; c < ncent; c += NT) {
+          double *s_ = stt + (size_t)c * PST;
           for (int i = 0; i < 3; ++i) {
-            const double xn = a[i * 3] * bx[0] + a[i * 3 + 1] * bx[1] + a[i * 3 + 2] * bx[2];
-            const double yn = a[i] * by[0] + a[3 + i] * by[1] + a[6 + i] * by[2];
-            dmax = fmax(dmax, fmax(fabs(xn - vo[i]), fabs(yn - vo[3 + i])));
-            vmax = fmax(vmax, fmax(fabs(xn), fabs(yn)));
-            vn[i] = xn; vn[3 + i] = yn;
+            s_[i] += al * s_[12 + i]; s_[3 + i] += al * s_[15 + i];
+            const double r = s_[6 + i] - al * s_[24 + i], rt = s_[9 + i] - al * s_[27 + i];
+            s_[6 + i] = r; s_[9 + i] = rt;
+            prho += rt * r; pr = fmax(pr, fmax(fabs(r), fabs(rt)));
           }
         }
+        const double rho1 = block_sum(prho, s_red);
+        resid = block_max(pr, s_red) / bnorm;
+        if (!(resid > p.pol_tol)) break;
+        if (!(fabs(rho) > 0.0) || !isfinite(rho1)) { broke = true; break; }
+        const double be = rho1 / rho;
+        rho = rho1;
+        for (int c = tid; c < ncent; c += NT) {
+          double *s_ = stt + (size_t)c * PST;
+          for (int i = 0; i < 3; ++i) { s_[12 + i] = s_[6 + i] + be * s_[12 + i]; s_[15 + i] = s_[9 + i] + be * s_[15 + i]; }
+        }
       }
-      dmax = block_max(dmax, s_red);
-      vmax = block_max(vmax, s_red);
-      cur ^= 1;
-      resid = vmax > 0.0 ? dmax / vmax : 0.0;
-      if (!(resid > p.pol_tol)) { ++iters; break; }
+    } else resid = 0.0;
+    for (int c = tid; c < ncent; c += NT) {       // x, and y = alpha^T xt
+      const double *s_ = stt + (size_t)c * PST;
+      const double *a = wk.cent_alpha + (size_t)c * 9;
+      double *v = vfin + (size_t)c * 6;
+      for (int i = 0; i < 3; ++i) {
+        v[i] = s_[i];
+        v[3 + i] = a[i] * s_[3] + a[3 + i] * s_[4] + a[6 + i] * s_[5];
+      }
     }
     __syncthreads();
-    const double *vxy = wk.xy + cur * bstride;
+    const double *vxy = vfin;
+    if (broke) resid = 1.0;
 
     // ---- (d) contractions with the solute rows: y^T dD x - (x+y).dF
     // solute tables in shared memory: centres [npolc][21]: pos3 r1(3) G(9) x3 y3 ; sites [ndmac][46]: pos3 mom20 dma1(20) L3

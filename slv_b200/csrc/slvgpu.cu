@@ -93,7 +93,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   p.ntypes = d->ntypes; p.ninst = d->ninst; p.natoms_total = d->natoms_total; p.flags = d->flags;
   p.ccut = d->ccut; p.pcut = d->pcut; p.ecut = d->ecut;
   p.pol_maxit = d->pol_maxit > 0 ? d->pol_maxit : 200;
-  p.pol_tol = d->pol_tol > 0 ? d->pol_tol : 1e-13;
+  p.pol_tol = d->pol_tol > 0 ? d->pol_tol : 1e-12;
   int rc = 0;
 #define TRY(x) do { rc = (x); if (rc) { slvgpu_plan_destroy(pl); return rc; } } while (0)
   TRY(upload(pl, &p.type_meta, d->type_meta, (size_t)d->ntypes * SLVGPU_NMETA));
@@ -166,7 +166,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
     TRY(dalloc(pl, &pl->pw.cent_pos, nc * cc * 3));
     TRY(dalloc(pl, &pl->pw.cent_alpha, nc * cc * 9));
     TRY(dalloc(pl, &pl->pw.fld, nc * cc * 3));
-    TRY(dalloc(pl, &pl->pw.xy, nc * cc * 12));
+    TRY(dalloc(pl, &pl->pw.xy, nc * cc * (PST + 6)));
     TRY(dalloc(pl, &pl->pw.site, nc * (size_t)p.site_cap * SITE_ROW));
     TRY(dalloc(pl, &pl->pw.cent_mol, nc * cc));
     TRY(dalloc(pl, &pl->pw.ent_coff, nc * (size_t)p.list_cap));

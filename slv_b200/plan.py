@@ -157,7 +157,7 @@ class Plan(object):
 
     def __del__(self):
         h = getattr(self, '_h', None)
-        if h:
+        if h and _lib is not None and getattr(_lib, 'lib', None) is not None:
             _lib.lib.slvgpu_plan_destroy(h)
             self._h = None
 
