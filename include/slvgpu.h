@@ -131,6 +131,13 @@ int slvgpu_eval_frames_host(slvgpu_plan *plan, const double *h_coords, int64_t n
 /* Number of kernel launches issued by the last slvgpu_eval_frames* call on this plan. */
 int64_t slvgpu_last_launches(const slvgpu_plan *plan);
 
+/* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel of
+ * slvgpu_eval_frames*): kernels 0 = superimposition+electrostatics, 1 = dispersion, 2 = polarisation,
+ * 3 = exchange-repulsion.  get_timing synchronises and returns accumulated ms and launch counts since
+ * set_timing(plan, 1). */
+int slvgpu_set_timing(slvgpu_plan *plan, int on);
+int slvgpu_get_timing(slvgpu_plan *plan, double *ms4, int64_t *launches4);
+
 /* Optional per-frame detail of the LAST evaluated frame range: induced dipoles and fields at the
  * polarisable centres (EFP.get_dipind / get_fields, solvshift/solefp.py:303-313).  Buffers are
  * [ncent][3]; returns the number of centres written, or a negative error. */

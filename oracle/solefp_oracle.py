@@ -411,7 +411,7 @@ def pol_shift(parc, solv, mode, literal_gemm=False):
 
 # --------------------------------------------------------------------------- one frame, all terms
 def eval_frame(pos, ind, nmol, pars, supl, reord, mode, ccut=1e10, pcut=1e10, ecut=1e10,
-               elect=True, ea=True, corr=True, pol=False, disp=False, rep=False, rep_fn=None):
+               elect=True, ea=True, corr=True, pol=False, disp=False, rep=False, rep_fn=None, literal_gemm=False):
     """EFP.set + EFP.eval(0) for one frame in central mode (solefp.py:223-277, 738-787, 1011-1629).
     pars: list of parameter dicts (Frag.get()); returns a dict of a.u. terms + rms values."""
     ind = np.asarray(ind, int); nmol = np.asarray(nmol, int)
@@ -441,7 +441,7 @@ def eval_frame(pos, ind, nmol, pars, supl, reord, mode, ccut=1e10, pcut=1e10, ec
         if pol or disp:
             lay_p = [sup(i + 1)[0] for i in np.nonzero(ipm)[0]]
         if pol:
-            sh, fip, dip, av = pol_shift(parc, lay_p, mode)
+            sh, fip, dip, av = pol_shift(parc, lay_p, mode, literal_gemm=literal_gemm)
             out.update(pol_mea=sh, fi_pol=fip, dipind=dip, avec=av)
         if disp:
             iso, ani = disp_shifts(parc, lay_p, mode)

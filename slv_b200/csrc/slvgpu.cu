@@ -42,6 +42,10 @@ struct slvgpu_plan {
   int64_t stage_frames = 0;
   int64_t last_launches = 0;
   cudaStream_t own_stream = nullptr;
+  int timing = 0;
+  std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  std::vector<int> ev_kind;            // kernel id of each (start, stop) pair in use
+  double t_acc[4] = {0, 0, 0, 0}; int64_t t_cnt[4] = {0, 0, 0, 0};
 };
 
 template <class T>
@@ -67,8 +71,43 @@ static int upload(slvgpu_plan *pl, const T **dptr, const T *h, size_t n) {
 extern "C" const char *slvgpu_last_error(void) { return g_err.c_str(); }
 extern "C" const char *slvgpu_version(void) { return "slvgpu 0.1 (sm_100a)"; }
 
+static void ev_begin(slvgpu_plan *pl, int kind, cudaStream_t st) {
+  if (!pl->timing) return;
+  if (pl->ev_used + 2 > pl->ev_pool.size()) {
+    for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); pl->ev_pool.push_back(e); }
+  }
+  cudaEventRecord(pl->ev_pool[pl->ev_used], st);
+  pl->ev_kind.push_back(kind);
+}
+static void ev_end(slvgpu_plan *pl, cudaStream_t st) {
+  if (!pl->timing) return;
+  cudaEventRecord(pl->ev_pool[pl->ev_used + 1], st);
+  pl->ev_used += 2;
+}
+
+extern "C" int slvgpu_set_timing(slvgpu_plan *pl, int on) {
+  if (!pl) return fail(SLVGPU_EINVAL, "null plan");
+  pl->timing = on; pl->ev_used = 0; pl->ev_kind.clear();
+  for (int k = 0; k < 4; ++k) { pl->t_acc[k] = 0; pl->t_cnt[k] = 0; }
+  return 0;
+}
+
+extern "C" int slvgpu_get_timing(slvgpu_plan *pl, double *ms4, int64_t *launches4) {
+  if (!pl || !ms4 || !launches4) return fail(SLVGPU_EINVAL, "null argument");
+  CK(cudaDeviceSynchronize());
+  for (size_t i = 0; i < pl->ev_kind.size(); ++i) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, pl->ev_pool[2 * i], pl->ev_pool[2 * i + 1]));
+    pl->t_acc[pl->ev_kind[i]] += ms; pl->t_cnt[pl->ev_kind[i]] += 1;
+  }
+  pl->ev_used = 0; pl->ev_kind.clear();
+  for (int k = 0; k < 4; ++k) { ms4[k] = pl->t_acc[k]; launches4[k] = pl->t_cnt[k]; }
+  return 0;
+}
+
 extern "C" void slvgpu_plan_destroy(slvgpu_plan *pl) {
   if (!pl) return;
+  for (cudaEvent_t e : pl->ev_pool) cudaEventDestroy(e);
   for (void *q : pl->allocs) cudaFree(q);
   if (pl->d_stage_coords) cudaFree(pl->d_stage_coords);
   if (pl->d_stage_out) cudaFree(pl->d_stage_out);
@@ -210,20 +249,28 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
   const size_t sm_po = ((size_t)pl->npolc * 21 + (size_t)pl->ndmac * 46) * sizeof(double);
   for (int64_t f0 = 0; f0 < nframes; f0 += pl->max_chunk) {
     const int nf = (int)((nframes - f0) < pl->max_chunk ? (nframes - f0) : pl->max_chunk);
+    ev_begin(pl, 0, st);
     k_frame_elect<<<nf, ELECT_THREADS, sm_el, st>>>(p, d_coords, (int)f0, pl->fl, d_out);
+    ev_end(pl, st);
     ++pl->last_launches;
     if ((p.flags & SLVGPU_DISP) && p.ninst > 1) {
+      ev_begin(pl, 1, st);
       k_disp<<<nf, DISP_THREADS, sm_di, st>>>(p, (int)f0, pl->fl, d_out);
+      ev_end(pl, st);
       ++pl->last_launches;
     }
     if ((p.flags & SLVGPU_POL) && p.ninst > 1) {
       const int g = nf < pl->pol_ctas ? nf : pl->pol_ctas;
+      ev_begin(pl, 2, st);
       k_pol<<<g, POL_THREADS, sm_po, st>>>(p, (int)f0, nf, pl->fl, pl->pw, d_out, d_status, pl->d_detail);
+      ev_end(pl, st);
       ++pl->last_launches;
     }
     if ((p.flags & SLVGPU_REP) && p.ninst > 1) {
       const int g = nf < pl->rep_ctas ? nf : pl->rep_ctas;
+      ev_begin(pl, 3, st);
       k_rep<<<g, REP_THREADS, rep_smem_bytes(pl->nmosc, pl->max_nmos, pl->natc, pl->max_nat), st>>>(p, (int)f0, nf, pl->fl, pl->rw, d_out);
+      ev_end(pl, st);
       ++pl->last_launches;
     }
   }

@@ -197,6 +197,15 @@ class Plan(object):
         _lib.check(_lib.lib.slvgpu_eval_frames_host(self._h, cptr, nf, optr, sptr))
         return out, status
 
+    def set_timing(self, on=True):
+        _lib.check(_lib.lib.slvgpu_set_timing(self._h, int(on)))
+
+    def get_timing(self):
+        """{kernel: (ms, launches)} accumulated since set_timing(True)."""
+        ms = numpy.zeros(4); n = numpy.zeros(4, numpy.int64)
+        _lib.check(_lib.lib.slvgpu_get_timing(self._h, ms.ctypes.data, n.ctypes.data))
+        return dict((k, (float(ms[i]), int(n[i]))) for i, k in enumerate(('k_frame_elect', 'k_disp', 'k_pol', 'k_rep')))
+
     def last_launches(self):
         return int(_lib.lib.slvgpu_last_launches(self._h))
 
