@@ -19,7 +19,7 @@
 namespace slv {
 
 constexpr int POL_THREADS = 512;
-constexpr int POL_TILE = 128;
+constexpr int POL_TILE = 512;    // centres staged per shared-memory tile of the sweep (== POL_THREADS)
 constexpr int SITE_ROW = 24;     // pos3, mom20, molecule id
 constexpr int PST = 30;          // BiCG state per centre: x xt r rt p pt u ut q qt (3 each)
 
@@ -36,12 +36,13 @@ struct PolWork {                 // per-CTA workspace (device pointers already o
 
 __global__ void __launch_bounds__(POL_THREADS)
 k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, double *__restrict__ out, int *__restrict__ status,
-      double *__restrict__ detail /* optional [nframes][cent_cap][9]: dipind, flds, rpol */) {
+      double *__restrict__ detail /* optional [nframes][cent_cap][9]: dipind, flds, rpol */, int *__restrict__ queue) {
   __shared__ double s_red[32];
-  __shared__ double s_tile[POL_TILE * 10];
   __shared__ int s_tmol[POL_TILE];
+  __shared__ int s_fi;
   __shared__ int s_n[4];
-  extern __shared__ double sm[];    // solute tables for the contraction phase
+  extern __shared__ double sm[];    // [POL_TILE*10] sweep tile, then the solute tables of the contraction phase
+  double *s_tile = sm;
 
   PolWork wk = wk0;
   {
@@ -55,7 +56,14 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
   const int npolc = tm0[SLVGPU_M_NPOL], ndmac = tm0[SLVGPU_M_NDMA];
   const int tid = threadIdx.x, NT = blockDim.x;
 
-  for (int fi = blockIdx.x; fi < nframes; fi += gridDim.x) {
+  for (;;) {
+    // frames are handed out dynamically: their cost varies with the number of centres inside pcut and the
+    // BiCG iteration count, so a static round-robin leaves SMs idle at the tail
+    __syncthreads();
+    if (tid == 0) s_fi = atomicAdd(queue, 1);
+    __syncthreads();
+    const int fi = s_fi;
+    if (fi >= nframes) break;
     const int nl = fl.nlist[fi];
     const size_t lbase = (size_t)fi * p.list_cap;
     // ---- (a) offsets of every pol-layer entry, then the lab-frame centre and site tables
@@ -189,12 +197,14 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
             __syncthreads();
             if (act) {
               const int jn = min(POL_TILE, ncent - j0);
+#pragma unroll 4
               for (int jj = 0; jj < jn; ++jj) {
-                if (s_tmol[jj] == mc) continue;
+                const bool same = (s_tmol[jj] == mc);          // same molecule (incl. self): no interaction, branch-free
                 const double *tt = s_tile + jj * 10;
                 const double Rx = rc[0] - tt[0], Ry = rc[1] - tt[1], Rz = rc[2] - tt[2];
-                const double r2 = Rx * Rx + Ry * Ry + Rz * Rz;
-                const double u = rsqrt64(r2), u2 = u * u, u3 = u2 * u, t5 = 3.0 * u3 * u2;
+                const double r2 = same ? 1.0 : (Rx * Rx + Ry * Ry + Rz * Rz);
+                const double u = rsqrt64(r2), u2 = u * u;
+                const double u3 = same ? 0.0 : u2 * u, t5 = 3.0 * u3 * u2;
                 const double Rxj = Rx * tt[3] + Ry * tt[4] + Rz * tt[5];
                 const double Ryj = Rx * tt[6] + Ry * tt[7] + Rz * tt[8];
                 const double fx = t5 * Rxj, fy = t5 * Ryj;
@@ -255,7 +265,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
 
     // ---- (d) contractions with the solute rows: y^T dD x - (x+y).dF
     // solute tables in shared memory: centres [npolc][21]: pos3 r1(3) G(9) x3 y3 ; sites [ndmac][46]: pos3 mom20 dma1(20) L3
-    double *s_c = sm, *s_s = sm + (size_t)npolc * 21;
+    double *s_c = sm + POL_TILE * 10, *s_s = s_c + (size_t)npolc * 21;
     {
       const double *sx = fl.sol_xf + (size_t)fi * 12;
       double R[9];

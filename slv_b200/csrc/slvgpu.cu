@@ -36,6 +36,7 @@ struct slvgpu_plan {
   PolWork pw{};
   RepWork rw{};
   double *d_detail = nullptr;
+  int *d_queue = nullptr;
   int detail_frames = 0;
   int want_detail = 0;
   double *d_stage_coords = nullptr, *d_stage_out = nullptr; int *d_stage_status = nullptr;
@@ -194,6 +195,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   pl->max_chunk = d->max_chunk > 0 ? d->max_chunk : 1024;
   pl->want_detail = d->want_detail;
   const size_t ch = (size_t)pl->max_chunk;
+  TRY(dalloc(pl, &pl->d_queue, 4));
   TRY(dalloc(pl, &pl->fl.sol_xf, ch * 12));
   TRY(dalloc(pl, &pl->fl.nlist, ch));
   TRY(dalloc(pl, &pl->fl.list_inst, ch * p.list_cap));
@@ -246,7 +248,7 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
   CK(cudaMemsetAsync(d_status, 0, (size_t)nframes * sizeof(int32_t), st));
   const size_t sm_el = (size_t)pl->ndmac * SOLROW * sizeof(double);
   const size_t sm_di = ((size_t)pl->npolc * DISP_SOLROW + 108 * DISP_THREADS) * sizeof(double);
-  const size_t sm_po = ((size_t)pl->npolc * 21 + (size_t)pl->ndmac * 46) * sizeof(double);
+  const size_t sm_po = ((size_t)POL_TILE * 10 + (size_t)pl->npolc * 21 + (size_t)pl->ndmac * 46) * sizeof(double);
   for (int64_t f0 = 0; f0 < nframes; f0 += pl->max_chunk) {
     const int nf = (int)((nframes - f0) < pl->max_chunk ? (nframes - f0) : pl->max_chunk);
     ev_begin(pl, 0, st);
@@ -262,7 +264,8 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
     if ((p.flags & SLVGPU_POL) && p.ninst > 1) {
       const int g = nf < pl->pol_ctas ? nf : pl->pol_ctas;
       ev_begin(pl, 2, st);
-      k_pol<<<g, POL_THREADS, sm_po, st>>>(p, (int)f0, nf, pl->fl, pl->pw, d_out, d_status, pl->d_detail);
+      CK(cudaMemsetAsync(pl->d_queue, 0, sizeof(int), st));
+      k_pol<<<g, POL_THREADS, sm_po, st>>>(p, (int)f0, nf, pl->fl, pl->pw, d_out, d_status, pl->d_detail, pl->d_queue);
       ev_end(pl, st);
       ++pl->last_launches;
     }
