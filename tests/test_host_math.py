@@ -1,0 +1,110 @@
+"""The __host__ __device__ math of slv_b200/csrc/slv_math.cuh, compiled for the host
+(tests/libhostmath.so, built by __graft_entry__.build()), against the oracle."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBP = os.path.join(HERE, 'libhostmath.so')
+pytestmark = pytest.mark.skipif(not os.path.isfile(LIBP), reason='tests/libhostmath.so not built')
+P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope='module')
+def L():
+    lib = ctypes.CDLL(LIBP)
+    lib.hm_site_field.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
+    lib.hm_site_dfield.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
+    return lib
+
+
+def _rows(par, sfx=''):
+    from slv_b200.slvpar import traceless
+    qt, ot = traceless(par['dmaq' + sfx], par['dmao' + sfx])
+    return np.ascontiguousarray(np.concatenate([par['dmac' + sfx][..., None], par['dmad' + sfx], qt, ot], -1))
+
+
+@pytest.mark.parametrize('name,sel', [('water', None), ('nma', [1, 7, 2, 4]), ('dmso', None)])
+def test_kabsch_matches_svd(L, frags, name, sel):
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O
+    rng = np.random.default_rng(0)
+    ref = frags(name).get()['pos']
+    ref = ref if sel is None else ref[sel]
+    worst = 0.0
+    for t in range(100):
+        Rt = synth.random_rotations(rng, 1)[0]
+        tgt = ref @ Rt + rng.normal(0, 3, 3) + rng.normal(0, 0.03, ref.shape)
+        rot, tr, rms = O.kabsch(ref, tgt)
+        c = ref - ref.mean(0); r = tgt - tgt.mean(0)
+        a = np.ascontiguousarray(c.T @ r); out = np.zeros(9)
+        L.hm_kabsch_rot(P(a), P(out))
+        worst = max(worst, np.abs(out.reshape(3, 3) - rot).max())
+    assert worst < 1e-12
+
+
+def test_kabsch_large_rotation_and_reflection_guard(L):
+    """180-degree rotations and mirror-image targets: the result is always a proper rotation."""
+    from oracle import solefp_oracle as O
+    ref = np.array([[0.0, 0.2, 0.0], [1.4, -0.85, 0.0], [-1.4, -0.85, 0.0], [0.3, 0.1, 0.9]])
+    for Rt in (np.diag([-1.0, -1.0, 1.0]), np.diag([1.0, 1.0, -1.0])):
+        tgt = ref @ Rt
+        rot, tr, rms = O.kabsch(ref, tgt)
+        c = ref - ref.mean(0); r = tgt - tgt.mean(0)
+        out = np.zeros(9); L.hm_kabsch_rot(P(np.ascontiguousarray(c.T @ r)), P(out))
+        out = out.reshape(3, 3)
+        assert abs(np.linalg.det(out) - 1.0) < 1e-12
+        assert np.abs(out - rot).max() < 1e-10
+
+
+def test_moment_and_matrix_rotation(L, frags):
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O
+    par = frags('dmso').get()
+    Rt = np.ascontiguousarray(synth.random_rotations(np.random.default_rng(1), 1)[0])
+    p2 = O.sup_params(par, Rt, np.zeros(3))
+    m, m2 = _rows(par), _rows(p2)
+    for i in range(len(m)):
+        o = np.zeros(20); L.hm_rot_mom20(P(Rt), P(np.ascontiguousarray(m[i])), P(o))
+        assert np.abs(o - m2[i]).max() < 1e-13
+    for i in range(par['npol']):
+        o = np.zeros(9); L.hm_rot_mat(P(Rt), P(np.ascontiguousarray(par['dpol'][i].ravel())), P(o))
+        assert np.abs(o.reshape(3, 3) - p2['dpol'][i]).max() < 1e-13
+
+
+def test_pair_potentials_energy_and_charge_field(L, frags):
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O
+    A = frags('nma').get()
+    Rt = synth.random_rotations(np.random.default_rng(2), 1)[0]
+    B = O.sup_params(frags('water').get(), Rt, np.array([8.0, 1.0, -2.0]))
+    qA, muA, ThA, OmA = O._lab_moments(A); qB, muB, ThB, OmB = O._lab_moments(B)
+    e_ref = O.emtp_r4(A['rdma'], qA, muA, ThA, OmA, B['rdma'], qB, muB, ThB, OmB)
+    sA, mB = _rows(A), _rows(B)
+    e = 0.0; G = np.zeros((12, 3))
+    for i in range(12):
+        s = sA[i].copy(); L.hm_fold20(P(s))
+        for j in range(5):
+            Pv = np.zeros(23)
+            L.hm_pair_potentials(P(np.ascontiguousarray(A['rdma'][i])), P(np.ascontiguousarray(B['rdma'][j])), P(np.ascontiguousarray(mB[j])), P(Pv))
+            e += s @ Pv[:20]; G[i] += Pv[20:]
+    assert abs(e - e_ref) < 1e-15 + 1e-12 * abs(e_ref)
+    R = A['rdma'][:, None, :] - B['rdma'][None, :, :]
+    Gref = -(qB[None, :, None] * R / ((R * R).sum(-1) ** 1.5)[..., None]).sum(1)
+    assert np.abs(G - Gref).max() < 1e-14
+
+
+def test_field_and_field_derivative(L, frags):
+    from oracle import solefp_oracle as O
+    par = frags('nma').get(); m = _rows(par)
+    q, mu, Th, Om = O._lab_moments(par)
+    rng = np.random.default_rng(1)
+    for s in range(12):
+        R = rng.normal(0, 4, 3); v = rng.normal(0, 1, 3)
+        for fac in (5.0, 7.0):
+            F = np.zeros(3); L.hm_site_field(P(R), P(np.ascontiguousarray(m[s])), fac, P(F))
+            assert np.abs(F - O._field_traceless(R, q[s], mu[s], Th[s], Om[s], fac)).max() < 1e-15
+        F = np.zeros(3); L.hm_site_dfield(P(R), P(v), P(np.ascontiguousarray(m[s])), 1.0, P(F))
+        assert np.abs(F - O._dfield_traceless(R, v, q[s], mu[s], Th[s], Om[s])).max() < 1e-15
