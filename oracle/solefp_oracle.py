@@ -411,7 +411,7 @@ def pol_shift(parc, solv, mode, literal_gemm=False):
 
 # --------------------------------------------------------------------------- one frame, all terms
 def eval_frame(pos, ind, nmol, pars, supl, reord, mode, ccut=1e10, pcut=1e10, ecut=1e10,
-               elect=True, ea=True, corr=True, pol=False, disp=False, rep=False, rep_fn=None, literal_gemm=False):
+               elect=True, ea=True, corr=True, pol=False, disp=False, rep=False, make_basis=None, literal_gemm=False):
     """EFP.set + EFP.eval(0) for one frame in central mode (solefp.py:223-277, 738-787, 1011-1629).
     pars: list of parameter dicts (Frag.get()); returns a dict of a.u. terms + rms values."""
     ind = np.asarray(ind, int); nmol = np.asarray(nmol, int)
@@ -424,8 +424,10 @@ def eval_frame(pos, ind, nmol, pars, supl, reord, mode, ccut=1e10, pcut=1e10, ec
         ro = reord[t] if reord is not None and reord[t] is not None else np.arange(p['natoms'])
         sl = supl[t] if supl is not None else None
         r, tr, rms = kabsch(p['pos'], reorder_xyz(xyz[i], ro), sl)
+        rots[i] = r
         return sup_params(p, r, tr), rms
 
+    rots = {}
     parc, rms_c = sup(0)
     out = dict(ele_mea=0.0, ele_ea=0.0, cor_mea=0.0, cor_ea=0.0, pol_mea=0.0, rep_mea=0.0, dis_mea=0.0, dis_mea_iso=0.0)
     lay_c = [sup(i + 1) for i in np.nonzero(icm)[0]]
@@ -447,6 +449,81 @@ def eval_frame(pos, ind, nmol, pars, supl, reord, mode, ccut=1e10, pcut=1e10, ec
             iso, ani = disp_shifts(parc, lay_p, mode)
             out.update(dis_mea=ani, dis_mea_iso=iso)
     if rep:
-        lay_e = [sup(i + 1)[0] for i in np.nonzero(iem)[0]]
-        out['rep_mea'] = rep_fn(parc, lay_e, mode) if lay_e else 0.0
+        ie = [i + 1 for i in np.nonzero(iem)[0]]
+        lay_e = [sup(i)[0] for i in ie]
+        if lay_e:
+            out['rep_mea'], out['fi_rep'] = rep_shift(parc, lay_e, mode, make_basis, rots[0], [rots[i] for i in ie])
     return out
+
+
+# --------------------------------------------------------------------------- exchange-repulsion
+def vecrot(vec, rot, typ):
+    """VECROT / VC1ROT (efprot.f:22-283): rotate AO->LMO coefficient rows [..., nbasis].  p triples as
+    vectors; d sextets (xx yy zz xy xz yz) as the symmetric matrix whose off-diagonals ARE the xy/xz/yz
+    coefficients (so they are counted twice in R^T M R -- the reference's convention, efprot.f:78-136)."""
+    out = np.array(vec, float, copy=True)
+    k = 0; n = len(typ)
+    while k < n:
+        if typ[k] == 1:
+            out[..., k:k + 3] = vec[..., k:k + 3] @ rot
+            k += 3
+        elif typ[k] == 2:
+            M = quad_full(vec[..., k:k + 6])
+            out[..., k:k + 6] = quad_reduced(np.einsum('ai,...ab,bj->...ij', rot, M, rot))
+            k += 6
+        else:
+            k += 1
+    return out
+
+
+def rep_shift(parc, solv, mode, make_basis, rotc=None, rots=None, par0c=None, par0s=None):
+    """rep_mea (a.u.) and fi_rep[nmodes]: SHFTEX = CALCIJ + CALCFI (shftex.f:12-438) summed over the solvent
+    molecules of the EXREP layer (solefp.py:1497-1560), integrals from oracle/ints_oracle.py.
+    parc/solv are superimposed dicts that still carry UNROTATED wave-function arrays; rotc / rots are the
+    rotations of their superimpositions (sup_params does not touch vecl/vecl1).  make_basis(atno, pos)
+    returns the basis tables (slv_b200.basis.BasisSet layout)."""
+    from . import ints_oracle as IO
+    w, den = mode_weights(parc, mode)
+    nmodes = len(w)
+    bA = make_basis(parc['atno'], parc['pos'])
+    typA = bA.powers.sum(1)
+    CA = vecrot(parc['vecl'], rotc, typA); CA1 = vecrot(parc['vecl1'], rotc, typA)
+    FA, FA1 = parc['fock'], parc['fock1']
+    riA, riA1, rnA, L = parc['lmoc'], parc['lmoc1'], parc['pos'], parc['lvec']
+    ZA = np.asarray(parc['atno'], float)
+    atomA = bA.center
+    fi = np.zeros(nmodes)
+    for pb, rb in zip(solv, rots):
+        bB = make_basis(pb['atno'], pb['pos'])
+        CB = vecrot(pb['vecl'], rb, bB.powers.sum(1))
+        S, T, S1, T1 = IO.one_electron(bA, parc['pos'], bB, pb['pos'])
+        FB = pb['fock']; riB = pb['lmoc']; rnB = pb['pos']; ZB = np.asarray(pb['atno'], float)
+        Sij = CA @ S @ CB.T; Tij = CA @ T @ CB.T
+        dS = np.einsum('mka,kla->mkl', L[:, atomA, :], S1); dT = np.einsum('mka,kla->mkl', L[:, atomA, :], T1)
+        Sm = np.einsum('ik,mkl,jl->mij', CA, dS, CB) + np.einsum('mik,kl,jl->mij', CA1, S, CB)
+        Tm = np.einsum('ik,mkl,jl->mij', CA, dT, CB) + np.einsum('mik,kl,jl->mij', CA1, T, CB)
+        Rij = riA[:, None, :] - riB[None, :, :]; rij = np.linalg.norm(Rij, axis=-1)         # [i,j]
+        rm_ij = np.einsum('ija,mia->mij', Rij, riA1) / rij
+        sl = np.log(np.abs(Sij)); aux = 2.0 * np.sqrt(-2.0 * sl / np.pi)
+        sdr = Sij / rij
+        TS1 = 4.0 * sdr * Sm * (np.sqrt(-1.0 / (2.0 * np.pi * sl)) - aux - 1.0)
+        TS2 = 2.0 * sdr * sdr * rm_ij * (aux + 1.0)
+        TS3 = 4.0 * Sm * Tij; TS4 = 4.0 * Tm * Sij
+        # TA1: sum over k in A (distances r_kj)
+        TA1 = (-2.0 * Sm * (FA @ Sij)
+               + 8.0 * Sij * Sm * (1.0 / rij).sum(0)[None, :]
+               - 2.0 * Sij * (np.einsum('mik,kj->mij', FA1, Sij) + np.einsum('ik,mkj->mij', FA, Sm))
+               - 4.0 * Sij ** 2 * (rm_ij / rij ** 2).sum(1)[:, None, :])
+        # TA2: sum over l in B (distances r_il)
+        TA2 = (-2.0 * Sm * (Sij @ FB.T)
+               + 8.0 * Sij * Sm * (1.0 / rij).sum(1)[:, None]
+               - 2.0 * Sij * np.einsum('jl,mil->mij', FB, Sm)
+               - 4.0 * Sij ** 2 * (rm_ij / rij ** 2).sum(2)[:, :, None])
+        Rxj = rnA[:, None, :] - riB[None, :, :]; rxj = np.linalg.norm(Rxj, axis=-1)           # [x,j]
+        rm_xj = np.einsum('xja,mxa->mxj', Rxj, L) / rxj
+        TA3 = 2.0 * Sij ** 2 * (ZA[:, None] * rm_xj / rxj ** 2).sum(1)[:, None, :] - 4.0 * Sij * Sm * (ZA[:, None] / rxj).sum(0)[None, :]
+        Riy = riA[:, None, :] - rnB[None, :, :]; riy = np.linalg.norm(Riy, axis=-1)           # [i,y]
+        rm_iy = np.einsum('iya,mia->miy', Riy, riA1) / riy
+        TA4 = 2.0 * Sij ** 2 * (ZB[None, :] * rm_iy / riy ** 2).sum(2)[:, :, None] - 4.0 * Sij * Sm * (ZB[None, :] / riy).sum(1)[:, None]
+        fi += (TS1 + TS2 + TS3 + TS4 + TA1 + TA2 + TA3 + TA4).sum((1, 2))
+    return -(w * fi).sum() / den, fi

@@ -1,0 +1,95 @@
+// slv_ints.cuh -- one-electron integrals over contracted Cartesian Gaussians (s, p, d) for the
+// exchange-repulsion shift: overlap S, kinetic T = <k|-1/2 del^2|l>, and their derivatives with respect
+// to the centre of the bra function contracted with a displacement vector L (the normal-mode direction
+// of the bra's atom).  Replaces PyQuante.Ints.getSAB/getTAB/getSA1B/getTA1B at the reference call sites
+// solvshift/solefp.py:1523-1526 (PyQuante "1.0.3-BBG" is un-vendored; convention: each primitive and each
+// contracted Cartesian component normalised, see slv_b200/basis.py).  Obara-Saika 1-D recursions; the
+// 4x5 table per axis is built unconditionally and the entries a given (l_bra, l_ket) needs are picked
+// with selects, so the code is branch-free across mixed s/p/d pairs.  __host__ __device__ for host checks.
+#pragma once
+#include "slv_math.cuh"
+
+namespace slv {
+
+SLV_HD double sel3(int i, double v0, double v1, double v2) { return i == 0 ? v0 : (i == 1 ? v1 : v2); }
+
+// For one axis: s(i,j) = int (x-A)^i (x-B)^j exp(-a(x-A)^2 - b(x-B)^2) dx / s(0,0).
+// Returns overlap factors S0 = s(la,lb), Sp = s(la+1,lb), Sm = s(la-1,lb) and the matching kinetic
+// factors t(i,lb) = b(2lb+1) s(i,lb) - 2b^2 s(i,lb+2) - lb(lb-1)/2 s(i,lb-2).
+SLV_HD void axis_factors(double PA, double PB, double h, double b, int la, int lb,
+                         double &S0, double &Sp, double &Sm, double &T0, double &Tp, double &Tm) {
+  double s[4][5];
+  s[0][0] = 1.0;
+  s[0][1] = PB;
+#pragma unroll
+  for (int j = 1; j < 4; ++j) s[0][j + 1] = PB * s[0][j] + h * j * s[0][j - 1];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      double v = PA * s[i][j];
+      if (i > 0) v += h * i * s[i - 1][j];
+      if (j > 0) v += h * j * s[i][j - 1];
+      s[i + 1][j] = v;
+    }
+  }
+  // rows la-1, la, la+1 for the three columns lb-2, lb, lb+2
+  double r0[3], rp[3], rm[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    // column index: c=0 -> lb-2 (exists only for lb=2: column 0), c=1 -> lb, c=2 -> lb+2
+    double col[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      col[i] = (c == 0) ? (lb == 2 ? s[i][0] : 0.0) : (c == 1) ? sel3(lb, s[i][0], s[i][1], s[i][2]) : sel3(lb, s[i][2], s[i][3], s[i][4]);
+    r0[c] = sel3(la, col[0], col[1], col[2]);
+    rp[c] = sel3(la, col[1], col[2], col[3]);
+    rm[c] = sel3(la, 0.0, col[0], col[1]);
+  }
+  const double k0 = b * (2.0 * lb + 1.0), k2 = -2.0 * b * b, km = -0.5 * lb * (lb - 1.0);
+  S0 = r0[1]; Sp = rp[1]; Sm = rm[1];
+  T0 = k0 * r0[1] + k2 * r0[2] + km * r0[0];
+  Tp = k0 * rp[1] + k2 * rp[2] + km * rp[0];
+  Tm = k0 * rm[1] + k2 * rm[2] + km * rm[0];
+}
+
+// Integrals between contracted functions k (centre A, powers la[3], npa primitives ea/ca) and l (centre B, ...).
+// out[0] = S, out[1] = T, out[2] = L . dS/dA, out[3] = L . dT/dA.
+SLV_HD void ao_pair(const double A[3], const int la[3], int npa, const double *ea, const double *ca,
+                    const double B[3], const int lb[3], int npb, const double *eb, const double *cb,
+                    const double L[3], double out[4]) {
+  const double ABx = A[0] - B[0], ABy = A[1] - B[1], ABz = A[2] - B[2];
+  const double AB2 = ABx * ABx + ABy * ABy + ABz * ABz;
+  double S = 0.0, T = 0.0, dS = 0.0, dT = 0.0;
+  for (int p = 0; p < npa; ++p) {
+    const double a = ea[p];
+    for (int q = 0; q < npb; ++q) {
+      const double b = eb[q];
+      const double pp = a + b, ip = 1.0 / pp, h = 0.5 * ip;
+      const double mu = a * b * ip;
+      const double pref = ca[p] * cb[q] * exp(-mu * AB2) * (3.14159265358979323846 * ip) * sqrt(3.14159265358979323846 * ip);
+      // P - A = -b/p (A-B) ; P - B = a/p (A-B)
+      const double fa = -b * ip, fb = a * ip;
+      double S0[3], Sp[3], Sm[3], T0[3], Tp[3], Tm[3];
+      axis_factors(fa * ABx, fb * ABx, h, b, la[0], lb[0], S0[0], Sp[0], Sm[0], T0[0], Tp[0], Tm[0]);
+      axis_factors(fa * ABy, fb * ABy, h, b, la[1], lb[1], S0[1], Sp[1], Sm[1], T0[1], Tp[1], Tm[1]);
+      axis_factors(fa * ABz, fb * ABz, h, b, la[2], lb[2], S0[2], Sp[2], Sm[2], T0[2], Tp[2], Tm[2]);
+      const double sxy = S0[0] * S0[1], sxz = S0[0] * S0[2], syz = S0[1] * S0[2];
+      S += pref * sxy * S0[2];
+      T += pref * (T0[0] * syz + T0[1] * sxz + T0[2] * sxy);
+      const double a2 = 2.0 * a;
+      // d/dA_x of the bra: 2a (l+1) - l (l-1)
+      const double dsx = a2 * Sp[0] - la[0] * Sm[0], dsy = a2 * Sp[1] - la[1] * Sm[1], dsz = a2 * Sp[2] - la[2] * Sm[2];
+      const double dtx = a2 * Tp[0] - la[0] * Tm[0], dty = a2 * Tp[1] - la[1] * Tm[1], dtz = a2 * Tp[2] - la[2] * Tm[2];
+      const double gSx = dsx * syz, gSy = dsy * sxz, gSz = dsz * sxy;
+      const double gTx = dtx * syz + dsx * (T0[1] * S0[2] + S0[1] * T0[2]);
+      const double gTy = dty * sxz + dsy * (T0[0] * S0[2] + S0[0] * T0[2]);
+      const double gTz = dtz * sxy + dsz * (T0[0] * S0[1] + S0[0] * T0[1]);
+      dS += pref * (L[0] * gSx + L[1] * gSy + L[2] * gSz);
+      dT += pref * (L[0] * gTx + L[1] * gTy + L[2] * gTz);
+    }
+  }
+  out[0] = S; out[1] = T; out[2] = dS; out[3] = dT;
+}
+
+}  // namespace slv

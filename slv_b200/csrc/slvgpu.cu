@@ -217,7 +217,14 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
       TRY(dalloc(pl, &pl->d_detail, (size_t)pl->detail_frames * cc * 9));
     }
   }
-  if (d->flags & SLVGPU_REP) TRY(rep_alloc(pl->rw, pl->allocs, g_err, pl->sm_count, pl->nmosc, pl->nbasc, pl->max_nmos, pl->max_nbas, &pl->rep_ctas));
+  if (d->flags & SLVGPU_REP) {
+    if (tm0[SLVGPU_M_O_VECL] < 0 || d->sol_meta[SLVGPU_S_VECL1] < 0) {
+      slvgpu_plan_destroy(pl);
+      return fail(SLVGPU_EINVAL, "exchange-repulsion needs the wave-function tables (vecl, fock, basis) in the plan");
+    }
+    pl->rep_ctas = pl->sm_count * 2;
+    TRY(rep_alloc(pl->rw, pl->allocs, g_err, pl->rep_ctas, pl->nmosc, pl->nbasc, pl->max_nmos, pl->max_nbas));
+  }
 #undef TRY
   // opt in to large dynamic shared memory where needed
   cudaFuncSetAttribute(k_frame_elect, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -271,6 +278,7 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
     }
     if ((p.flags & SLVGPU_REP) && p.ninst > 1) {
       const int g = nf < pl->rep_ctas ? nf : pl->rep_ctas;
+      CK(cudaMemsetAsync(pl->rw.queue, 0, sizeof(int), st));
       ev_begin(pl, 3, st);
       k_rep<<<g, REP_THREADS, rep_smem_bytes(pl->nmosc, pl->max_nmos, pl->natc, pl->max_nat), st>>>(p, (int)f0, nf, pl->fl, pl->rw, d_out);
       ev_end(pl, st);

@@ -12,3 +12,10 @@ extern "C" {
 void hm_site_field(const double* R, const double* m, double f, double* F) { slv::site_field(R, m, f, F); }
 void hm_site_dfield(const double* R, const double* v, const double* m, double sg, double* F) { slv::site_dfield(R, v, m, sg, F); }
 }
+#include "../slv_b200/csrc/slv_ints.cuh"
+extern "C" {
+void hm_ao_pair(const double* A, const int* la, int npa, const double* ea, const double* ca,
+                const double* B, const int* lb, int npb, const double* eb, const double* cb, const double* L, double* out) {
+  slv::ao_pair(A, la, npa, ea, ca, B, lb, npb, eb, cb, L, out);
+}
+}

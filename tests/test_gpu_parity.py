@@ -139,3 +139,43 @@ def test_frag_sup_matches_oracle(frags):
     assert abs(rms - rms_o) < 1e-10
     for k in ('pos', 'rdma', 'rpol', 'lmoc', 'dmad', 'dmaq', 'dmao', 'dpol', 'dpoli'):
         assert np.abs(got[k] - ref[k]).max() < 1e-12, k
+
+
+@pytest.mark.parametrize('solute,mode,nw,seed', [('nma', 8, 5, 21), ('mescn', 4, 12, 22)])
+def test_exchange_repulsion_vs_oracle(frags, solute, mode, nw, seed):
+    """rep_mea: CUDA integrals + SHFTEX against the oracle (integrals restated; SHFTEX restatement validated
+    against the transpiled reference Fortran in tests/test_oracle_vs_ref.py)."""
+    from slv_b200 import synth
+    from slv_b200.basis import BasisSet
+    from oracle import solefp_oracle as O
+    sol, wat = frags(solute), frags('water')
+    nat = sol.get_natoms()
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos()], np.zeros(nw, int), 3, seed=seed)
+    ind = [0] + [1] * nw; nmol = [nat] + [3] * nw
+    cuts = (20.0, 13.0, 11.0)
+    efp = _efp(mode=mode, rep=True, pol=False, disp=False, ccut=cuts[0], pcut=cuts[1], ecut=cuts[2])
+    rows, status = efp.eval_frames(X, ind, nmol, [sol, wat], [None, None], [None, None])
+    got = efp.shifts_of(rows)
+    c = O.HartreePerHbarToCmRec
+    for f in range(len(X)):
+        ref = O.eval_frame(X[f], ind, nmol, [sol.get(), wat.get()], [None, None], [None, None], mode, *cuts,
+                           elect=True, ea=True, corr=True, rep=True, make_basis=lambda a, p: BasisSet(a, p))
+        assert abs(got['rep_mea'][f] - ref['rep_mea'] * c) < TOL * max(1.0, abs(ref['rep_mea'] * c) * 1e-3), (f, got['rep_mea'][f], ref['rep_mea'] * c)
+        assert rows[f, 13] == ref['n_rep']
+
+
+def test_exchange_repulsion_mixed_types(frags):
+    from slv_b200 import synth
+    from slv_b200.basis import BasisSet
+    from oracle import solefp_oracle as O
+    sol, wat, dmso = frags('mescn'), frags('water'), frags('dmso')
+    types = np.array([0, 1, 0, 1, 0, 0])
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos(), dmso.get_pos()], types, 1, seed=33, spacing=8.5)
+    ind = [0] + [1 + t for t in types]; nmol = [7] + [3 if t == 0 else 10 for t in types]
+    efp = _efp(mode=4, rep=True, pol=False, disp=False, ccut=40.0, pcut=17.0, ecut=14.0)
+    rows, status = efp.eval_frames(X, ind, nmol, [sol, wat, dmso], [None] * 3, [None] * 3)
+    got = efp.shifts_of(rows)
+    ref = O.eval_frame(X[0], ind, nmol, [sol.get(), wat.get(), dmso.get()], [None] * 3, [None] * 3, 4, 40.0, 17.0, 14.0,
+                       elect=True, rep=True, make_basis=lambda a, p: BasisSet(a, p))
+    c = O.HartreePerHbarToCmRec
+    assert abs(got['rep_mea'][0] - ref['rep_mea'] * c) < TOL * max(1.0, abs(ref['rep_mea'] * c) * 1e-3), (got['rep_mea'][0], ref['rep_mea'] * c)
