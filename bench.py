@@ -148,7 +148,7 @@ def main():
     sol, wat, X = make_frames(nw, a.unique, a.frames, 2, rank)
     ind = [0] + [1] * nw; nmol = [12] + [3] * nw
     efp = EFP(elect=True, pol=True, corr=True, freq=True, mode=MODE, ccut=CUTS[0], pcut=CUTS[1], ecut=CUTS[2], cunit=True)
-    efp.max_chunk = 2048
+    efp.max_chunk = min(a.frames, 10240)
     d_coords = torch.from_numpy(X).to(dev)
     h_coords = torch.from_numpy(X).pin_memory()
     nf = d_coords.shape[0]

@@ -40,6 +40,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
   __shared__ double s_red[32];
   __shared__ int s_tmol[POL_TILE];
   __shared__ int s_fi;
+  __shared__ unsigned long long s_scan[POL_THREADS / 32];
   __shared__ int s_n[4];
   extern __shared__ double sm[];    // [POL_TILE*10] sweep tile, then the solute tables of the contraction phase
   double *s_tile = sm;
@@ -67,16 +68,34 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     const int nl = fl.nlist[fi];
     const size_t lbase = (size_t)fi * p.list_cap;
     // ---- (a) offsets of every pol-layer entry, then the lab-frame centre and site tables
-    if (tid == 0) {
-      int nc = npolc, ns = ndmac;
-      for (int e = 0; e < nl; ++e) {
-        wk.ent_coff[e] = nc; wk.ent_soff[e] = ns;
-        if (fl.list_flag[lbase + e] & 1) {
+    // offsets by a block-wide exclusive scan over the list entries (ordered, deterministic)
+    {
+      int run_c = npolc, run_s = ndmac;
+      for (int e0 = 0; e0 < nl; e0 += NT) {
+        const int e = e0 + tid;
+        int nc = 0, ns = 0;
+        if (e < nl && (fl.list_flag[lbase + e] & 1)) {
           const int *tm = tmeta(p, p.inst_type[fl.list_inst[lbase + e]]);
-          nc += tm[SLVGPU_M_NPOL]; ns += tm[SLVGPU_M_NDMA];
+          nc = tm[SLVGPU_M_NPOL]; ns = tm[SLVGPU_M_NDMA];
         }
+        // pack both counts into one 64-bit value for a single scan
+        unsigned long long v = ((unsigned long long)nc << 32) | (unsigned)ns, incl = v;
+        const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        __syncthreads();
+        if (lane == 31) s_scan[w] = incl;
+        __syncthreads();
+        unsigned long long base = 0, tot = 0;
+        for (int i = 0; i < (NT >> 5); ++i) { if (i < w) base += s_scan[i]; tot += s_scan[i]; }
+        const unsigned long long excl = base + incl - v;
+        if (e < nl) { wk.ent_coff[e] = run_c + (int)(excl >> 32); wk.ent_soff[e] = run_s + (int)(excl & 0xffffffffu); }
+        run_c += (int)(tot >> 32); run_s += (int)(tot & 0xffffffffu);
       }
-      s_n[0] = nc; s_n[1] = ns;
+      if (tid == 0) { s_n[0] = run_c; s_n[1] = run_s; }
     }
     __syncthreads();
     const int ncent = s_n[0], nsite = s_n[1];
@@ -200,7 +219,9 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
 #pragma unroll 4
               for (int jj = 0; jj < jn; ++jj) {
                 const bool same = (s_tmol[jj] == mc);          // same molecule (incl. self): no interaction, branch-free
-                const double *tt = s_tile + jj * 10;
+                const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
+                const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
+                const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
                 const double Rx = rc[0] - tt[0], Ry = rc[1] - tt[1], Rz = rc[2] - tt[2];
                 const double r2 = same ? 1.0 : (Rx * Rx + Ry * Ry + Rz * Rz);
                 const double u = rsqrt64(r2), u2 = u * u;

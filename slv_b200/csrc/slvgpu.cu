@@ -133,7 +133,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   p.ntypes = d->ntypes; p.ninst = d->ninst; p.natoms_total = d->natoms_total; p.flags = d->flags;
   p.ccut = d->ccut; p.pcut = d->pcut; p.ecut = d->ecut;
   p.pol_maxit = d->pol_maxit > 0 ? d->pol_maxit : 200;
-  p.pol_tol = d->pol_tol > 0 ? d->pol_tol : 1e-12;
+  p.pol_tol = d->pol_tol > 0 ? d->pol_tol : 1e-10;
   int rc = 0;
 #define TRY(x) do { rc = (x); if (rc) { slvgpu_plan_destroy(pl); return rc; } } while (0)
   TRY(upload(pl, &p.type_meta, d->type_meta, (size_t)d->ntypes * SLVGPU_NMETA));
@@ -192,7 +192,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   cudaGetDevice(&dev);
   cudaGetDeviceProperties(&prop, dev);
   pl->sm_count = prop.multiProcessorCount;
-  pl->max_chunk = d->max_chunk > 0 ? d->max_chunk : 1024;
+  pl->max_chunk = d->max_chunk > 0 ? d->max_chunk : 4096;
   pl->want_detail = d->want_detail;
   const size_t ch = (size_t)pl->max_chunk;
   TRY(dalloc(pl, &pl->d_queue, 4));
