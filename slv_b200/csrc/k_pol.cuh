@@ -140,21 +140,38 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     }
     __syncthreads();
 
-    // ---- (b) fields at every centre from the multipoles of all OTHER molecules (FFFFFF)
-    for (int c = tid; c < ncent; c += NT) {
-      const double rc[3] = {wk.cent_pos[(size_t)c * 3], wk.cent_pos[(size_t)c * 3 + 1], wk.cent_pos[(size_t)c * 3 + 2]};
-      const int mc = wk.cent_mol[c];
-      double F[3] = {0, 0, 0};
-      for (int s = 0; s < nsite; ++s) {
-        const double *row = wk.site + (size_t)s * SITE_ROW;
-        if ((int)row[23] == mc) continue;
-        const double R[3] = {rc[0] - row[0], rc[1] - row[1], rc[2] - row[2]};
-        site_field(R, row + 3, 5.0, F);
+    // ---- (b) fields at every centre from the multipoles of all OTHER molecules (FFFFFF); sites staged
+    //      through shared memory in tiles, own-molecule sites masked branch-free
+    {
+      constexpr int FT = 128;                               // sites per tile (FT * SITE_ROW doubles <= POL_TILE * 10)
+      for (int c0 = 0; c0 < ncent; c0 += NT) {
+        const int c = c0 + tid;
+        const bool act = c < ncent;
+        double rc[3] = {0, 0, 0}; int mc = -1;
+        if (act) { rc[0] = wk.cent_pos[(size_t)c * 3]; rc[1] = wk.cent_pos[(size_t)c * 3 + 1]; rc[2] = wk.cent_pos[(size_t)c * 3 + 2]; mc = wk.cent_mol[c]; }
+        double F[3] = {0, 0, 0};
+        for (int s0 = 0; s0 < nsite; s0 += FT) {
+          const int sn = min(FT, nsite - s0);
+          __syncthreads();
+          for (int w = tid; w < sn * SITE_ROW; w += NT) s_tile[w] = wk.site[(size_t)s0 * SITE_ROW + w];
+          __syncthreads();
+          if (act) {
+#pragma unroll 2
+            for (int s = 0; s < sn; ++s) {
+              const double *row = s_tile + s * SITE_ROW;
+              const bool same = ((int)row[23] == mc);
+              const double R[3] = {same ? 1.0 : rc[0] - row[0], same ? 0.0 : rc[1] - row[1], same ? 0.0 : rc[2] - row[2]};
+              site_field_acc(R, row + 3, 5.0, same ? 0.0 : 1.0, F);
+            }
+          }
+        }
+        if (act) {
+          const double *a = wk.cent_alpha + (size_t)c * 9;
+          wk.fld[(size_t)c * 3] = F[0]; wk.fld[(size_t)c * 3 + 1] = F[1]; wk.fld[(size_t)c * 3 + 2] = F[2];
+          double *v = wk.xy + (size_t)c * PST;               // state slot 0..2 <- b = alpha F
+          for (int i = 0; i < 3; ++i) v[i] = a[i * 3] * F[0] + a[i * 3 + 1] * F[1] + a[i * 3 + 2] * F[2];
+        }
       }
-      const double *a = wk.cent_alpha + (size_t)c * 9;
-      wk.fld[(size_t)c * 3] = F[0]; wk.fld[(size_t)c * 3 + 1] = F[1]; wk.fld[(size_t)c * 3 + 2] = F[2];
-      double *v = wk.xy + (size_t)c * PST;              // state slot 0..2 <- b = alpha F
-      for (int i = 0; i < 3; ++i) v[i] = a[i * 3] * F[0] + a[i * 3 + 1] * F[1] + a[i * 3 + 2] * F[2];
     }
     __syncthreads();
 

@@ -292,4 +292,29 @@ SLV_HD void site_dfield(const double R[3], const double v[3], const double m[20]
     F[a] += sign * (cR * R[a] + cv * v[a] + cm * m[1 + a] + ctR * tR[a] + ctv * tv[a] + coRR * oRR[a] + covR * ovR[a]);
 }
 
+// Lean form of site_field for the hot field loop of k_pol: same arithmetic, octupole contractions through
+// the six R_b R_c monomials.  `w` masks the contribution (0 for sites of the centre's own molecule).
+SLV_HD void site_field_acc(const double R[3], const double m[20], double octfac, double w, double F[3]) {
+  const double r2 = R[0] * R[0] + R[1] * R[1] + R[2] * R[2];
+  const double u = rsqrt64(r2), u2 = u * u, u3 = w * u2 * u, u5 = u3 * u2, u7 = u5 * u2, u9 = u7 * u2;
+  const double xx = R[0] * R[0], yy = R[1] * R[1], zz = R[2] * R[2];
+  const double xy = 2.0 * R[0] * R[1], xz = 2.0 * R[0] * R[2], yz = 2.0 * R[1] * R[2];
+  const double *th = m + 4, *om = m + 10;
+  const double mR = m[1] * R[0] + m[2] * R[1] + m[3] * R[2];
+  const double tRx = th[0] * R[0] + th[3] * R[1] + th[4] * R[2];
+  const double tRy = th[3] * R[0] + th[1] * R[1] + th[5] * R[2];
+  const double tRz = th[4] * R[0] + th[5] * R[1] + th[2] * R[2];
+  const double tRR = tRx * R[0] + tRy * R[1] + tRz * R[2];
+  // O: XXX0 YYY1 ZZZ2 XXY3 XXZ4 XYY5 YYZ6 XZZ7 YZZ8 XYZ9
+  const double oRRx = om[0] * xx + om[5] * yy + om[7] * zz + om[3] * xy + om[4] * xz + om[9] * yz;
+  const double oRRy = om[3] * xx + om[1] * yy + om[8] * zz + om[5] * xy + om[9] * xz + om[6] * yz;
+  const double oRRz = om[4] * xx + om[6] * yy + om[2] * zz + om[9] * xy + om[7] * xz + om[8] * yz;
+  const double oRRR = oRRx * R[0] + oRRy * R[1] + oRRz * R[2];
+  const double sR = m[0] * u3 + 3.0 * mR * u5 + 5.0 * tRR * u7 + octfac * oRRR * u9;
+  const double c5 = 2.0 * u5, c7 = 3.0 * u7;
+  F[0] += sR * R[0] - u3 * m[1] - c5 * tRx - c7 * oRRx;
+  F[1] += sR * R[1] - u3 * m[2] - c5 * tRy - c7 * oRRy;
+  F[2] += sR * R[2] - u3 * m[3] - c5 * tRz - c7 * oRRz;
+}
+
 }  // namespace slv

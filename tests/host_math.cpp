@@ -19,3 +19,4 @@ void hm_ao_pair(const double* A, const int* la, int npa, const double* ea, const
   slv::ao_pair(A, la, npa, ea, ca, B, lb, npb, eb, cb, L, out);
 }
 }
+extern "C" void hm_site_field_acc(const double* R, const double* m, double f, double w, double* F) { slv::site_field_acc(R, m, f, w, F); }

@@ -108,3 +108,14 @@ def test_field_and_field_derivative(L, frags):
             assert np.abs(F - O._field_traceless(R, q[s], mu[s], Th[s], Om[s], fac)).max() < 1e-15
         F = np.zeros(3); L.hm_site_dfield(P(R), P(v), P(np.ascontiguousarray(m[s])), 1.0, P(F))
         assert np.abs(F - O._dfield_traceless(R, v, q[s], mu[s], Th[s], Om[s])).max() < 1e-15
+
+
+def test_lean_field_equals_generic(L):
+    L.hm_site_field_acc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+    rng = np.random.default_rng(0)
+    for t in range(20):
+        R = rng.normal(0, 3, 3); m = rng.normal(0, 1, 20); F1 = np.zeros(3); F2 = np.zeros(3); F3 = np.ones(3)
+        L.hm_site_field(P(R), P(m), 5.0, P(F1)); L.hm_site_field_acc(P(R), P(m), 5.0, 1.0, P(F2))
+        assert np.abs(F1 - F2).max() < 1e-14 * np.abs(F1).max()
+        L.hm_site_field_acc(P(np.array([1.0, 0.0, 0.0])), P(m), 5.0, 0.0, P(F3))      # masked: no contribution
+        assert np.array_equal(F3, np.ones(3))
