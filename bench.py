@@ -193,11 +193,11 @@ def main():
     h_rows = torch.empty((nf, _lib.NOUT), dtype=torch.float64).pin_memory()
     h_status = torch.empty((nf,), dtype=torch.int32).pin_memory()
     for _ in range(2):
-        plan.eval_host(h_coords, h_rows, h_status)
+        efp.eval_frames(h_coords, out=h_rows, status=h_status)
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        plan.eval_host(h_coords, h_rows, h_status)
+        efp.eval_frames(h_coords, out=h_rows, status=h_status)     # the public call: pinned host in, host rows out
     barrier()
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag = True; sampler.join(timeout=2)

@@ -42,7 +42,8 @@ struct slvgpu_plan {
   double *d_stage_coords = nullptr, *d_stage_out = nullptr; int *d_stage_status = nullptr;
   int64_t stage_frames = 0;
   int64_t last_launches = 0;
-  cudaStream_t own_stream = nullptr;
+  cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_ev;
   int timing = 0;
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   std::vector<int> ev_kind;            // kernel id of each (start, stop) pair in use
@@ -114,6 +115,8 @@ extern "C" void slvgpu_plan_destroy(slvgpu_plan *pl) {
   if (pl->d_stage_out) cudaFree(pl->d_stage_out);
   if (pl->d_stage_status) cudaFree(pl->d_stage_status);
   if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
+  if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
+  for (cudaEvent_t e : pl->copy_ev) cudaEventDestroy(e);
   delete pl;
 }
 
@@ -305,10 +308,30 @@ extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, 
     CK(cudaMalloc(&pl->d_stage_status, (size_t)nframes * sizeof(int32_t)));
     pl->stage_frames = nframes;
   }
+  // Pipelined: coordinates go up in slices on a copy stream while the previous slice is being evaluated on
+  // the compute stream (frames are independent, so slices are just sub-ranges of the same buffers).
   cudaStream_t st = pl->own_stream;
-  CK(cudaMemcpyAsync(pl->d_stage_coords, h_coords, (size_t)nframes * p.natoms_total * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-  int rc = slvgpu_eval_frames(pl, pl->d_stage_coords, nframes, pl->d_stage_out, pl->d_stage_status, st);
-  if (rc) return rc;
+  if (!pl->copy_stream) CK(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
+  // a short first slice hides the first copy; later slices are long so the persistent kernels keep a full queue
+  const int64_t first = pl->max_chunk < 1024 ? pl->max_chunk : 1024;
+  const int64_t slice = pl->max_chunk < 4096 ? pl->max_chunk : 4096;
+  const int64_t nsl = nframes <= first ? 1 : 1 + (nframes - first + slice - 1) / slice;
+  while ((int64_t)pl->copy_ev.size() < nsl) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); pl->copy_ev.push_back(e); }
+  const size_t fstride = (size_t)p.natoms_total * 3;
+  int64_t launches = 0, f0 = 0;
+  for (int64_t c = 0; c < nsl; ++c) {
+    const int64_t want = c == 0 ? first : slice, n = (nframes - f0) < want ? (nframes - f0) : want;
+    CK(cudaMemcpyAsync(pl->d_stage_coords + f0 * fstride, h_coords + f0 * fstride, (size_t)n * fstride * sizeof(double),
+                       cudaMemcpyHostToDevice, pl->copy_stream));
+    CK(cudaEventRecord(pl->copy_ev[c], pl->copy_stream));
+    CK(cudaStreamWaitEvent(st, pl->copy_ev[c], 0));
+    int rc = slvgpu_eval_frames(pl, pl->d_stage_coords + f0 * fstride, n, pl->d_stage_out + f0 * SLVGPU_NOUT,
+                                pl->d_stage_status + f0, st);
+    if (rc) return rc;
+    launches += pl->last_launches;
+    f0 += n;
+  }
+  pl->last_launches = launches;
   CK(cudaMemcpyAsync(h_out, pl->d_stage_out, (size_t)nframes * SLVGPU_NOUT * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(h_status, pl->d_stage_status, (size_t)nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

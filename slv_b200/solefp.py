@@ -181,7 +181,7 @@ class EFP(UNITS):
             print(self)
         return
 
-    def eval_frames(self, coords, ind=None, nmol=None, bsm=None, supl=None, reord=None, device=True):
+    def eval_frames(self, coords, ind=None, nmol=None, bsm=None, supl=None, reord=None, out=None, status=None):
         """Batched evaluation: coords [nframes, natoms, 3] (Bohr).  A CUDA torch tensor is evaluated in
         place on the device and CUDA tensors are returned; a host array (numpy / pinned torch) goes
         through the host entry point.  Returns (rows [nframes,16] in a.u., status [nframes])."""
@@ -195,8 +195,8 @@ class EFP(UNITS):
                 self._reord = reord
         plan = self._get_plan()
         if hasattr(coords, 'is_cuda') and coords.is_cuda:
-            return plan.eval_device(coords)
-        return plan.eval_host(coords)
+            return plan.eval_device(coords, out, status)
+        return plan.eval_host(coords, out, status)
 
     def shifts_of(self, rows):
         """Dictionary of per-frame arrays with the reference's shift keys."""
