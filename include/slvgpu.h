@@ -39,7 +39,8 @@ enum {
   SLVGPU_RMS_C = 8, SLVGPU_RMS_SMAX = 9, SLVGPU_RMS_AVE = 10,
   SLVGPU_N_ELECT = 11, SLVGPU_N_POL = 12, SLVGPU_N_REP = 13,
   SLVGPU_POL_ITERS = 14, SLVGPU_POL_RESID = 15,
-  SLVGPU_NOUT = 16
+  SLVGPU_POL_ADD = 16,   /* part of POL_MEA from the additive two-body solves of removable fragments */
+  SLVGPU_NOUT = 20
 };
 
 /* per-frame status bits */
@@ -69,6 +70,7 @@ enum {
   SLVGPU_M_IO_BFNP,   /* itab: [nbasis] number of primitives                                     */
   SLVGPU_M_O_BFEXP,   /* dtab: [nbasis][6] exponents                                             */
   SLVGPU_M_O_BFCOEF,  /* dtab: [nbasis][6] normalised contraction coefficients                   */
+  SLVGPU_M_REMOVABLE, /* 1: polarisation of this type is treated pair-wise (remove_clashes)          */
   SLVGPU_NMETA = 32
 };
 

@@ -411,7 +411,7 @@ def pol_shift(parc, solv, mode, literal_gemm=False):
 
 # --------------------------------------------------------------------------- one frame, all terms
 def eval_frame(pos, ind, nmol, pars, supl, reord, mode, ccut=1e10, pcut=1e10, ecut=1e10,
-               elect=True, ea=True, corr=True, pol=False, disp=False, rep=False, make_basis=None, literal_gemm=False):
+               elect=True, ea=True, corr=True, pol=False, disp=False, rep=False, make_basis=None, literal_gemm=False, removable=None):
     """EFP.set + EFP.eval(0) for one frame in central mode (solefp.py:223-277, 738-787, 1011-1629).
     pars: list of parameter dicts (Frag.get()); returns a dict of a.u. terms + rms values."""
     ind = np.asarray(ind, int); nmol = np.asarray(nmol, int)
@@ -443,8 +443,17 @@ def eval_frame(pos, ind, nmol, pars, supl, reord, mode, ccut=1e10, pcut=1e10, ec
         if pol or disp:
             lay_p = [sup(i + 1)[0] for i in np.nonzero(ipm)[0]]
         if pol:
-            sh, fip, dip, av = pol_shift(parc, lay_p, mode, literal_gemm=literal_gemm)
-            out.update(pol_mea=sh, fi_pol=fip, dipind=dip, avec=av)
+            # remove_clashes (solefp.py:1224-1236, 1333-1404): fragments of removable TYPES leave the many-body
+            # solve and each gets a two-body solve with the solute; the shifts add
+            ipl = [i + 1 for i in np.nonzero(ipm)[0]]
+            keep = [p_ for p_, i in zip(lay_p, ipl) if removable is None or ind[i] not in removable]
+            add = [p_ for p_, i in zip(lay_p, ipl) if removable is not None and ind[i] in removable]
+            sh, fip, dip, av = pol_shift(parc, keep, mode, literal_gemm=literal_gemm)
+            sh_add = 0.0
+            for p_ in add:
+                s2, f2, _, _ = pol_shift(parc, [p_], mode)
+                sh_add += s2; fip = fip + f2
+            out.update(pol_mea=sh + sh_add, pol_add_mea=sh_add, fi_pol=fip, dipind=dip, avec=av)
         if disp:
             iso, ani = disp_shifts(parc, lay_p, mode)
             out.update(dis_mea=ani, dis_mea_iso=iso)
@@ -527,3 +536,14 @@ def rep_shift(parc, solv, mode, make_basis, rotc=None, rots=None, par0c=None, pa
         TA4 = 2.0 * Sij ** 2 * (ZB[None, :] * rm_iy / riy ** 2).sum(2)[:, :, None] - 4.0 * Sij * Sm * (ZB[None, :] / riy).sum(1)[:, None]
         fi += (TS1 + TS2 + TS3 + TS4 + TA1 + TA2 + TA3 + TA4).sum((1, 2))
     return -(w * fi).sum() / den, fi
+
+
+def eval_dma_frame(pos_c, parc0, supl_c, mode, env, ea=True, corr=True):
+    """EFP.eval_dma (solefp.py:798-903): SolCAMM + corrections of the superimposed solute against an environment
+    given as point charges env[n,4] = x,y,z,q; no cut-off, no superimposition of the environment."""
+    r, tr, rms = kabsch(parc0['pos'], pos_c, supl_c)
+    parc = sup_params(parc0, r, tr)
+    n = len(env)
+    pe = dict(rdma=env[:, :3], dmac=env[:, 3], dmad=np.zeros((n, 3)), dmaq=np.zeros((n, 6)), dmao=np.zeros((n, 10)))
+    m, e, cm, ce, fi = elect_shifts(parc, [pe], mode, ea=ea, corr=corr)
+    return dict(ele_env_mea=m, ele_env_ea=e, cor_env_mea=cm, cor_env_ea=ce)

@@ -169,6 +169,7 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, Fr
     o[SLVGPU_RMS_AVE] = (s_xf[12] + rms_sum) / (dn_c + 1.0);
     o[SLVGPU_N_ELECT] = dn_c; o[SLVGPU_N_POL] = dn_p; o[SLVGPU_N_REP] = dn_e;
     o[SLVGPU_POL_ITERS] = 0.0; o[SLVGPU_POL_RESID] = 0.0;
+    for (int k = SLVGPU_POL_ADD; k < SLVGPU_NOUT; ++k) o[k] = 0.0;
     fl.nlist[fi] = s_base < p.list_cap ? s_base : p.list_cap;
   }
 }

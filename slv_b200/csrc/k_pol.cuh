@@ -67,6 +67,18 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     if (fi >= nframes) break;
     const int nl = fl.nlist[fi];
     const size_t lbase = (size_t)fi * p.list_cap;
+    // Pass -1 is the many-body solve over the pol-layer fragments whose type is not flagged removable; every
+    // removable fragment (EFP.eval(remove_clashes=True), solvshift/solefp.py:1224-1236, 1333-1404, 1722-1773) then
+    // gets its own two-body solve with the solute, and the shifts add.
+    double shift_main = 0.0, shift_add = 0.0, resid_out = 0.0;
+    int iters_out = 0;
+    for (int pass = -1;;) {
+    auto included = [&](int e) -> bool {
+      if (!(fl.list_flag[lbase + e] & 1)) return false;
+      const bool rem = tmeta(p, p.inst_type[fl.list_inst[lbase + e]])[SLVGPU_M_REMOVABLE] > 0;
+      return pass < 0 ? !rem : e == pass;
+    };
+    do {
     // ---- (a) offsets of every pol-layer entry, then the lab-frame centre and site tables
     // offsets by a block-wide exclusive scan over the list entries (ordered, deterministic)
     {
@@ -74,7 +86,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       for (int e0 = 0; e0 < nl; e0 += NT) {
         const int e = e0 + tid;
         int nc = 0, ns = 0;
-        if (e < nl && (fl.list_flag[lbase + e] & 1)) {
+        if (e < nl && included(e)) {
           const int *tm = tmeta(p, p.inst_type[fl.list_inst[lbase + e]]);
           nc = tm[SLVGPU_M_NPOL]; ns = tm[SLVGPU_M_NDMA];
         }
@@ -101,8 +113,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     const int ncent = s_n[0], nsite = s_n[1];
     if (ncent > p.cent_cap || nsite > p.site_cap || ncent == npolc) {
       if (tid == 0 && ncent != npolc) status[frame0 + fi] |= SLVGPU_ST_OVERFLOW;
-      __syncthreads();
-      continue;
+      break;                                   // nothing to solve in this pass
     }
     for (int e = tid - 1; e < nl; e += NT) {          // e == -1 is the solute
       const int *tm; double R[9], t[3]; int c0, s0, mol;
@@ -112,7 +123,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
         for (int d = 0; d < 3; ++d) t[d] = sx[9 + d];
         c0 = 0; s0 = 0; mol = 0;
       } else {
-        if (!(fl.list_flag[lbase + e] & 1)) continue;
+        if (!included(e)) continue;
         tm = tmeta(p, p.inst_type[fl.list_inst[lbase + e]]);
         const double *xf = fl.list_xf + (lbase + e) * 12;
         for (int d = 0; d < 9; ++d) R[d] = xf[d];
@@ -374,21 +385,38 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       }
     }
     acc = block_sum(acc, s_red);
-    if (tid == 0) {
-      double *o = out + (size_t)(frame0 + fi) * SLVGPU_NOUT;
-      o[SLVGPU_POL_MEA] = -0.5 * acc;
-      o[SLVGPU_POL_ITERS] = (double)iters;
-      o[SLVGPU_POL_RESID] = resid;
-      if (resid > p.pol_tol) status[frame0 + fi] |= SLVGPU_ST_POL_NOCONV;
-    }
-    if (detail) {
-      double *dd = detail + (size_t)fi * p.cent_cap * 9;
+    if (pass < 0) { shift_main = -0.5 * acc; iters_out = iters; resid_out = resid; }
+    else { shift_add += -0.5 * acc; resid_out = fmax(resid_out, resid); }
+    if (detail && pass < 0) {
+      double *dd = detail + (size_t)fi * ((size_t)p.cent_cap * 9 + 1);
       for (int c = tid; c < ncent; c += NT)
         for (int d = 0; d < 3; ++d) {
           dd[(size_t)c * 9 + d] = vxy[(size_t)c * 6 + d];
           dd[(size_t)c * 9 + 3 + d] = wk.fld[(size_t)c * 3 + d];
           dd[(size_t)c * 9 + 6 + d] = wk.cent_pos[(size_t)c * 3 + d];
         }
+      if (tid == 0) dd[(size_t)p.cent_cap * 9] = (double)ncent;
+    }
+    } while (0);
+    // next removable fragment inside pcut, if any
+    __syncthreads();
+    if (tid == 0) {
+      int nx = -1;
+      for (int e = pass + 1; e < nl; ++e)
+        if ((fl.list_flag[lbase + e] & 1) && tmeta(p, p.inst_type[fl.list_inst[lbase + e]])[SLVGPU_M_REMOVABLE] > 0) { nx = e; break; }
+      s_n[2] = nx;
+    }
+    __syncthreads();
+    pass = s_n[2];
+    if (pass < 0) break;
+    }   // passes
+    if (tid == 0) {
+      double *o = out + (size_t)(frame0 + fi) * SLVGPU_NOUT;
+      o[SLVGPU_POL_MEA] = shift_main + shift_add;
+      o[SLVGPU_POL_ADD] = shift_add;
+      o[SLVGPU_POL_ITERS] = (double)iters_out;
+      o[SLVGPU_POL_RESID] = resid_out;
+      if (resid_out > p.pol_tol) status[frame0 + fi] |= SLVGPU_ST_POL_NOCONV;
     }
     __syncthreads();
   }

@@ -217,7 +217,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
     TRY(dalloc(pl, &pl->pw.ent_soff, nc * (size_t)p.list_cap));
     if (pl->want_detail) {
       pl->detail_frames = pl->max_chunk;
-      TRY(dalloc(pl, &pl->d_detail, (size_t)pl->detail_frames * cc * 9));
+      TRY(dalloc(pl, &pl->d_detail, (size_t)pl->detail_frames * (cc * 9 + 1)));
     }
   }
   if (d->flags & SLVGPU_REP) {
@@ -345,10 +345,11 @@ extern "C" int slvgpu_get_pol_detail(slvgpu_plan *pl, int64_t frame, double *h_d
   if (!pl || !pl->d_detail) return fail(SLVGPU_EINVAL, "plan was created without want_detail / pol");
   if (frame < 0 || frame >= pl->detail_frames) return fail(SLVGPU_EINVAL, "frame outside the last chunk");
   const int cc = pl->dp.cent_cap;
-  std::vector<double> buf((size_t)cc * 9);
+  std::vector<double> buf((size_t)cc * 9 + 1);
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(buf.data(), pl->d_detail + (size_t)frame * cc * 9, buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  const int n = max_centres < cc ? max_centres : cc;
+  CK(cudaMemcpy(buf.data(), pl->d_detail + (size_t)frame * ((size_t)cc * 9 + 1), buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  const int ncent = (int)buf[(size_t)cc * 9];
+  const int n = max_centres < ncent ? max_centres : ncent;
   for (int c = 0; c < n; ++c)
     for (int d = 0; d < 3; ++d) {
       if (h_dipind) h_dipind[c * 3 + d] = buf[(size_t)c * 9 + d];

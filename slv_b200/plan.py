@@ -55,7 +55,8 @@ class Plan(object):
     """Device-resident evaluation plan (owns the slvgpu_plan handle)."""
 
     def __init__(self, ind, nmol, bsm, supl, reord, mode, flags, ccut, pcut, ecut,
-                 max_chunk=4096, pol_maxit=200, pol_tol=1e-10, pol_cent_cap=0, want_detail=False):
+                 max_chunk=4096, pol_maxit=200, pol_tol=1e-10, pol_cent_cap=0, want_detail=False,
+                 g_override=None, removable=None):
         ind = numpy.asarray(ind, int); nmol = numpy.asarray(nmol, int)
         assert len(ind) == len(nmol) and len(ind) >= 1
         self.ninst = len(ind)
@@ -80,6 +81,7 @@ class Plan(object):
             m[M['NATOMS']] = nat; m[M['NDMA']] = par.get('ndma', 0) or 0; m[M['NPOL']] = par.get('npol', 0) or 0
             m[M['NMOS']] = par.get('nmos', 0) or 0; m[M['NBASIS']] = par.get('nbasis', 0) or 0
             m[M['NSUPL']] = len(sl)
+            m[M['REMOVABLE']] = 1 if (removable is not None and t in removable) else 0
             m[M['IO_SUPL']] = it.add(sl); m[M['IO_REORD']] = it.add(ro)
             m[M['O_POS']] = dt.add(par['pos'])
             if 'rdma' in par:
@@ -108,6 +110,9 @@ class Plan(object):
         self.mode = mode
         if mode is not None and 'gijk' in pc:
             g, den = mode_weights(pc, mode)
+            if g_override is not None:          # one-hot mode weights: used by EFP.get_forces (fi_m = dE/dQ_m)
+                g = numpy.asarray(g_override, numpy.float64)
+                assert g.shape == (int(pc['nmodes']),)
             j = mode - 1
             dma1 = mom20(pc['dmac1'], pc['dmad1'], pc['dmaq1'], pc['dmao1'])          # [nmodes, ndma, 20]
             gd = numpy.tensordot(g, dma1, (0, 0))
@@ -210,10 +215,9 @@ class Plan(object):
         return int(_lib.lib.slvgpu_last_launches(self._h))
 
     def pol_detail(self, frame=0, max_centres=None):
-        n = max_centres or 1 << 20
         k = self._keep
         tot = int(sum(k['meta'][t][_lib.M['NPOL']] for t in k['inst_type']))
-        n = min(n, tot)
+        n = min(max_centres or tot, tot)
         dip = numpy.zeros((n, 3)); fld = numpy.zeros((n, 3)); rp = numpy.zeros((n, 3))
         got = _lib.check(_lib.lib.slvgpu_get_pol_detail(self._h, frame, dip.ctypes.data, fld.ctypes.data, rp.ctypes.data, n))
         return dip[:got], fld[:got], rp[:got]

@@ -44,7 +44,8 @@ SHIFT_TERMS = {
     'dis_tot': 'Dispersion (anisotropic, mechanical + electronic anharmonicity)',
     'ele_env_mea': 'SolCAMM:DMA[non-EFP Environment]: mechanical anharmonicity ',
     'ele_env_ea': 'SolCAMM:DMA[non-EFP Environment]: electronic anharmonicity ',
-    'cor_env_mea': 'Corrections:DMA[non-EFP Environment]: electronic anharmonicity ',
+    'cor_env_mea': 'Corrections:DMA[non-EFP Environment]: mechanical anharmonicity ',
+    'cor_env_ea': 'Corrections:DMA[non-EFP Environment]: electronic anharmonicity ',
     'tot_env': 'SolCAMM+Corrections:DMA[non-EFP Environment]: mechanical + electronic anharmonicity',
     'total+env': 'SolEFP + DMA[non-EFP Environment] (total+tot_env terms)',
 }
@@ -78,8 +79,18 @@ def shifts_from_rows(rows, cunit):
     s['total_ea'] = s['ele_ea'] + s['cor_ea'] + s['pol_ea'] + s['rep_ea'] + s['dis_ea']
     s['solcamm'] = s['ele_mea'] + s['ele_ea']
     s['total_cor'] = s['cor_mea'] + s['cor_ea']
-    s['pol_add_mea'] = z.copy(); s['pol_add_ea'] = z.copy(); s['pol_add_tot'] = z.copy()
+    s['pol_add_mea'] = r[:, O['pol_add']] * c; s['pol_add_ea'] = z.copy(); s['pol_add_tot'] = s['pol_add_mea'].copy()
     return s
+
+
+class _ParHolder(object):
+    """Minimal stand-in for a Frag: just a parameter dictionary."""
+
+    def __init__(self, par):
+        self._par = par
+
+    def get(self):
+        return self._par
 
 
 class EFP(UNITS):
@@ -115,6 +126,7 @@ class EFP(UNITS):
         self._bsm = None; self._supl = None; self._reord = None; self._ind = None; self._nmol = None
         self.pol_maxit = 200; self.pol_tol = 1e-10; self.max_chunk = 4096; self.pol_cent_cap = 0
         self.want_detail = False
+        self._removable = None
 
     def __call__(self, lwrite=False, num=False, step=0.006, theory=0):
         self.eval(lwrite, num, step, theory)
@@ -156,15 +168,44 @@ class EFP(UNITS):
     def _get_plan(self):
         key = (tuple(self._ind), tuple(self._nmol), tuple(id(b) for b in self._bsm), self._mode, self._ccut, self._pcut,
                self._ecut, tuple(sorted(self._flags().items())), self.pol_maxit, self.pol_tol, self.max_chunk,
-               self.pol_cent_cap, self.want_detail,
+               self.pol_cent_cap, self.want_detail, None if self._removable is None else tuple(sorted(self._removable)),
                tuple(None if s is None else tuple(s) for s in (self._supl or [])),
                tuple(None if s is None else tuple(s) for s in (self._reord or [])))
         if self._plan is None or key != self._plan_key:
             self._plan = Plan(self._ind, self._nmol, self._bsm, self._supl, self._reord, self._mode, self._flags(),
                               self._ccut, self._pcut, self._ecut, max_chunk=self.max_chunk, pol_maxit=self.pol_maxit,
-                              pol_tol=self.pol_tol, pol_cent_cap=self.pol_cent_cap, want_detail=self.want_detail)
+                              pol_tol=self.pol_tol, pol_cent_cap=self.pol_cent_cap, want_detail=self.want_detail,
+                              removable=self._removable)
             self._plan_key = key
         return self._plan
+
+    # fragment names whose polarisation is treated pair-wise when remove_clashes is on (solefp.py:1733-1761)
+    _RCL_BASE = ['Methane', 'Ethane', 'N-Propane', 'N-methylacethamide', 'N-methylacethamide-D7', 'Formamide',
+                 'Dimethyl Sulfide', 'S-Methyl-2-Propenethioate', 'N-Methyl Formamide', '4-Methyl Phenol', '4-Methyl Imidazole',
+                 'Benzene', 'Dimethyloformamide', 'Thiomethylaldehyde']
+    _RCL_POLAR = ['Methanol', 'Phenol', 'Acetic acid', 'Imidazole', 'Methyl thiol']
+    _RCL_IONS = ['Acetate anion (-1)', 'Methyl Guanidinium Cation (+1)', 'Methyl amonium cation (+1)', 'Imidazolium cation (+1)',
+                 'Phenolate anion (-1)']
+    _RCL_ADDITIVE_EXTRA = ['Tetrahydrofurane', 'Sulphate (VI) -2 anion', 'Chloride anion (-1)', 'Sodium cation (+1)',
+                           'Lithium cation (+1)', 'WATER MOLECULE', 'Dichloromethane', 'Dimethyl Sulphoxide', 'Acetamide',
+                           'Cyclohexane', 'dummy', 'Methyl Acetate', 'Chloroform', 'Methyl nitrile', 'Diethyl carbonate',
+                           'Methyl Sulphate (VI) -1 anion']
+
+    def _removable_types(self, rcl_algorithm, include_ions, include_polar):
+        """Indices into bsm of the fragment types _remove_clashes would reject (solefp.py:1722-1773)."""
+        if rcl_algorithm == 'remove_by_name':
+            names = self._RCL_BASE + ['Acetamide']
+            if not include_polar:
+                names = names + self._RCL_POLAR
+            if not include_ions:
+                names = names + self._RCL_IONS + ['Methyl Sulphate (VI) -1 anion']
+        elif rcl_algorithm == 'additive':
+            names = self._RCL_BASE + self._RCL_POLAR + self._RCL_IONS + self._RCL_ADDITIVE_EXTRA
+        else:
+            raise ValueError('unknown rcl_algorithm %r' % rcl_algorithm)
+        names = set(names)
+        solute_t = int(self._ind[0])
+        return set(t for t, b in enumerate(self._bsm) if t != solute_t and b.get().get('name') in names)
 
     # ------------------------------------------------------------------ evaluation
     def eval(self, lwrite=False, num=False, step=0.006, theory=0, remove_clashes=False,
@@ -173,8 +214,7 @@ class EFP(UNITS):
         if num:
             raise NotImplementedError('numerical (finite-difference) mode needs the num_0.006/*.frg sets, which are '
                                       'not part of the parameter library')
-        if remove_clashes:
-            raise NotImplementedError('remove_clashes (biomol path) is not on the GPU path yet')
+        self._removable = self._removable_types(rcl_algorithm, include_ions, include_polar) if remove_clashes else None
         rows, status = self._get_plan().eval_host(self._pos[None])
         self._store(rows, status)
         if lwrite:
@@ -236,21 +276,80 @@ class EFP(UNITS):
             return max(self._rms_central, self._rms_solvent_max)
         return self._rms_solvent_max
 
+    def get_forces(self, tot=False):
+        """Solvation forces on the solute's normal coordinates, a.u. (solefp.py:341-357): electrostatic,
+        repulsion and polarisation parts, each an array of nmodes.  The frame kernels work with mode-contracted
+        tables, so the per-mode values come from nmodes extra evaluations of the current frame with one-hot
+        mode weights (fi_m = dE/dQ_m is the shift obtained for g = -e_m)."""
+        par = self._bsm[int(self._ind[0])].get()
+        nmodes = int(par['nmodes'])
+        fl = self._flags(); fl['ea'] = False; fl['corr'] = False; fl['disp'] = False
+        fi = numpy.zeros((3, nmodes))
+        for m in range(nmodes):
+            g = numpy.zeros(nmodes); g[m] = -1.0
+            plan = Plan(self._ind, self._nmol, self._bsm, self._supl, self._reord, self._mode, fl, self._ccut, self._pcut,
+                        self._ecut, max_chunk=1, pol_maxit=self.pol_maxit, pol_tol=self.pol_tol, g_override=g,
+                        removable=self._removable)
+            rows, _ = plan.eval_host(self._pos[None])
+            fi[0, m] = rows[0, _lib.OUT['ele_mea']]; fi[1, m] = rows[0, _lib.OUT['rep_mea']]; fi[2, m] = rows[0, _lib.OUT['pol_mea']]
+        if tot:
+            return fi.sum(0)
+        return fi[0], fi[1], fi[2]
+
+    def eval_dma(self, dma, lwrite=False):
+        """Shift due to a non-EFP electrostatic environment (solefp.py:151-178, 798-903): SolCAMM + corrections of
+        the solute against point charges `dma[n,4]` = x,y,z,q (Bohr, a.u.), or against a tuple
+        (pos[n,3], q[n], dip[n,3], quad[n,6], oct[n,10]) of primitive (not traceless) moments.  No cut-offs and no
+        superimposition of the environment, as in the reference.  Runs through the same electrostatic kernel:
+        the environment enters as fixed pseudo-fragments of up to 16 sites anchored on a dummy atom."""
+        if isinstance(dma, numpy.ndarray):
+            assert dma.ndim == 2 and dma.shape[1] == 4, " Incorrect shape of ndarray! %s, The last dimension needs to be 4!" % (dma.shape,)
+            n = len(dma)
+            pos, q = dma[:, :3], dma[:, 3]
+            mu, Q, O = numpy.zeros((n, 3)), numpy.zeros((n, 6)), numpy.zeros((n, 10))
+        else:
+            pos, q, mu, Q, O = [numpy.asarray(x, numpy.float64) for x in dma]
+            n = len(pos)
+        solute = self._bsm[int(self._ind[0])]
+        natc = int(self._nmol[0])
+        bsm = [solute]; ind = [0]; nmol = [natc]
+        for c0 in range(0, n, 16):
+            sl = slice(c0, min(n, c0 + 16))
+            bsm.append(_ParHolder(dict(name='environment', natoms=1, pos=numpy.zeros((1, 3)), atno=numpy.zeros(1, int),
+                                       ndma=sl.stop - sl.start, rdma=pos[sl], dmac=q[sl], dmad=mu[sl], dmaq=Q[sl], dmao=O[sl])))
+            ind.append(len(bsm) - 1); nmol.append(1)
+        supl = [self._supl[int(self._ind[0])] if self._supl is not None else None] + [None] * (len(bsm) - 1)
+        reord = [self._reord[int(self._ind[0])] if self._reord is not None else None] + [None] * (len(bsm) - 1)
+        el = bool(self._elect)
+        flags = dict(elect=True, ea=bool(self._ea), corr=bool(self._corr), pol=False, disp=False, rep=False)
+        plan = Plan(ind, nmol, bsm, supl, reord, self._mode, flags, 1e10, 1e10, 1e10, max_chunk=1)
+        xyz = numpy.concatenate([self._pos[:natc], numpy.zeros((len(bsm) - 1, 3))])
+        rows, status = plan.eval_host(xyz[None])
+        c = self.HartreePerHbarToCmRec if self._cunit else 1.0
+        O_ = _lib.OUT
+        self._shift['ele_env_mea'] = float(rows[0, O_['ele_mea']]) * c; self._shift['ele_env_ea'] = float(rows[0, O_['ele_ea']]) * c
+        self._shift['cor_env_mea'] = float(rows[0, O_['cor_mea']]) * c; self._shift['cor_env_ea'] = float(rows[0, O_['cor_ea']]) * c
+        self._shift['tot_env'] = (self._shift['ele_env_mea'] + self._shift['ele_env_ea'] + self._shift['cor_env_mea']
+                                  + self._shift['cor_env_ea'])
+        self._rms_central = float(rows[0, O_['rms_c']])
+        if not numpy.isnan(self._shift['total']):
+            self._shift['total+env'] = self._shift['total'] + self._shift['tot_env']
+        return
+
     def get_dipind(self):
         """(induced dipoles, centres) at the polarisable centres inside pcut (solefp.py:307-309)."""
-        n = self._n_pol_centres()
-        dip, fld, rp = self._get_plan().pol_detail(0, n)
+        dip, fld, rp = self._pol_detail()
         return dip, rp
 
     def get_fields(self):
-        n = self._n_pol_centres()
-        dip, fld, rp = self._get_plan().pol_detail(0, n)
+        """(fields, centres) at the polarisable centres inside pcut (solefp.py:303-305)."""
+        dip, fld, rp = self._pol_detail()
         return fld, rp
 
-    def _n_pol_centres(self):
+    def _pol_detail(self):
         if not self.want_detail:
             raise RuntimeError('set efp.want_detail = True before eval() to keep fields / induced dipoles')
-        raise NotImplementedError
+        return self._get_plan().pol_detail(0)
 
     def __repr__(self):
         s = self._shift

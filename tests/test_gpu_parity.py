@@ -179,3 +179,75 @@ def test_exchange_repulsion_mixed_types(frags):
                        elect=True, rep=True, make_basis=lambda a, p: BasisSet(a, p))
     c = O.HartreePerHbarToCmRec
     assert abs(got['rep_mea'][0] - ref['rep_mea'] * c) < TOL * max(1.0, abs(ref['rep_mea'] * c) * 1e-3), (got['rep_mea'][0], ref['rep_mea'] * c)
+
+
+def test_remove_clashes_additive_polarisation(frags):
+    """EFP.eval(remove_clashes=True): NMA fragments ('N-methylacethamide' is on the reference's removable list)
+    leave the many-body induction and are treated pair-wise; water stays."""
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O
+    sol, wat, nma = frags('mescn'), frags('water'), frags('nma')
+    types = np.array([0, 1, 0, 0, 1, 0, 1, 0])
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos(), nma.get_pos()], types, 2, seed=41, spacing=9.0)
+    ind = [0] + [1 + t for t in types]; nmol = [7] + [3 if t == 0 else 12 for t in types]
+    c = O.HartreePerHbarToCmRec
+    for f in range(2):
+        efp = _efp(mode=4, disp=False, ccut=40.0, pcut=30.0, ecut=12.0)
+        efp.set(X[f], ind, nmol, [sol, wat, nma], [None] * 3, [None] * 3)
+        efp.eval(0, remove_clashes=True)
+        s = efp.get_shifts()
+        ref = O.eval_frame(X[f], ind, nmol, [sol.get(), wat.get(), nma.get()], [None] * 3, [None] * 3, 4, 40.0, 30.0, 12.0,
+                           elect=True, pol=True, removable={2})
+        assert abs(s['pol_mea'] - ref['pol_mea'] * c) < TOL, (s['pol_mea'], ref['pol_mea'] * c)
+        assert abs(s['pol_add_mea'] - ref['pol_add_mea'] * c) < TOL and abs(ref['pol_add_mea']) > 0
+        efp.eval(0)                                           # and without it: everything in the many-body solve
+        ref0 = O.eval_frame(X[f], ind, nmol, [sol.get(), wat.get(), nma.get()], [None] * 3, [None] * 3, 4, 40.0, 30.0, 12.0,
+                            elect=True, pol=True)
+        assert abs(efp.get_shifts()['pol_mea'] - ref0['pol_mea'] * c) < TOL and efp.get_shifts()['pol_add_mea'] == 0.0
+
+
+def test_eval_dma_point_charges(frags, golden):
+    """EFP.eval_dma against a point-charge environment (biomol.py:233-247 feeds 8 CONH charges; here 40 random)."""
+    from oracle import solefp_oracle as O
+    rng = np.random.default_rng(5)
+    xyz = scan_geometries(golden, 1)[0]
+    env = np.concatenate([rng.normal(0, 1, (40, 3)) * 3 + np.array([0, 0, 14.0]), rng.normal(0, 0.4, (40, 1))], 1)
+    efp = _efp(pol=False, disp=False)
+    efp.set(xyz, [0, 1], [12, 3], (frags('nma'), frags('water')), SCAN_SUPL, SCAN_REORD)
+    efp.eval(0)
+    efp.eval_dma(env)
+    s = efp.get_shifts()
+    ref = O.eval_dma_frame(xyz[:12], frags('nma').get(), SCAN_SUPL[0], 8, env)
+    c = O.HartreePerHbarToCmRec
+    for k in ('ele_env_mea', 'ele_env_ea', 'cor_env_mea', 'cor_env_ea'):
+        assert abs(s[k] - ref[k] * c) < TOL, (k, s[k], ref[k] * c)
+    assert abs(s['total+env'] - (s['total'] + s['tot_env'])) < 1e-12
+
+
+def test_get_forces_consistent_with_shifts(frags, golden):
+    """fi_m from the one-hot evaluations reproduce the shifts (term = -sum_m g_m fi_m) and match the oracle's fi."""
+    from slv_b200.plan import mode_weights
+    from oracle import solefp_oracle as O
+    xyz = scan_geometries(golden, 3)[2]
+    efp = _efp(disp=False, corr=False)
+    efp.set(xyz, [0, 1], [12, 3], (frags('nma'), frags('water')), SCAN_SUPL, SCAN_REORD)
+    efp.eval(0)
+    s = efp.get_shifts()
+    fe, fr, fp = efp.get_forces()
+    g, den = mode_weights(frags('nma').get(), 8)
+    c = O.HartreePerHbarToCmRec
+    assert abs(-(g * fe).sum() * c - s['ele_mea']) < TOL and abs(-(g * fp).sum() * c - s['pol_mea']) < TOL
+    ref = O.eval_frame(xyz, [0, 1], [12, 3], [frags('nma').get(), frags('water').get()], SCAN_SUPL, SCAN_REORD, 8,
+                       elect=True, corr=False, pol=True)
+    assert np.abs(fe - ref['fi_el']).max() < 1e-11 and np.abs(fp - ref['fi_pol']).max() < 1e-11
+
+
+def test_dipind_and_fields_detail(frags, golden):
+    from oracle import solefp_oracle as O
+    xyz = scan_geometries(golden, 2)[1]
+    efp = _efp(disp=False); efp.want_detail = True
+    efp.set(xyz, [0, 1], [12, 3], (frags('nma'), frags('water')), SCAN_SUPL, SCAN_REORD)
+    efp.eval(0)
+    dip, rp = efp.get_dipind(); fld, _ = efp.get_fields()
+    ref = O.eval_frame(xyz, [0, 1], [12, 3], [frags('nma').get(), frags('water').get()], SCAN_SUPL, SCAN_REORD, 8, elect=True, pol=True)
+    assert dip.shape == (25, 3) and np.abs(dip - ref['dipind']).max() < 1e-9 * np.abs(ref['dipind']).max() + 1e-12
