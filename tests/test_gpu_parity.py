@@ -251,3 +251,23 @@ def test_dipind_and_fields_detail(frags, golden):
     dip, rp = efp.get_dipind(); fld, _ = efp.get_fields()
     ref = O.eval_frame(xyz, [0, 1], [12, 3], [frags('nma').get(), frags('water').get()], SCAN_SUPL, SCAN_REORD, 8, elect=True, pol=True)
     assert dip.shape == (25, 3) and np.abs(dip - ref['dipind']).max() < 1e-9 * np.abs(ref['dipind']).max() + 1e-12
+
+
+def test_md_run_report_format(frags, golden, tmp_path):
+    """The MD frame loop (util/slv_md-run_nopp) end to end: $Frag input + trajectory in Angstrom -> report file."""
+    from slv_b200 import mdrun
+    from util import BohrToAngstrom
+    X = np.array(scan_geometries(golden, 5)) * BohrToAngstrom
+    inp = '$Frag\n  NMA  nma\n  supl 2,8,3,5\n  atoms 1-12  1\n$endFrag\n$Frag\n  water water\n  supl 1-3\n  atoms 13-15 1\n$endFrag\n'
+    out = tmp_path / 'shifts.dat'
+    rows, status = mdrun.run(inp, X, str(out), 8, cuts=(1e10, 1e10, 1e10), no_repul=True)
+    lines = out.read_text().split('\n')
+    assert lines[0].split()[:4] == ['#', 'Frame', 'EL-CAMM', 'EL-MEA'] and len(lines[0].split()) == 18
+    cols = lines[1].split()
+    assert len(cols) == 17 and cols[0] == '1'
+    f = golden['f']
+    assert abs(float(cols[1]) - round(f['solcamm'], 2)) < 0.011 and abs(float(cols[6]) - round(f['pol_mea'], 2)) < 0.011
+    assert abs(float(cols[12]) - round(f['dis_mea_iso'], 2)) < 0.011
+    for i in range(5):
+        ele = sum(float(lines[1 + i].split()[k]) for k in (2, 3, 4, 5))
+        assert abs(ele - golden['dat'][i][1]) < 0.03
