@@ -327,11 +327,12 @@ def pol_system(parc, solv):
     pol = np.concatenate([p['dpol'] for p in PAR]); polinv = np.linalg.inv(pol)
     N = len(rp)
     R = rp[:, None, :] - rd[None, :, :]
+    R = np.where((molp[:, None] != mold[None, :])[..., None], R, 1.0)       # own-molecule pairs are masked below
     Fij = _field_traceless(R, q[None], mu[None], Th[None], Om[None], 5.0)
     Fij = np.where((molp[:, None] != mold[None, :])[..., None], Fij, 0.0)
     F = Fij.sum(1)
     Rp = rp[:, None, :] - rp[None, :, :]
-    r2 = (Rp * Rp).sum(-1); np.fill_diagonal(r2, 1.0)
+    r2 = (Rp * Rp).sum(-1); r2 = np.where(molp[:, None] != molp[None, :], r2, 1.0)
     T = np.eye(3) / r2[..., None, None] ** 1.5 - 3.0 * np.einsum('ija,ijb->ijab', Rp, Rp) / r2[..., None, None] ** 2.5
     T = np.where((molp[:, None] != molp[None, :])[..., None, None], T, 0.0)
     D = T.transpose(0, 2, 1, 3).reshape(3 * N, 3 * N).copy()

@@ -271,3 +271,34 @@ def test_md_run_report_format(frags, golden, tmp_path):
     for i in range(5):
         ele = sum(float(lines[1 + i].split()[k]) for k in (2, 3, 4, 5))
         assert abs(ele - golden['dat'][i][1]) < 0.03
+
+
+def test_protein_like_mixed_fragments(frags):
+    """BASELINE config 4 shape, small: MeSCN probe among mixed EFP fragment types incl. charged residues and
+    one-atom ions (identity superimposition, slvpar.py:668-671), remove_clashes=True, full SolEFP incl. rep."""
+    from slv_b200 import synth
+    from slv_b200.basis import BasisSet
+    from oracle import solefp_oracle as O
+    names = ['water', 'mecoo-', 'menh3+', 'meoh', 'methane', 'phenol', 'benzene', 'chonh2', 'nma', 'na+', 'cl-']
+    sol = frags('mescn'); fr = [frags(n) for n in names]
+    rng = np.random.default_rng(44)
+    types = rng.integers(0, len(names), 30)
+    X = synth.make_trajectory(sol.get_pos(), [f.get_pos() for f in fr], types, 2, seed=44, spacing=11.0, rmin=3.5)
+    ind = [0] + [1 + int(t) for t in types]; nmol = [7] + [fr[t].get_natoms() for t in types]
+    bsm = [sol] + fr; nt = len(bsm)
+    cuts = (45.0, 16.0, 13.0)
+    efp = _efp(mode=4, rep=True, ccut=cuts[0], pcut=cuts[1], ecut=cuts[2])
+    c = O.HartreePerHbarToCmRec
+    pars = [b.get() for b in bsm]
+    for f in range(2):
+        efp.set(X[f], ind, nmol, bsm, [None] * nt, [None] * nt)
+        efp.eval(0, remove_clashes=True, include_ions=False, include_polar=False)
+        s = efp.get_shifts()
+        rem = efp._removable
+        assert rem == set(1 + names.index(n) for n in ('mecoo-', 'menh3+', 'meoh', 'methane', 'phenol', 'benzene', 'chonh2', 'nma'))
+        ref = O.eval_frame(X[f], ind, nmol, pars, [None] * nt, [None] * nt, 4, *cuts, elect=True, ea=True, corr=True, pol=True,
+                           disp=True, rep=True, make_basis=lambda a, p: BasisSet(a, p), removable=rem)
+        for k in TERMS + ('rep_mea',):
+            tol = TOL * max(1.0, abs(ref[k] * c) * 1e-3)
+            assert abs(s[k] - ref[k] * c) < tol, (f, k, s[k], ref[k] * c)
+        assert efp.get_status() == 0
