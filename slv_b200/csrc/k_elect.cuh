@@ -16,7 +16,7 @@ namespace slv {
 constexpr int ELECT_THREADS = 256;
 constexpr int SOLROW = 52;   // doubles per solute site in shared memory: pos3, smea20, sea20, cmea3, cea3 (+3 pad)
 
-__global__ void __launch_bounds__(ELECT_THREADS)
+__global__ void __launch_bounds__(ELECT_THREADS, 2)
 k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, FrameLists fl, double *__restrict__ out) {
   extern __shared__ double sm[];
   double *s_sol = sm;                                   // [ndma_c][SOLROW]

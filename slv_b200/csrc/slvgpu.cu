@@ -257,7 +257,7 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
   if (nframes == 0) return 0;
   CK(cudaMemsetAsync(d_status, 0, (size_t)nframes * sizeof(int32_t), st));
   const size_t sm_el = (size_t)pl->ndmac * SOLROW * sizeof(double);
-  const size_t sm_di = ((size_t)pl->npolc * DISP_SOLROW + 108 * DISP_THREADS) * sizeof(double);
+  const size_t sm_di = ((size_t)pl->npolc * DISP_SOLROW + (108 + 4) * DISP_TJ) * sizeof(double) + ((size_t)p.list_cap + 2) * sizeof(int);
   const size_t sm_po = ((size_t)POL_TILE * 10 + (size_t)pl->npolc * 21 + (size_t)pl->ndmac * 46) * sizeof(double);
   for (int64_t f0 = 0; f0 < nframes; f0 += pl->max_chunk) {
     const int nf = (int)((nframes - f0) < pl->max_chunk ? (nframes - f0) : pl->max_chunk);
