@@ -129,7 +129,7 @@ k_disp(const DevPlan p, int frame0, FrameLists fl, double *__restrict__ out) {
         const double Rx = row[0] - rj[0], Ry = row[1] - rj[1], Rz = row[2] - rj[2];
         const double ux = row[3], uy = row[4], uz = row[5];
         const double r2 = Rx * Rx + Ry * Ry + Rz * Rz;
-        const double iv = rsqrt64(r2), iv2 = iv * iv, iv5 = iv2 * iv2 * iv;
+        const double iv = rsqrt_fast(r2), iv2 = iv * iv, iv5 = iv2 * iv2 * iv;
         const double Ru = Rx * ux + Ry * uy + Rz * uz;
         // T = (3RR - r2)/r^5 and its directional derivative along u (u moves r_i)
         double T[9], dT[9];

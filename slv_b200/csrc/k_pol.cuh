@@ -18,7 +18,7 @@
 
 namespace slv {
 
-constexpr int POL_THREADS = 512;
+constexpr int POL_THREADS = 256;
 constexpr int POL_TILE = 512;    // centres staged per shared-memory tile of the sweep (== POL_THREADS)
 constexpr int SITE_ROW = 24;     // pos3, mom20, molecule id
 constexpr int PST = 30;          // BiCG state per centre: x xt r rt p pt u ut q qt (3 each)
@@ -34,7 +34,7 @@ struct PolWork {                 // per-CTA workspace (device pointers already o
   int *ent_soff;      // [list_cap] first site of a list entry
 };
 
-__global__ void __launch_bounds__(POL_THREADS)
+__global__ void __launch_bounds__(POL_THREADS, 2)
 k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, double *__restrict__ out, int *__restrict__ status,
       double *__restrict__ detail /* optional [nframes][cent_cap][9]: dipind, flds, rpol */, int *__restrict__ queue) {
   __shared__ double s_red[32];
@@ -231,15 +231,15 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
           double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0};
           for (int j0 = 0; j0 < ncent; j0 += POL_TILE) {
             __syncthreads();
-            if (tid < POL_TILE) {
-              const int j = j0 + tid;
+            for (int tl = tid; tl < POL_TILE; tl += NT) {
+              const int j = j0 + tl;
               if (j < ncent) {
-                double *tt = s_tile + tid * 10;
+                double *tt = s_tile + tl * 10;
                 tt[0] = wk.cent_pos[(size_t)j * 3]; tt[1] = wk.cent_pos[(size_t)j * 3 + 1]; tt[2] = wk.cent_pos[(size_t)j * 3 + 2];
                 const double *vj = stt + (size_t)j * PST + 18;
                 for (int d = 0; d < 6; ++d) tt[3 + d] = vj[d];
-                s_tmol[tid] = wk.cent_mol[j];
-              } else s_tmol[tid] = -2;
+                s_tmol[tl] = wk.cent_mol[j];
+              } else s_tmol[tl] = -2;
             }
             __syncthreads();
             if (act) {
@@ -252,13 +252,13 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
                 const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
                 const double Rx = rc[0] - tt[0], Ry = rc[1] - tt[1], Rz = rc[2] - tt[2];
                 const double r2 = same ? 1.0 : (Rx * Rx + Ry * Ry + Rz * Rz);
-                const double u = rsqrt64(r2), u2 = u * u;
+                const double u = rsqrt_fast(r2), u2 = u * u;
                 const double u3 = same ? 0.0 : u2 * u, t5 = 3.0 * u3 * u2;
-                const double Rxj = Rx * tt[3] + Ry * tt[4] + Rz * tt[5];
-                const double Ryj = Rx * tt[6] + Ry * tt[7] + Rz * tt[8];
-                const double fx = t5 * Rxj, fy = t5 * Ryj;
-                ax[0] += u3 * tt[3] - fx * Rx; ax[1] += u3 * tt[4] - fx * Ry; ax[2] += u3 * tt[5] - fx * Rz;
-                ay[0] += u3 * tt[6] - fy * Rx; ay[1] += u3 * tt[7] - fy * Ry; ay[2] += u3 * tt[8] - fy * Rz;
+                const double Rxj = fma(Rz, tt[5], fma(Ry, tt[4], Rx * tt[3]));
+                const double Ryj = fma(Rz, tt[8], fma(Ry, tt[7], Rx * tt[6]));
+                const double fx = -t5 * Rxj, fy = -t5 * Ryj;
+                ax[0] = fma(fx, Rx, fma(u3, tt[3], ax[0])); ax[1] = fma(fx, Ry, fma(u3, tt[4], ax[1])); ax[2] = fma(fx, Rz, fma(u3, tt[5], ax[2]));
+                ay[0] = fma(fy, Rx, fma(u3, tt[6], ay[0])); ay[1] = fma(fy, Ry, fma(u3, tt[7], ay[1])); ay[2] = fma(fy, Rz, fma(u3, tt[8], ay[2]));
               }
             }
           }

@@ -67,6 +67,7 @@ SLV_HD void ao_pair(const double A[3], const int la[3], int npa, const double *e
       const double b = eb[q];
       const double pp = a + b, ip = 1.0 / pp, h = 0.5 * ip;
       const double mu = a * b * ip;
+      if (mu * AB2 > 46.0) continue;      // exp(-46) = 1e-20: below FP64 resolution of every contracted integral
       const double pref = ca[p] * cb[q] * exp(-mu * AB2) * (3.14159265358979323846 * ip) * sqrt(3.14159265358979323846 * ip);
       // P - A = -b/p (A-B) ; P - B = a/p (A-B)
       const double fa = -b * ip, fb = a * ip;

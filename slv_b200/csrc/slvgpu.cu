@@ -205,7 +205,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   TRY(dalloc(pl, &pl->fl.list_flag, ch * p.list_cap));
   TRY(dalloc(pl, &pl->fl.list_xf, ch * p.list_cap * 12));
   if (d->flags & SLVGPU_POL) {
-    pl->pol_ctas = pl->sm_count;        // one persistent CTA per SM (512 threads, ~6 KB static smem + solute tables)
+    pl->pol_ctas = pl->sm_count * 2;    // two persistent 256-thread CTAs per SM: one frame each, their barrier phases interleave
     const size_t nc = (size_t)pl->pol_ctas, cc = (size_t)p.cent_cap;
     TRY(dalloc(pl, &pl->pw.cent_pos, nc * cc * 3));
     TRY(dalloc(pl, &pl->pw.cent_alpha, nc * cc * 9));
