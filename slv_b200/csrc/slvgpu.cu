@@ -314,7 +314,7 @@ extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, 
   if (!pl->copy_stream) CK(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
   // a short first slice hides the first copy; later slices are long so the persistent kernels keep a full queue
   const int64_t first = pl->max_chunk < 1024 ? pl->max_chunk : 1024;
-  const int64_t slice = pl->max_chunk < 4096 ? pl->max_chunk : 4096;
+  const int64_t slice = pl->max_chunk;      // everything after the first slice in as few launches as the scratch allows
   const int64_t nsl = nframes <= first ? 1 : 1 + (nframes - first + slice - 1) / slice;
   while ((int64_t)pl->copy_ev.size() < nsl) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); pl->copy_ev.push_back(e); }
   const size_t fstride = (size_t)p.natoms_total * 3;
