@@ -67,7 +67,7 @@ __device__ inline void rotate_vecl_rows(const DevPlan &p, const int *tm, const d
   }
 }
 
-__global__ void __launch_bounds__(REP_THREADS)
+__global__ void __launch_bounds__(REP_THREADS, 2)
 k_rep(const DevPlan p, int frame0, int nframes, FrameLists fl, RepWork rw, double *__restrict__ out) {
   extern __shared__ double sm[];
   __shared__ double s_red[32];

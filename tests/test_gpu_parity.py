@@ -302,3 +302,36 @@ def test_protein_like_mixed_fragments(frags):
             tol = TOL * max(1.0, abs(ref[k] * c) * 1e-3)
             assert abs(s[k] - ref[k] * c) < tol, (f, k, s[k], ref[k] * c)
         assert efp.get_status() == 0
+
+
+def test_reorder_with_missing_atoms_and_supl_subset(frags):
+    """Fragmented-residue case of biomol (solefp.py:1633-1645): the MD instance has fewer atoms than the parameter
+    fragment and lists them in another order; reorder carries -1 for the absent atoms and supl excludes them."""
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O
+    sol, wat, nma = frags('mescn'), frags('water'), frags('nma')
+    types = np.array([1, 0, 1, 0, 0, 1])
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos(), nma.get_pos()], types, 2, seed=51, spacing=9.5)
+    # MD layout of an NMA instance: parameter atoms 10 and 11 are absent, the remaining ten come in permuted order
+    perm = np.array([3, 0, 1, 2, 7, 6, 5, 4, 9, 8])               # MD atom m holds parameter atom perm[m]
+    reord_nma = np.full(12, -1); reord_nma[perm] = np.arange(10)  # parameter atom i sits at MD index reord[i]
+    supl_nma = np.array([0, 1, 2, 3, 4, 6])
+    cols = [np.arange(7)]; off = 7; nmol = [7]
+    for t in types:
+        if t == 0:
+            cols.append(off + np.arange(3)); nmol.append(3); off += 3
+        else:
+            cols.append(off + perm); nmol.append(10); off += 12
+    Xmd = np.ascontiguousarray(X[:, np.concatenate(cols), :])
+    ind = [0] + [1 + int(t) for t in types]
+    supl = [None, None, supl_nma]; reord = [None, None, reord_nma]
+    efp = _efp(mode=4, ccut=40.0, pcut=20.0, ecut=12.0)
+    rows, status = efp.eval_frames(Xmd, ind, nmol, [sol, wat, nma], supl, reord)
+    got = efp.shifts_of(rows)
+    c = O.HartreePerHbarToCmRec
+    for f in range(2):
+        ref = O.eval_frame(Xmd[f], ind, nmol, [sol.get(), wat.get(), nma.get()], supl, reord, 4, 40.0, 20.0, 12.0,
+                           elect=True, ea=True, corr=True, pol=True, disp=True)
+        for k in TERMS:
+            assert abs(got[k][f] - ref[k] * c) < TOL, (f, k, got[k][f], ref[k] * c)
+        assert abs(rows[f, 9] - ref['rms_smax']) < 1e-9 and abs(rows[f, 10] - ref['rms_ave']) < 1e-9
