@@ -71,6 +71,8 @@ enum {
   SLVGPU_M_O_BFEXP,   /* dtab: [nbasis][6] exponents                                             */
   SLVGPU_M_O_BFCOEF,  /* dtab: [nbasis][6] normalised contraction coefficients                   */
   SLVGPU_M_REMOVABLE, /* 1: polarisation of this type is treated pair-wise (remove_clashes)          */
+  SLVGPU_M_NSHELL,    /* number of basis shells                                                  */
+  SLVGPU_M_IO_SHELL,  /* itab: [nshell][4] atom, first function, functions in shell, primitives  */
   SLVGPU_NMETA = 32
 };
 

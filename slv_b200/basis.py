@@ -53,14 +53,18 @@ class BasisSet(object):
     """Function tables of one fragment at given atomic positions.
 
     Attributes (numpy): center[nbf] atom index, powers[nbf,3], nprim[nbf], exps[nbf,MAXPRIM],
-    coefs[nbf,MAXPRIM] (contraction coefficient x primitive norm x contracted norm; zero padded)."""
+    coefs[nbf,MAXPRIM] (contraction coefficient x primitive norm x contracted norm; zero padded);
+    shells[nshell,4] = atom, first function, number of functions (S 1, P 3, D 6, L = SP 4), primitives --
+    all functions of a shell share the exponents of its first function."""
 
     def __init__(self, atno, pos, name='6-311++G**'):
         tab = _table()
         center, powers, nprim, exps, coefs = [], [], [], [], []
+        shells = []            # (atom, first function, number of functions, number of primitives) per shell
         for ia, z in enumerate(numpy.asarray(atno, int)):
             for typ, prims in tab[_SYMBOL[int(z)]]:
                 subs = [('S', 1), ('P', 2)] if typ == 'L' else [(typ, 1)]
+                f0 = len(center)
                 for st, col in subs:
                     for (l, m, n) in _POWERS[st]:
                         e = [p[0] for p in prims]
@@ -69,7 +73,9 @@ class BasisSet(object):
                         center.append(ia); powers.append((l, m, n)); nprim.append(len(e))
                         exps.append(e + [1.0] * (MAXPRIM - len(e)))
                         coefs.append([x * nrm for x in c] + [0.0] * (MAXPRIM - len(e)))
+                shells.append((ia, f0, len(center) - f0, len(prims)))
         self.atno = numpy.asarray(atno, int)
+        self.shells = numpy.array(shells, numpy.int32).reshape(-1, 4)
         self.pos = numpy.asarray(pos, numpy.float64)
         self.center = numpy.array(center, numpy.int32)
         self.powers = numpy.array(powers, numpy.int32)

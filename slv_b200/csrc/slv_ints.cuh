@@ -93,4 +93,79 @@ SLV_HD void ao_pair(const double A[3], const int la[3], int npa, const double *e
   out[0] = S; out[1] = T; out[2] = dS; out[3] = dT;
 }
 
+// Shell-pair form: all functions of a shell share exponents and centre, so the three 1-D tables of a primitive
+// pair are built once and every (function of A, function of B) picks its entries from them.  nfa, nfb <= 6
+// (S 1, P 3, D 6, L = SP 4).  la/lb: [nf][3] Cartesian powers; ca/cb: [nf][6] normalised coefficients;
+// out[(fa*nfb + fb)*4 + q], q = S, T, L.dS, L.dT (overwritten).
+SLV_HD void shell_pair(const double A[3], int nfa, const int *la, int npa, const double *ea, const double *ca,
+                       const double B[3], int nfb, const int *lb, int npb, const double *eb, const double *cb,
+                       const double L[3], double *out) {
+  const double ABx = A[0] - B[0], ABy = A[1] - B[1], ABz = A[2] - B[2];
+  const double AB2 = ABx * ABx + ABy * ABy + ABz * ABz;
+  const int nout = nfa * nfb * 4;
+  for (int w = 0; w < nout; ++w) out[w] = 0.0;
+  double t[3][4][5];
+  for (int p = 0; p < npa; ++p) {
+    const double a = ea[p], a2 = 2.0 * a;
+    for (int q = 0; q < npb; ++q) {
+      const double b = eb[q];
+      const double pp = a + b, ip = 1.0 / pp, h = 0.5 * ip;
+      const double mu = a * b * ip;
+      if (mu * AB2 > 46.0) continue;
+      const double pref = exp(-mu * AB2) * (3.14159265358979323846 * ip) * sqrt(3.14159265358979323846 * ip);
+      const double fa_ = -b * ip, fb_ = a * ip;
+      const double AB[3] = {ABx, ABy, ABz};
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        const double PA = fa_ * AB[ax], PB = fb_ * AB[ax];
+        double (*s)[5] = t[ax];
+        s[0][0] = 1.0; s[0][1] = PB;
+#pragma unroll
+        for (int j = 1; j < 4; ++j) s[0][j + 1] = PB * s[0][j] + h * j * s[0][j - 1];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            double v = PA * s[i][j];
+            if (i > 0) v += h * i * s[i - 1][j];
+            if (j > 0) v += h * j * s[i][j - 1];
+            s[i + 1][j] = v;
+          }
+      }
+      const double k2 = -2.0 * b * b;
+      for (int fa = 0; fa < nfa; ++fa) {
+        const double cap = ca[fa * 6 + p] * pref;
+        for (int fb = 0; fb < nfb; ++fb) {
+          const double cc = cap * cb[fb * 6 + q];
+          double S0[3], T0[3], dS[3], dT[3];
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            const int i = la[fa * 3 + ax], j = lb[fb * 3 + ax];
+            const double (*s)[5] = t[ax];
+            const double k0 = b * (2.0 * j + 1.0), km = -0.5 * j * (j - 1.0);
+            const double s0 = s[i][j], sp = s[i + 1][j], sm = i > 0 ? s[i - 1][j] : 0.0;
+            const double s0p = s[i][j + 2], spp = s[i + 1][j + 2], smp = i > 0 ? s[i - 1][j + 2] : 0.0;
+            const double s0m = j > 1 ? s[i][j - 2] : 0.0, spm = j > 1 ? s[i + 1][j - 2] : 0.0, smm = (i > 0 && j > 1) ? s[i - 1][j - 2] : 0.0;
+            const double t0 = k0 * s0 + k2 * s0p + km * s0m;
+            const double tp = k0 * sp + k2 * spp + km * spm;
+            const double tm = k0 * sm + k2 * smp + km * smm;
+            S0[ax] = s0; T0[ax] = t0;
+            dS[ax] = a2 * sp - i * sm; dT[ax] = a2 * tp - i * tm;
+          }
+          const double sxy = S0[0] * S0[1], sxz = S0[0] * S0[2], syz = S0[1] * S0[2];
+          const double gS = L[0] * dS[0] * syz + L[1] * dS[1] * sxz + L[2] * dS[2] * sxy;
+          const double gT = L[0] * (dT[0] * syz + dS[0] * (T0[1] * S0[2] + S0[1] * T0[2]))
+                          + L[1] * (dT[1] * sxz + dS[1] * (T0[0] * S0[2] + S0[0] * T0[2]))
+                          + L[2] * (dT[2] * sxy + dS[2] * (T0[0] * S0[1] + S0[0] * T0[1]));
+          double *o = out + (fa * nfb + fb) * 4;
+          o[0] += cc * sxy * S0[2];
+          o[1] += cc * (T0[0] * syz + T0[1] * sxz + T0[2] * sxy);
+          o[2] += cc * gS;
+          o[3] += cc * gT;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace slv

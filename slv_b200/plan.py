@@ -103,6 +103,7 @@ class Plan(object):
                 m[M['O_VECL']] = dt.add(par['vecl']); m[M['O_ZNUC']] = dt.add(numpy.asarray(par['atno'], float))
                 m[M['IO_BFC']] = it.add(bfs.center); m[M['IO_BFL']] = it.add(bfs.powers); m[M['IO_BFNP']] = it.add(bfs.nprim)
                 m[M['O_BFEXP']] = dt.add(bfs.exps); m[M['O_BFCOEF']] = dt.add(bfs.coefs)
+                m[M['NSHELL']] = len(bfs.shells); m[M['IO_SHELL']] = it.add(bfs.shells)
         # ---- solute: mode-contracted tables
         sol = numpy.full(_lib.NSOL, -1, numpy.int32)
         S = _lib.S

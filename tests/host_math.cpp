@@ -20,3 +20,7 @@ void hm_ao_pair(const double* A, const int* la, int npa, const double* ea, const
 }
 }
 extern "C" void hm_site_field_acc(const double* R, const double* m, double f, double w, double* F) { slv::site_field_acc(R, m, f, w, F); }
+extern "C" void hm_shell_pair(const double* A, int nfa, const int* la, int npa, const double* ea, const double* ca,
+                              const double* B, int nfb, const int* lb, int npb, const double* eb, const double* cb, const double* L, double* out) {
+  slv::shell_pair(A, nfa, la, npa, ea, ca, B, nfb, lb, npb, eb, cb, L, out);
+}
