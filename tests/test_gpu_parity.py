@@ -335,3 +335,39 @@ def test_reorder_with_missing_atoms_and_supl_subset(frags):
         for k in TERMS:
             assert abs(got[k][f] - ref[k] * c) < TOL, (f, k, got[k][f], ref[k] * c)
         assert abs(rows[f, 9] - ref['rms_smax']) < 1e-9 and abs(rows[f, 10] - ref['rms_ave']) < 1e-9
+
+
+def test_full_size_batch_properties(frags):
+    """BASELINE config 2 at full frame count (10 000 frames of NMA-d7 + 500 waters, elect + pol): size-independent
+    properties instead of the (hours-long) oracle -- (1) a permutation of the frames permutes the rows bit-for-bit,
+    (2) the result does not depend on the internal chunking, (3) host and device entry points agree bit-for-bit,
+    (4) every frame converged, (5) the frames that are copies of the oracle-checked ones reproduce them."""
+    import torch
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O
+    sol, wat = frags('nma-d7'), frags('water')
+    nw, nu, nf = 500, 40, 10000
+    U = synth.make_trajectory(sol.get_pos(), [wat.get_pos()], np.zeros(nw, int), nu, seed=2)
+    rng = np.random.default_rng(0)
+    pick = rng.integers(0, nu, nf)
+    X = U[pick]
+    ind = [0] + [1] * nw; nmol = [12] + [3] * nw
+    efp = _efp(disp=False, ccut=40.0, pcut=17.0, ecut=12.0)
+    d = torch.from_numpy(X).cuda()
+    rows, status = efp.eval_frames(d, ind, nmol, [sol, wat], [None, None], [None, None])
+    rows = rows.cpu().numpy()
+    assert int(status.max()) == 0 and np.isfinite(rows).all()
+    ru, _ = efp.eval_frames(torch.from_numpy(U).cuda())
+    ru = ru.cpu().numpy()
+    assert np.array_equal(rows[:, :8], ru[pick][:, :8])                         # (1) + determinism
+    efp2 = _efp(disp=False, ccut=40.0, pcut=17.0, ecut=12.0); efp2.max_chunk = 777
+    r2, _ = efp2.eval_frames(d, ind, nmol, [sol, wat], [None, None], [None, None])
+    assert np.array_equal(r2.cpu().numpy()[:, :8], rows[:, :8])                 # (2)
+    rh, sh = efp.eval_frames(X)
+    assert np.array_equal(rh[:, :8], rows[:, :8]) and int(sh.max()) == 0        # (3)
+    c = O.HartreePerHbarToCmRec
+    ref = O.eval_frame(U[0], ind, nmol, [sol.get(), wat.get()], [None, None], [None, None], 8, 40.0, 17.0, 12.0,
+                       elect=True, ea=True, corr=True, pol=True)
+    s = efp.shifts_of(ru[:1])
+    for k in ('ele_mea', 'ele_ea', 'cor_mea', 'cor_ea', 'pol_mea'):
+        assert abs(s[k][0] - ref[k] * c) < TOL, (k, s[k][0], ref[k] * c)         # (5)
