@@ -30,6 +30,17 @@ sys.path.insert(0, ROOT)
 
 MODE = 8
 CUTS = (40.0, 17.0, 12.0)
+
+# BASELINE.json configs that fit one GPU; 2 is the configuration the metric is quoted on.
+WORKLOADS = {
+    2: dict(name='NMA-d7 + %(n)d waters, SolEFP elect(MEA+EA+corr)+pol', solute='nma-d7', solvents=['water'], nsolv=500, mode=8,
+            flags=dict(elect=True, corr=True, pol=True), frames=10000, spacing=5.87, seed=2),
+    3: dict(name='MeSCN in 50/50 water/DMSO (%(n)d fragments), full SolEFP elect+pol+rep+disp', solute='mescn',
+            solvents=['water', 'dmso'], nsolv=400, mode=4, flags=dict(elect=True, corr=True, pol=True, rep=True, disp=True),
+            frames=10000, spacing=9.5, seed=3, jit_lattice=0.3),
+    5: dict(name='NMA + %(n)d waters, full SolEFP elect+pol+rep+disp', solute='nma', solvents=['water'], nsolv=4000, mode=8,
+            flags=dict(elect=True, corr=True, pol=True, rep=True, disp=True), frames=2000, spacing=5.87, seed=5),
+}
 FLOPS_PER_T_PAIR = 43.0      # one (centre, centre) dipole-tensor apply to two vectors, DESIGN.md "k_pol"
 FLOPS_PER_FIELD_PAIR = 130.0  # one (centre, site) multipole field through octupoles
 FLOPS_PER_ELECT_PAIR = 300.0  # one (solute site, solvent site) pair through R^-4 with two moment sets + corrections
@@ -41,23 +52,29 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
-    ap.add_argument('--frames', type=int, default=10000, help='frames per GPU per step')
-    ap.add_argument('--waters', type=int, default=500)
+    ap.add_argument('--config', type=int, default=2, choices=sorted(WORKLOADS), help='BASELINE.json config number')
+    ap.add_argument('--frames', type=int, default=0, help='frames per GPU per step (0 = the config default)')
+    ap.add_argument('--waters', type=int, default=0, help='solvent fragments (0 = the config default)')
     ap.add_argument('--unique', type=int, default=250, help='distinct generated frames (tiled up to --frames)')
     ap.add_argument('--cpu-sample', type=int, default=3, help='frames of the cpu_baseline sample')
     return ap.parse_args()
 
 
-def make_frames(nw, nunique, nframes, seed, rank):
+def make_frames(wl, nw, nunique, nframes, rank):
+    """Synthetic trajectory of the workload: returns (bsm list, ind, nmol, coords[nframes, natoms, 3])."""
     import numpy as np
     from slv_b200 import synth
     from slv_b200.slvpar import Frag
-    sol, wat = Frag('nma-d7'), Frag('water')
+    sol = Frag(wl['solute']); solv = [Frag(n) for n in wl['solvents']]
+    types = np.random.default_rng(wl['seed']).integers(0, len(solv), nw) if len(solv) > 1 else np.zeros(nw, int)
     nu = min(nunique, nframes)
-    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos()], np.zeros(nw, int), nu, seed=seed + 1000 * rank)
+    X = synth.make_trajectory(sol.get_pos(), [f.get_pos() for f in solv], types, nu, seed=wl['seed'] + 1000 * rank,
+                              spacing=wl['spacing'], jit_lattice=wl.get('jit_lattice', 0.6))
     reps = (nframes + nu - 1) // nu
     X = np.concatenate([X] * reps)[:nframes]
-    return sol, wat, np.ascontiguousarray(X)
+    ind = [0] + [1 + int(t) for t in types]
+    nmol = [sol.get_natoms()] + [solv[t].get_natoms() for t in types]
+    return [sol] + solv, ind, nmol, np.ascontiguousarray(X)
 
 
 class ClockSampler(threading.Thread):
@@ -87,17 +104,18 @@ class ClockSampler(threading.Thread):
                     samples=len(s))
 
 
-def cpu_reference_frames(X, nw, nsample):
+def cpu_reference_frames(wl, bsm, ind, nmol, X, nsample):
     """Oracle port timed on the host cores: returns (frames/s, seconds, nframes)."""
-    import numpy as np
-    from slv_b200.slvpar import Frag
+    from slv_b200.basis import BasisSet
     from oracle import solefp_oracle as O
-    pars = [Frag('nma-d7').get(), Frag('water').get()]
-    ind = [0] + [1] * nw; nmol = [12] + [3] * nw
+    pars = [b.get() for b in bsm]
+    nt = len(bsm)
+    fl = wl['flags']
     t0 = time.time()
     for f in range(nsample):
-        O.eval_frame(X[f % len(X)], ind, nmol, pars, [None, None], [None, None], MODE, *CUTS,
-                     elect=True, ea=True, corr=True, pol=True, disp=False, literal_gemm=True)
+        O.eval_frame(X[f % len(X)], ind, nmol, pars, [None] * nt, [None] * nt, wl['mode'], *CUTS,
+                     elect=True, ea=True, corr=True, pol=fl.get('pol', False), disp=fl.get('disp', False),
+                     rep=fl.get('rep', False), make_basis=lambda a_, p_: BasisSet(a_, p_), literal_gemm=True)
     dt = time.time() - t0
     return nsample / dt, dt, nsample
 
@@ -106,21 +124,22 @@ def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sol, wat, X = make_frames(a.waters, 8, 8, 2, 0)
+    wl = WORKLOADS[a.config]; nw = a.waters or wl['nsolv']
+    bsm, ind, nmol, X = make_frames(wl, nw, 8, 8, 0)
     per_step = 1
     for _ in range(a.warmup):
-        cpu_reference_frames(X, a.waters, per_step)
+        cpu_reference_frames(wl, bsm, ind, nmol, X, per_step)
     t0 = time.time()
     for s in range(a.steps):
-        cpu_reference_frames(X[s % len(X):], a.waters, per_step)
+        cpu_reference_frames(wl, bsm, ind, nmol, X[s % len(X):], per_step)
     dt = time.time() - t0
     fps = a.steps * per_step / dt
     cores = os.cpu_count()
     line = dict(metric='md_frames_per_sec', value=fps, unit='frames/s', n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                 ms_per_step=dt / a.steps * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
                 data='synthetic', impl='reference',
-                config=dict(workload='NMA-d7 + %d waters, SolEFP elect(MEA+EA+corr)+pol, mode 8, ccut/pcut/ecut 40/17/12 Bohr' % a.waters,
-                            frames_per_step=per_step),
+                config=dict(workload=(wl['name'] % dict(n=nw)) + ', mode %d, ccut/pcut/ecut 40/17/12 Bohr' % wl['mode'],
+                            baseline_config=a.config, frames_per_step=per_step),
                 cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port',
                                   sample='%d frame(s) per step of the same synthetic workload; NumPy/BLAS restatement with the '
                                          'reference cost structure (LU inverse + 2 DGEMM per mode)' % per_step),
@@ -144,11 +163,12 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    nw = a.waters
-    sol, wat, X = make_frames(nw, a.unique, a.frames, 2, rank)
-    ind = [0] + [1] * nw; nmol = [12] + [3] * nw
-    efp = EFP(elect=True, pol=True, corr=True, freq=True, mode=MODE, ccut=CUTS[0], pcut=CUTS[1], ecut=CUTS[2], cunit=True)
-    efp.max_chunk = min(a.frames, 10240)
+    wl = WORKLOADS[a.config]
+    nw = a.waters or wl['nsolv']; nframes = a.frames or wl['frames']
+    bsm, ind, nmol, X = make_frames(wl, nw, a.unique, nframes, rank)
+    nt = len(bsm)
+    efp = EFP(freq=True, mode=wl['mode'], ccut=CUTS[0], pcut=CUTS[1], ecut=CUTS[2], cunit=True, **wl['flags'])
+    efp.max_chunk = min(nframes, 10240)
     d_coords = torch.from_numpy(X).to(dev)
     h_coords = torch.from_numpy(X).pin_memory()
     nf = d_coords.shape[0]
@@ -159,7 +179,7 @@ def main():
 
     def step_device():
         nonlocal plan
-        r, s = efp.eval_frames(d_coords, ind, nmol, [sol, wat], [None, None], [None, None]) if plan is None else plan.eval_device(d_coords, rows, status)
+        r, s = efp.eval_frames(d_coords, ind, nmol, bsm, [None] * nt, [None] * nt) if plan is None else plan.eval_device(d_coords, rows, status)
         if plan is None:
             plan = efp._get_plan()
             rows.copy_(r); status.copy_(s)
@@ -212,26 +232,27 @@ def main():
         total_frames = nf * world
         fps = total_frames * a.steps / (ms * 1e-3)
         npol = r[:, _lib.OUT['n_pol']]; nel = r[:, _lib.OUT['n_elect']]; its = r[:, _lib.OUT['pol_iters']]
-        ncent = 20 + 5 * npol; nsite = 12 + 5 * npol
-        tpairs = ncent * ncent - (400 + 25 * npol)
+        ncent = r[:, _lib.OUT['pol_ncent']]; nsite = r[:, _lib.OUT['pol_nsite']]; tpairs = r[:, _lib.OUT['pol_pairs']]
         pol_flops = float((its * tpairs * FLOPS_PER_T_PAIR + ncent * nsite * FLOPS_PER_FIELD_PAIR).sum())
         pol_ms = max(ms_pol, 1e-9) / a.steps
-        elect_pairs = float((12 * 5 * nel).sum())
+        ndma_c = int(bsm[0].get()['ndma'])
+        ndma_s = float(np.mean([bsm[i].get()['ndma'] for i in ind[1:]]))
+        elect_pairs = float((ndma_c * ndma_s * nel).sum())
         peak = 34.0
         pk = os.path.join(ROOT, 'profiles', 'fp64_peak_r01.json')
         if os.path.isfile(pk):
             peak = json.load(open(pk))['fp64_dfma_tflops']
         achieved = pol_flops / (pol_ms * 1e-3) / 1e12
         hbm = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.isfile(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
-        cpu_fps, cpu_dt, cpu_n = cpu_reference_frames(X, nw, a.cpu_sample)
+        cpu_fps, cpu_dt, cpu_n = cpu_reference_frames(wl, bsm, ind, nmol, X, a.cpu_sample)
         line = dict(
             metric='md_frames_per_sec', value=fps, unit='frames/s', n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
             ms_per_step=ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
-            config=dict(workload='NMA-d7 + %d waters, SolEFP elect(MEA+EA+corr)+pol, mode 8, ccut/pcut/ecut 40/17/12 Bohr, '
-                                 '%d frames per GPU per step' % (nw, nf),
-                        frames_per_gpu=nf, l2='inputs larger than L2 (%.0f MB of coordinates per step)' % (X.nbytes / 1e6),
+            config=dict(workload=(wl['name'] % dict(n=nw)) + ', mode %d, ccut/pcut/ecut 40/17/12 Bohr, %d frames per GPU per step' % (wl['mode'], nf),
+                        baseline_config=a.config, frames_per_gpu=nf, l2='inputs larger than L2 (%.0f MB of coordinates per step)' % (X.nbytes / 1e6),
                         parallelism='frames sharded over %d rank(s), one gather of the result rows' % world,
-                        mean_waters_in_pcut=float(npol.mean()), mean_pol_iters=float(its.mean()), status_max=st),
+                        mean_fragments_in_pcut=float(npol.mean()), mean_pol_iters=float(its.mean()), status_max=st,
+                        kernel_ms_per_step=dict((k, v[0] / a.steps) for k, v in ktimes.items())),
             pair_interactions_per_sec=elect_pairs * world * a.steps / (ms * 1e-3),
             pol_tensor_pairs_per_sec=float((its * tpairs).sum()) * world * a.steps / (ms * 1e-3),
             gpu_launches=int(launches_per_step * a.steps + (1 if world > 1 else 0) * a.steps * 0),

@@ -40,6 +40,9 @@ enum {
   SLVGPU_N_ELECT = 11, SLVGPU_N_POL = 12, SLVGPU_N_REP = 13,
   SLVGPU_POL_ITERS = 14, SLVGPU_POL_RESID = 15,
   SLVGPU_POL_ADD = 16,   /* part of POL_MEA from the additive two-body solves of removable fragments */
+  SLVGPU_POL_NCENT = 17, /* polarisable centres of the many-body solve                                  */
+  SLVGPU_POL_NSITE = 18, /* DMTP sites contributing fields                                              */
+  SLVGPU_POL_PAIRS = 19, /* ordered centre pairs of different molecules = dipole-tensor applies per sweep */
   SLVGPU_NOUT = 20
 };
 

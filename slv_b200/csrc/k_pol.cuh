@@ -70,7 +70,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     // Pass -1 is the many-body solve over the pol-layer fragments whose type is not flagged removable; every
     // removable fragment (EFP.eval(remove_clashes=True), solvshift/solefp.py:1224-1236, 1333-1404, 1722-1773) then
     // gets its own two-body solve with the solute, and the shifts add.
-    double shift_main = 0.0, shift_add = 0.0, resid_out = 0.0;
+    double shift_main = 0.0, shift_add = 0.0, resid_out = 0.0, pairs_out = 0.0, ncent_out = 0.0, nsite_out = 0.0;
     int iters_out = 0;
     for (int pass = -1;;) {
     auto included = [&](int e) -> bool {
@@ -83,12 +83,14 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     // offsets by a block-wide exclusive scan over the list entries (ordered, deterministic)
     {
       int run_c = npolc, run_s = ndmac;
+      double sq = 0.0;                       // sum of npol^2 over the included fragments (for the pair count)
       for (int e0 = 0; e0 < nl; e0 += NT) {
         const int e = e0 + tid;
         int nc = 0, ns = 0;
         if (e < nl && included(e)) {
           const int *tm = tmeta(p, p.inst_type[fl.list_inst[lbase + e]]);
           nc = tm[SLVGPU_M_NPOL]; ns = tm[SLVGPU_M_NDMA];
+          sq += (double)nc * nc;
         }
         // pack both counts into one 64-bit value for a single scan
         unsigned long long v = ((unsigned long long)nc << 32) | (unsigned)ns, incl = v;
@@ -107,7 +109,9 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
         if (e < nl) { wk.ent_coff[e] = run_c + (int)(excl >> 32); wk.ent_soff[e] = run_s + (int)(excl & 0xffffffffu); }
         run_c += (int)(tot >> 32); run_s += (int)(tot & 0xffffffffu);
       }
+      sq = block_sum(sq, s_red);
       if (tid == 0) { s_n[0] = run_c; s_n[1] = run_s; }
+      if (pass < 0) pairs_out = (double)run_c * run_c - sq - (double)npolc * npolc;
     }
     __syncthreads();
     const int ncent = s_n[0], nsite = s_n[1];
@@ -385,7 +389,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       }
     }
     acc = block_sum(acc, s_red);
-    if (pass < 0) { shift_main = -0.5 * acc; iters_out = iters; resid_out = resid; }
+    if (pass < 0) { shift_main = -0.5 * acc; iters_out = iters; resid_out = resid; ncent_out = ncent; nsite_out = nsite; }
     else { shift_add += -0.5 * acc; resid_out = fmax(resid_out, resid); }
     if (detail && pass < 0) {
       double *dd = detail + (size_t)fi * ((size_t)p.cent_cap * 9 + 1);
@@ -416,6 +420,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       o[SLVGPU_POL_ADD] = shift_add;
       o[SLVGPU_POL_ITERS] = (double)iters_out;
       o[SLVGPU_POL_RESID] = resid_out;
+      o[SLVGPU_POL_NCENT] = ncent_out; o[SLVGPU_POL_NSITE] = nsite_out; o[SLVGPU_POL_PAIRS] = pairs_out;
       if (resid_out > p.pol_tol) status[frame0 + fi] |= SLVGPU_ST_POL_NOCONV;
     }
     __syncthreads();
