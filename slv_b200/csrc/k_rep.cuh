@@ -139,7 +139,9 @@ k_rep(const DevPlan p, int frame0, int nframes, FrameLists fl, RepWork rw, doubl
       {
         const int *bcB = p.itab + tm[SLVGPU_M_IO_BFC], *blB = p.itab + tm[SLVGPU_M_IO_BFL], *bnB = p.itab + tm[SLVGPU_M_IO_BFNP];
         const double *beB = p.dtab + tm[SLVGPU_M_O_BFEXP], *bfB = p.dtab + tm[SLVGPU_M_O_BFCOEF];
-        for (int w = tid; w < nbsA * nbsB; w += NT) {
+        const int *order = p.itab + tm[SLVGPU_M_IO_PAIRORDER];      // cost/class-sorted: warp lanes run equal-length loops
+        for (int wi = tid; wi < nbsA * nbsB; wi += NT) {
+          const int w = order[wi];
           const int k = w / nbsB, l = w % nbsB;
           const int ak = bcA[k], al = bcB[l];
           const int la[3] = {blA[k * 3], blA[k * 3 + 1], blA[k * 3 + 2]}, lb[3] = {blB[l * 3], blB[l * 3 + 1], blB[l * 3 + 2]};

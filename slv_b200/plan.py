@@ -71,6 +71,7 @@ class Plan(object):
         M = _lib.M
         pars = [b.get() for b in bsm]
         need_rep = bool(self.flags & _lib.FLAG['rep'])
+        self._bfs = {}
         for t, par in enumerate(pars):
             nat = int(par['natoms'])
             sl = supl[t] if supl is not None and supl[t] is not None else numpy.arange(nat)
@@ -104,6 +105,16 @@ class Plan(object):
                 m[M['IO_BFC']] = it.add(bfs.center); m[M['IO_BFL']] = it.add(bfs.powers); m[M['IO_BFNP']] = it.add(bfs.nprim)
                 m[M['O_BFEXP']] = dt.add(bfs.exps); m[M['O_BFCOEF']] = dt.add(bfs.coefs)
                 m[M['NSHELL']] = len(bfs.shells); m[M['IO_SHELL']] = it.add(bfs.shells)
+                self._bfs[t] = bfs
+        # ---- exchange-repulsion work order: for every fragment type B, the (solute AO, B AO) pairs sorted by their
+        #      primitive-pair count and angular-momentum class, so that the 32 lanes of a warp run equal-length loops
+        if need_rep and int(ind[0]) in self._bfs:
+            bA = self._bfs[int(ind[0])]
+            for t, bB in self._bfs.items():
+                cost = (bA.nprim[:, None] * bB.nprim[None, :]).ravel()
+                cls = (bA.powers.sum(1)[:, None] * 3 + bB.powers.sum(1)[None, :]).ravel()
+                order = numpy.lexsort((cls, -cost)).astype(numpy.int32)
+                meta[t][M['IO_PAIRORDER']] = it.add(order)
         # ---- solute: mode-contracted tables
         sol = numpy.full(_lib.NSOL, -1, numpy.int32)
         S = _lib.S
