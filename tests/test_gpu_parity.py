@@ -371,3 +371,23 @@ def test_full_size_batch_properties(frags):
     s = efp.shifts_of(ru[:1])
     for k in ('ele_mea', 'ele_ea', 'cor_mea', 'cor_ea', 'pol_mea'):
         assert abs(s[k][0] - ref[k] * c) < TOL, (k, s[k][0], ref[k] * c)         # (5)
+
+
+def test_large_polarisation_system_multi_tile(frags):
+    """No pcut: 230 waters -> 1170 polarisable centres (NDIM 3510), more than one 512-centre tile per sweep and more
+    than one centre per thread; polarisation and dispersion against the dense LU oracle."""
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O
+    sol, wat = frags('nma'), frags('water')
+    nw = 230
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos()], np.zeros(nw, int), 1, seed=61)
+    ind = [0] + [1] * nw; nmol = [12] + [3] * nw
+    efp = _efp(ccut=1e10, pcut=1e10, ecut=8.0)
+    rows, status = efp.eval_frames(X, ind, nmol, [sol, wat], [None, None], [None, None])
+    got = efp.shifts_of(rows)
+    assert rows[0, 17] == 20 + 5 * nw and int(status[0]) == 0
+    ref = O.eval_frame(X[0], ind, nmol, [sol.get(), wat.get()], [None, None], [None, None], 8, 1e10, 1e10, 8.0,
+                       elect=True, ea=True, corr=True, pol=True, disp=True)
+    c = O.HartreePerHbarToCmRec
+    for k in TERMS:
+        assert abs(got[k][0] - ref[k] * c) < TOL, (k, got[k][0], ref[k] * c)
