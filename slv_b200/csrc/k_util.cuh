@@ -17,11 +17,13 @@ __global__ void k_kabsch_one(const double *ref, const double *tgt, int n, double
     for (int k = 0; k < n; ++k)
       for (int d = 0; d < 3; ++d) { c1[d] += ref[k * 3 + d]; c2[d] += tgt[k * 3 + d]; }
     for (int d = 0; d < 3; ++d) { c1[d] /= n; c2[d] /= n; }
-    double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, gsum = 0.0;
     for (int k = 0; k < n; ++k)
-      for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < 3; ++i) {
         for (int j = 0; j < 3; ++j) a[i * 3 + j] += (ref[k * 3 + i] - c1[i]) * (tgt[k * 3 + j] - c2[j]);
-    kabsch_rot(a, rot);
+        gsum += (ref[k * 3 + i] - c1[i]) * (ref[k * 3 + i] - c1[i]) + (tgt[k * 3 + i] - c2[i]) * (tgt[k * 3 + i] - c2[i]);
+      }
+    kabsch_rot(a, gsum, rot);
     double t1[3];
     rot_vec(rot, c1, t1);
     for (int d = 0; d < 3; ++d) tr[d] = c2[d] - t1[d];

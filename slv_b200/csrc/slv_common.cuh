@@ -100,7 +100,7 @@ __device__ inline void fit_instance(const DevPlan &p, const int *tm, const doubl
   const double inv = 1.0 / (double)nsupl;
 #pragma unroll
   for (int d = 0; d < 3; ++d) { c1[d] *= inv; c2[d] *= inv; }
-  double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, gsum = 0.0;
   for (int k = 0; k < nsupl; ++k) {
     const int ip = supl[k], md = reord[ip];
     double c[3], r[3];
@@ -113,8 +113,9 @@ __device__ inline void fit_instance(const DevPlan &p, const int *tm, const doubl
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int j = 0; j < 3; ++j) a[i * 3 + j] += c[i] * r[j];
+    gsum += c[0] * c[0] + c[1] * c[1] + c[2] * c[2] + r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
   }
-  kabsch_rot(a, rot);
+  kabsch_rot(a, gsum, rot);
   double t1[3];
   rot_vec(rot, c1, t1);
 #pragma unroll

@@ -32,7 +32,7 @@ SLV_HD constexpr int sym3(int a, int b, int c) {
 // Horn's quaternion form; the dominant eigenvector of the 4x4 symmetric matrix is found with
 // cyclic Jacobi sweeps (robust for planar / near-degenerate atom sets such as water).  Gives the
 // same rotation as the SVD route with the det<0 reflection fix (slvpar.py:646-652).
-SLV_HD void kabsch_rot(const double a[9], double rot[9]) {
+SLV_HD void kabsch_rot_jacobi(const double a[9], double rot[9]) {
   const double Sxx = a[0], Sxy = a[1], Sxz = a[2], Syx = a[3], Syy = a[4], Syz = a[5], Szx = a[6], Szy = a[7], Szz = a[8];
   double N[4][4] = {{Sxx + Syy + Szz, Syz - Szy, Szx - Sxz, Sxy - Syx},
                     {Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz},
@@ -85,6 +85,66 @@ SLV_HD void kabsch_rot(const double a[9], double rot[9]) {
   const double nrm = 1.0 / sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
   q0 *= nrm; q1 *= nrm; q2 *= nrm; q3 *= nrm;
   // column-vector rotation M (r = M c); the row-vector matrix is its transpose: rot[a][i] = M[i][a]
+  const double M00 = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3, M01 = 2.0 * (q1 * q2 - q0 * q3), M02 = 2.0 * (q1 * q3 + q0 * q2);
+  const double M10 = 2.0 * (q1 * q2 + q0 * q3), M11 = q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3, M12 = 2.0 * (q2 * q3 - q0 * q1);
+  const double M20 = 2.0 * (q1 * q3 - q0 * q2), M21 = 2.0 * (q2 * q3 + q0 * q1), M22 = q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3;
+  rot[0] = M00; rot[1] = M10; rot[2] = M20;
+  rot[3] = M01; rot[4] = M11; rot[5] = M21;
+  rot[6] = M02; rot[7] = M12; rot[8] = M22;
+}
+
+// Fast path of the same problem: the dominant eigenvector of Horn's matrix N by shifted inverse iteration.
+// With GA = sum|c_k|^2 and GB = sum|r_k|^2 (passed as gsum = GA + GB) the largest eigenvalue obeys
+// lambda_1 <= gsum/2, with equality for a perfect fit, so mu = gsum/2 (1 + 1e-7) makes mu I - N symmetric
+// positive definite: one 4x4 Cholesky factorisation, then a few triangular solves; the iteration contracts by
+// (mu - lambda_1)/(mu - lambda_2) per step (<< 1 for rigid fragments).  Convergence is verified on the
+// eigen-residual; anything that does not converge (poor fits, near-degenerate atom sets) goes to the
+// Jacobi solver above, so the result is the same rotation either way.
+SLV_HD void kabsch_rot(const double a[9], double gsum, double rot[9]) {
+  const double Sxx = a[0], Sxy = a[1], Sxz = a[2], Syx = a[3], Syy = a[4], Syz = a[5], Szx = a[6], Szy = a[7], Szz = a[8];
+  const double n00 = Sxx + Syy + Szz, n01 = Syz - Szy, n02 = Szx - Sxz, n03 = Sxy - Syx;
+  const double n11 = Sxx - Syy - Szz, n12 = Sxy + Syx, n13 = Szx + Sxz;
+  const double n22 = -Sxx + Syy - Szz, n23 = Syz + Szy, n33 = -Sxx - Syy + Szz;
+  const double mu = 0.5 * gsum * (1.0 + 1e-7) + 1e-300;
+  // Cholesky of M = mu I - N = L L^T
+  const double m00 = mu - n00, m11 = mu - n11, m22 = mu - n22, m33 = mu - n33;
+  bool ok = m00 > 0.0;
+  const double l00 = sqrt(m00), i00 = 1.0 / l00;
+  const double l10 = -n01 * i00, l20 = -n02 * i00, l30 = -n03 * i00;
+  const double d1 = m11 - l10 * l10;
+  ok = ok && d1 > 0.0;
+  const double l11 = sqrt(d1), i11 = 1.0 / l11;
+  const double l21 = (-n12 - l20 * l10) * i11, l31 = (-n13 - l30 * l10) * i11;
+  const double d2 = m22 - l20 * l20 - l21 * l21;
+  ok = ok && d2 > 0.0;
+  const double l22 = sqrt(d2), i22 = 1.0 / l22;
+  const double l32 = (-n23 - l30 * l20 - l31 * l21) * i22;
+  const double d3 = m33 - l30 * l30 - l31 * l31 - l32 * l32;
+  ok = ok && d3 > 0.0;
+  const double i33 = 1.0 / sqrt(d3);
+  double q0 = 1.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+  if (ok) {
+    // start from the row of adj-like guess: any vector not orthogonal to v1; use (1,1,1,1) mixed with e0
+    q0 = 1.0; q1 = 0.37; q2 = -0.23; q3 = 0.11;
+    for (int it = 0; it < 4; ++it) {
+      // L y = q
+      const double y0 = q0 * i00, y1 = (q1 - l10 * y0) * i11, y2 = (q2 - l20 * y0 - l21 * y1) * i22;
+      const double y3 = (q3 - l30 * y0 - l31 * y1 - l32 * y2) * i33;
+      // L^T x = y
+      const double x3 = y3 * i33, x2 = (y2 - l32 * x3) * i22, x1 = (y1 - l21 * x2 - l31 * x3) * i11;
+      const double x0 = (y0 - l10 * x1 - l20 * x2 - l30 * x3) * i00;
+      const double nr = 1.0 / sqrt(x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3);
+      q0 = x0 * nr; q1 = x1 * nr; q2 = x2 * nr; q3 = x3 * nr;
+    }
+    // eigen-residual check
+    const double w0 = n00 * q0 + n01 * q1 + n02 * q2 + n03 * q3, w1 = n01 * q0 + n11 * q1 + n12 * q2 + n13 * q3;
+    const double w2 = n02 * q0 + n12 * q1 + n22 * q2 + n23 * q3, w3 = n03 * q0 + n13 * q1 + n23 * q2 + n33 * q3;
+    const double lam = q0 * w0 + q1 * w1 + q2 * w2 + q3 * w3;
+    const double r0 = w0 - lam * q0, r1 = w1 - lam * q1, r2 = w2 - lam * q2, r3 = w3 - lam * q3;
+    const double res2 = r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
+    ok = res2 <= 1e-28 * mu * mu && lam > 0.0;
+  }
+  if (!ok) { kabsch_rot_jacobi(a, rot); return; }
   const double M00 = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3, M01 = 2.0 * (q1 * q2 - q0 * q3), M02 = 2.0 * (q1 * q3 + q0 * q2);
   const double M10 = 2.0 * (q1 * q2 + q0 * q3), M11 = q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3, M12 = 2.0 * (q2 * q3 - q0 * q1);
   const double M20 = 2.0 * (q1 * q3 - q0 * q2), M21 = 2.0 * (q2 * q3 + q0 * q1), M22 = q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3;

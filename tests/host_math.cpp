@@ -2,7 +2,8 @@
 // TEST INFRASTRUCTURE: the product never loads this.
 #include "../slv_b200/csrc/slv_math.cuh"
 extern "C" {
-void hm_kabsch_rot(const double* a, double* rot) { slv::kabsch_rot(a, rot); }
+void hm_kabsch_rot(const double* a, double* rot) { slv::kabsch_rot_jacobi(a, rot); }
+void hm_kabsch_rot_fast(const double* a, double gsum, double* rot) { slv::kabsch_rot(a, gsum, rot); }
 void hm_rot_mom20(const double* R, const double* m, double* o) { slv::rot_mom20(R, m, o); }
 void hm_rot_mat(const double* R, const double* a, double* o) { slv::rot_mat(R, a, o); }
 void hm_pair_potentials(const double* rA, const double* rB, const double* mB, double* P) { slv::pair_potentials(rA, rB, mB, P); }

@@ -16,6 +16,7 @@ P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
 def L():
     lib = ctypes.CDLL(LIBP)
     lib.hm_site_field.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
+    lib.hm_kabsch_rot_fast.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
     lib.hm_site_dfield.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
     return lib
 
@@ -42,6 +43,8 @@ def test_kabsch_matches_svd(L, frags, name, sel):
         a = np.ascontiguousarray(c.T @ r); out = np.zeros(9)
         L.hm_kabsch_rot(P(a), P(out))
         worst = max(worst, np.abs(out.reshape(3, 3) - rot).max())
+        L.hm_kabsch_rot_fast(P(a), float((c * c).sum() + (r * r).sum()), P(out))      # shifted inverse iteration path
+        worst = max(worst, np.abs(out.reshape(3, 3) - rot).max())
     assert worst < 1e-12
 
 
@@ -53,7 +56,7 @@ def test_kabsch_large_rotation_and_reflection_guard(L):
         tgt = ref @ Rt
         rot, tr, rms = O.kabsch(ref, tgt)
         c = ref - ref.mean(0); r = tgt - tgt.mean(0)
-        out = np.zeros(9); L.hm_kabsch_rot(P(np.ascontiguousarray(c.T @ r)), P(out))
+        out = np.zeros(9); L.hm_kabsch_rot_fast(P(np.ascontiguousarray(c.T @ r)), float((c * c).sum() + (r * r).sum()), P(out))
         out = out.reshape(3, 3)
         assert abs(np.linalg.det(out) - 1.0) < 1e-12
         assert np.abs(out - rot).max() < 1e-10
