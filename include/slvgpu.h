@@ -168,6 +168,13 @@ int slvgpu_rotate_vec(double *h_vec, int64_t n, const double *h_rot, const doubl
  * typ [nbasis] = 0 s, 1 p, 2 d (first component of each p triple / d sextet marks the shell). */
 int slvgpu_rotate_vecl(double *h_vec, int64_t nrows, int32_t nbasis, const int32_t *h_typ, const double *h_rot);
 
+/* Post-processing of the shift series, host pointers:
+ * slvgpu_tcf: TCF(i) = 1/(n-i) sum_j a[j] b[j+i], i < k -- GTCF (util/lib/genres.f:1-23); with demean != 0 the means
+ * are removed first, which makes it the `cf` of util/slv_calc-tcf:17-28 (cf(y1,y2)[i] = tcf(a=y2, b=y1)[i]).
+ * slvgpu_expres: classical line-shape function of util/slv_calc-expres:73-101: re/im [ndel+1]. */
+int slvgpu_tcf(const double *h_a, const double *h_b, int64_t n, int64_t k, int32_t demean, double *h_tcf);
+int slvgpu_expres(const double *h_f, int64_t n, double dt, int64_t ndel, double *h_re, double *h_im);
+
 const char *slvgpu_last_error(void);
 const char *slvgpu_version(void);
 

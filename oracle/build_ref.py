@@ -9,6 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = '/root/reference/solvshift/src'
 FILES = ['efprot.f', 'solpol2.f', 'shftex.f', 'exrep.f']
+EXTRA = [('/root/reference/util/lib/genres.f', {'GTCF'})]     # (path, units to translate)
 
 
 def build(force=False):
@@ -27,6 +28,14 @@ def build(force=False):
         c = os.path.join(out, f.replace('.f', '_f.c'))
         with open(c, 'w') as fh:
             fh.write(f77c.transpile(text))
+        cs.append(c)
+    for path, only in EXTRA:
+        with open(path, encoding='utf-8', errors='replace') as fh:
+            text = fh.read()
+        f77c.CALLED.clear()
+        c = os.path.join(out, os.path.basename(path).replace('.f', '_f.c'))
+        with open(c, 'w') as fh:
+            fh.write(f77c.transpile(text, only=only))
         cs.append(c)
     cmd = ['gcc', '-O2', '-fPIC', '-shared', '-w', '-o', lib] + cs + [os.path.join(HERE, 'f77_support.c'), '-lm']
     subprocess.check_call(cmd)

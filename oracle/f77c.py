@@ -555,8 +555,10 @@ def emit_unit(u, out, commons):
 CALLED = set()
 
 
-def transpile(text):
+def transpile(text, only=None):
     units = parse_units(text)
+    if only is not None:
+        units = [u for u in units if u.name in only]
     for u in units:
         CALLED.add(u.name)
     commons = {}

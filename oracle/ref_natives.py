@@ -127,3 +127,11 @@ def shftex(redmss, freq, gijj, lvec, ria, rib, rna, rnb, ria1, cika, cikb, cika1
                   _p(faij), _p(fbij), _p(faij1), _i(mode), _p(sij), _p(tij), _p(smij), _p(tmij), _p(fi),
                   ctypes.byref(ma), ctypes.byref(ea))
     return ma.value, ea.value, fi, sij, tij, smij, tmij
+
+
+def gtcf(a, b, k):
+    """genres.gtcf(a, b, k) -> tcf[k]  (util/lib/genres.f:1-23)."""
+    a = _d(a).ravel(); b = _d(b).ravel()
+    tcf = np.zeros(int(k))
+    lib().gtcf_(_p(a), _p(b), _i(a.size), _i(k), _p(tcf))
+    return tcf

@@ -13,6 +13,7 @@
 #include "k_elect.cuh"
 #include "k_pol.cuh"
 #include "k_rep.cuh"
+#include "k_spectra.cuh"
 #include "k_util.cuh"
 
 using namespace slv;
@@ -463,4 +464,44 @@ extern "C" int slvgpu_rotate_vecl(double *h_vec, int64_t nrows, int32_t nbasis, 
   });
   cudaFree(d_rot); cudaFree(d_start);
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------ spectra (row N2)
+extern "C" int slvgpu_tcf(const double *h_a, const double *h_b, int64_t n, int64_t k, int32_t demean, double *h_tcf) {
+  if (!h_a || !h_b || !h_tcf || n < 1 || k < 1 || k > n) return fail(SLVGPU_EINVAL, "bad argument");
+  double *d = nullptr;
+  CK(cudaMalloc(&d, (size_t)(2 * n + k + 2) * sizeof(double)));
+  double *da = d, *db = d + n, *dt = d + 2 * n, *dm = dt + k;
+  cudaError_t e = cudaMemcpy(da, h_a, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(db, h_b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    if (demean) {
+      k_mean<<<1, 1024>>>(da, n, dm); k_shift<<<(unsigned)((n + 255) / 256), 256>>>(da, n, dm);
+      k_mean<<<1, 1024>>>(db, n, dm + 1); k_shift<<<(unsigned)((n + 255) / 256), 256>>>(db, n, dm + 1);
+    }
+    k_tcf<<<(unsigned)((k + TCF_LAGS - 1) / TCF_LAGS), SPEC_THREADS>>>(da, db, n, k, dt);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(h_tcf, dt, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(SLVGPU_ECUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int slvgpu_expres(const double *h_f, int64_t n, double dt, int64_t ndel, double *h_re, double *h_im) {
+  if (!h_f || !h_re || !h_im || n < 2 || ndel < 0 || ndel >= n) return fail(SLVGPU_EINVAL, "bad argument");
+  double *d = nullptr;
+  CK(cudaMalloc(&d, (size_t)(2 * n + 1 + 2 * (ndel + 1)) * sizeof(double)));
+  double *df = d, *dC = d + n, *dre = dC + n + 1, *dim = dre + ndel + 1;
+  cudaError_t e = cudaMemcpy(df, h_f, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_trapz_prefix<<<1, 1024>>>(df, n, dt, dC);
+    k_expres<<<(unsigned)(ndel + 1), SPEC_THREADS>>>(dC, n, ndel, dre, dim);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(h_re, dre, (size_t)(ndel + 1) * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(h_im, dim, (size_t)(ndel + 1) * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(SLVGPU_ECUDA, cudaGetErrorString(e));
+  return 0;
 }
