@@ -41,8 +41,9 @@ WORKLOADS = {
     5: dict(name='NMA + %(n)d waters, full SolEFP elect+pol+rep+disp', solute='nma', solvents=['water'], nsolv=4000, mode=8,
             flags=dict(elect=True, corr=True, pol=True, rep=True, disp=True), frames=2000, spacing=5.87, seed=5),
 }
-FLOPS_PER_T_PAIR = 43.0      # one (centre, centre) dipole-tensor apply to two vectors, DESIGN.md "k_pol"
-FLOPS_PER_FIELD_PAIR = 130.0  # one (centre, site) multipole field through octupoles
+FLOPS_PER_T_PAIR = 49.0      # one (centre, centre) dipole-tensor apply to two vectors: R 3, r^2 5, rsqrt 1, powers 4,
+                             # two dots 10, two scalings 2, six accumulations x 4 (DESIGN.md "k_pol")
+FLOPS_PER_FIELD_PAIR = 123.0  # one (centre, site) multipole field through octupoles (slv::site_field_acc, counted)
 FLOPS_PER_ELECT_PAIR = 300.0  # one (solute site, solvent site) pair through R^-4 with two moment sets + corrections
 
 

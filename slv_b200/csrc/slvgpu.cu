@@ -40,8 +40,8 @@ struct slvgpu_plan {
   int *d_queue = nullptr;
   int detail_frames = 0;
   int want_detail = 0;
-  double *d_stage_coords = nullptr, *d_stage_out = nullptr; int *d_stage_status = nullptr;
-  int64_t stage_frames = 0;
+  double *d_stage_coords2[2] = {nullptr, nullptr}, *d_stage_out = nullptr; int *d_stage_status = nullptr;
+  int64_t stage_frames = 0, stage_slice = 0;
   int64_t last_launches = 0;
   cudaStream_t own_stream = nullptr, copy_stream = nullptr;
   std::vector<cudaEvent_t> copy_ev;
@@ -112,7 +112,7 @@ extern "C" void slvgpu_plan_destroy(slvgpu_plan *pl) {
   if (!pl) return;
   for (cudaEvent_t e : pl->ev_pool) cudaEventDestroy(e);
   for (void *q : pl->allocs) cudaFree(q);
-  if (pl->d_stage_coords) cudaFree(pl->d_stage_coords);
+  for (int b = 0; b < 2; ++b) if (pl->d_stage_coords2[b]) cudaFree(pl->d_stage_coords2[b]);
   if (pl->d_stage_out) cudaFree(pl->d_stage_out);
   if (pl->d_stage_status) cudaFree(pl->d_stage_status);
   if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
@@ -301,34 +301,39 @@ extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, 
   if (nframes <= 0) return nframes == 0 ? 0 : fail(SLVGPU_EINVAL, "negative frame count");
   const DevPlan &p = pl->dp;
   if (!pl->own_stream) CK(cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking));
+  // Device staging is bounded: two coordinate buffers of one slice each (double buffering), so trajectories far larger
+  // than device memory stream through; the result rows of the whole call stay on the device until the end.
+  const int64_t first = pl->max_chunk < 1024 ? pl->max_chunk : 1024;   // a short first slice hides the first copy
+  const int64_t slice = pl->max_chunk;
+  const size_t fstride = (size_t)p.natoms_total * 3;
+  if (pl->stage_slice < slice) {
+    for (int b = 0; b < 2; ++b) { if (pl->d_stage_coords2[b]) cudaFree(pl->d_stage_coords2[b]); pl->d_stage_coords2[b] = nullptr; }
+    pl->stage_slice = 0;
+    for (int b = 0; b < 2; ++b) CK(cudaMalloc(&pl->d_stage_coords2[b], (size_t)slice * fstride * sizeof(double)));
+    pl->stage_slice = slice;
+  }
   if (pl->stage_frames < nframes) {
-    if (pl->d_stage_coords) { cudaFree(pl->d_stage_coords); cudaFree(pl->d_stage_out); cudaFree(pl->d_stage_status); }
-    pl->d_stage_coords = nullptr; pl->d_stage_out = nullptr; pl->d_stage_status = nullptr; pl->stage_frames = 0;
-    CK(cudaMalloc(&pl->d_stage_coords, (size_t)nframes * p.natoms_total * 3 * sizeof(double)));
+    if (pl->d_stage_out) { cudaFree(pl->d_stage_out); cudaFree(pl->d_stage_status); }
+    pl->d_stage_out = nullptr; pl->d_stage_status = nullptr; pl->stage_frames = 0;
     CK(cudaMalloc(&pl->d_stage_out, (size_t)nframes * SLVGPU_NOUT * sizeof(double)));
     CK(cudaMalloc(&pl->d_stage_status, (size_t)nframes * sizeof(int32_t)));
     pl->stage_frames = nframes;
   }
-  // Pipelined: coordinates go up in slices on a copy stream while the previous slice is being evaluated on
-  // the compute stream (frames are independent, so slices are just sub-ranges of the same buffers).
   cudaStream_t st = pl->own_stream;
   if (!pl->copy_stream) CK(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
-  // a short first slice hides the first copy; later slices are long so the persistent kernels keep a full queue
-  const int64_t first = pl->max_chunk < 1024 ? pl->max_chunk : 1024;
-  const int64_t slice = pl->max_chunk;      // everything after the first slice in as few launches as the scratch allows
-  const int64_t nsl = nframes <= first ? 1 : 1 + (nframes - first + slice - 1) / slice;
-  while ((int64_t)pl->copy_ev.size() < nsl) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); pl->copy_ev.push_back(e); }
-  const size_t fstride = (size_t)p.natoms_total * 3;
+  while (pl->copy_ev.size() < 4) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); pl->copy_ev.push_back(e); }
   int64_t launches = 0, f0 = 0;
-  for (int64_t c = 0; c < nsl; ++c) {
+  for (int64_t c = 0; f0 < nframes; ++c) {
+    const int b = (int)(c & 1);
     const int64_t want = c == 0 ? first : slice, n = (nframes - f0) < want ? (nframes - f0) : want;
-    CK(cudaMemcpyAsync(pl->d_stage_coords + f0 * fstride, h_coords + f0 * fstride, (size_t)n * fstride * sizeof(double),
+    if (c >= 2) CK(cudaStreamWaitEvent(pl->copy_stream, pl->copy_ev[2 + b], 0));      // buffer b has been consumed
+    CK(cudaMemcpyAsync(pl->d_stage_coords2[b], h_coords + f0 * fstride, (size_t)n * fstride * sizeof(double),
                        cudaMemcpyHostToDevice, pl->copy_stream));
-    CK(cudaEventRecord(pl->copy_ev[c], pl->copy_stream));
-    CK(cudaStreamWaitEvent(st, pl->copy_ev[c], 0));
-    int rc = slvgpu_eval_frames(pl, pl->d_stage_coords + f0 * fstride, n, pl->d_stage_out + f0 * SLVGPU_NOUT,
-                                pl->d_stage_status + f0, st);
+    CK(cudaEventRecord(pl->copy_ev[b], pl->copy_stream));
+    CK(cudaStreamWaitEvent(st, pl->copy_ev[b], 0));
+    int rc = slvgpu_eval_frames(pl, pl->d_stage_coords2[b], n, pl->d_stage_out + f0 * SLVGPU_NOUT, pl->d_stage_status + f0, st);
     if (rc) return rc;
+    CK(cudaEventRecord(pl->copy_ev[2 + b], st));
     launches += pl->last_launches;
     f0 += n;
   }

@@ -365,6 +365,8 @@ def test_full_size_batch_properties(frags):
     assert np.array_equal(r2.cpu().numpy()[:, :8], rows[:, :8])                 # (2)
     rh, sh = efp.eval_frames(X)
     assert np.array_equal(rh[:, :8], rows[:, :8]) and int(sh.max()) == 0        # (3)
+    rh2, _ = efp2.eval_frames(X)                                                # 14 double-buffered slices of 777 frames
+    assert np.array_equal(rh2[:, :8], rows[:, :8])
     c = O.HartreePerHbarToCmRec
     ref = O.eval_frame(U[0], ind, nmol, [sol.get(), wat.get()], [None, None], [None, None], 8, 40.0, 17.0, 12.0,
                        elect=True, ea=True, corr=True, pol=True)
