@@ -37,7 +37,7 @@ struct PolWork {                 // per-CTA workspace (device pointers already o
 __global__ void __launch_bounds__(POL_THREADS, 2)
 k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, double *__restrict__ out, int *__restrict__ status,
       double *__restrict__ detail /* optional [nframes][cent_cap][9]: dipind, flds, rpol */, int *__restrict__ queue) {
-  __shared__ double s_red[32];
+  __shared__ double s_red[64];
   __shared__ int s_tmol[POL_TILE];
   __shared__ int s_fi;
   __shared__ unsigned long long s_scan[POL_THREADS / 32];
@@ -215,17 +215,30 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       bnorm = block_max(pb, s_red);
     }
     bool broke = false;
+    // When all centres fit one tile (the usual case: <= 512 inside pcut) the tile stays resident in shared memory for
+    // the whole solve: positions and molecule ids are staged once, and every iteration the owners write their search
+    // directions straight into it -- no per-iteration round trip through the L2 workspace, one barrier per sweep.
+    const bool resident = ncent <= POL_TILE;
+    if (resident) {
+      for (int j = tid; j < ncent; j += NT) {
+        double *tt = s_tile + j * 10;
+        tt[0] = wk.cent_pos[(size_t)j * 3]; tt[1] = wk.cent_pos[(size_t)j * 3 + 1]; tt[2] = wk.cent_pos[(size_t)j * 3 + 2];
+        s_tmol[j] = wk.cent_mol[j];
+      }
+    }
     if (bnorm > 0.0) {
       for (; iters < p.pol_maxit;) {
         // u = p, ut = alpha^T pt
         for (int c = tid; c < ncent; c += NT) {
           double *s_ = stt + (size_t)c * PST;
           const double *a = wk.cent_alpha + (size_t)c * 9;
+          double *dst = resident ? s_tile + c * 10 + 3 : s_ + 18;
           for (int i = 0; i < 3; ++i) {
-            s_[18 + i] = s_[12 + i];
-            s_[21 + i] = a[i] * s_[15] + a[3 + i] * s_[16] + a[6 + i] * s_[17];
+            dst[i] = s_[12 + i];
+            dst[3 + i] = a[i] * s_[15] + a[3 + i] * s_[16] + a[6 + i] * s_[17];
           }
         }
+        if (resident) __syncthreads();
         double pq = 0.0;
         for (int c0 = 0; c0 < ncent; c0 += NT) {
           const int c = c0 + tid;
@@ -234,18 +247,20 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
           if (act) { rc[0] = wk.cent_pos[(size_t)c * 3]; rc[1] = wk.cent_pos[(size_t)c * 3 + 1]; rc[2] = wk.cent_pos[(size_t)c * 3 + 2]; mc = wk.cent_mol[c]; }
           double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0};
           for (int j0 = 0; j0 < ncent; j0 += POL_TILE) {
-            __syncthreads();
-            for (int tl = tid; tl < POL_TILE; tl += NT) {
-              const int j = j0 + tl;
-              if (j < ncent) {
-                double *tt = s_tile + tl * 10;
-                tt[0] = wk.cent_pos[(size_t)j * 3]; tt[1] = wk.cent_pos[(size_t)j * 3 + 1]; tt[2] = wk.cent_pos[(size_t)j * 3 + 2];
-                const double *vj = stt + (size_t)j * PST + 18;
-                for (int d = 0; d < 6; ++d) tt[3 + d] = vj[d];
-                s_tmol[tl] = wk.cent_mol[j];
-              } else s_tmol[tl] = -2;
+            if (!resident) {
+              __syncthreads();
+              for (int tl = tid; tl < POL_TILE; tl += NT) {
+                const int j = j0 + tl;
+                if (j < ncent) {
+                  double *tt = s_tile + tl * 10;
+                  tt[0] = wk.cent_pos[(size_t)j * 3]; tt[1] = wk.cent_pos[(size_t)j * 3 + 1]; tt[2] = wk.cent_pos[(size_t)j * 3 + 2];
+                  const double *vj = stt + (size_t)j * PST + 18;
+                  for (int d = 0; d < 6; ++d) tt[3 + d] = vj[d];
+                  s_tmol[tl] = wk.cent_mol[j];
+                } else s_tmol[tl] = -2;
+              }
+              __syncthreads();
             }
-            __syncthreads();
             if (act) {
               const int jn = min(POL_TILE, ncent - j0);
 #pragma unroll 4
@@ -291,8 +306,9 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
             prho += rt * r; pr = fmax(pr, fmax(fabs(r), fabs(rt)));
           }
         }
-        const double rho1 = block_sum(prho, s_red);
-        resid = block_max(pr, s_red) / bnorm;
+        double rho1 = prho, rmax = pr;
+        block_sum_max(rho1, rmax, s_red);
+        resid = rmax / bnorm;
         if (!(resid > p.pol_tol)) break;
         if (!(fabs(rho) > 0.0) || !isfinite(rho1)) { broke = true; break; }
         const double be = rho1 / rho;

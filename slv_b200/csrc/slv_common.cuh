@@ -71,6 +71,18 @@ __device__ __forceinline__ double block_max(double v, double *scratch) {
   return r;
 }
 
+// one sum and one max in a single pass (two barriers); `scratch` must hold >= 64 doubles
+__device__ __forceinline__ void block_sum_max(double &s, double &m, double *scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  s = warp_sum(s); m = warp_max(m);
+  __syncthreads();
+  if (lane == 0) { scratch[w] = s; scratch[32 + w] = m; }
+  __syncthreads();
+  double rs = 0.0, rm = scratch[32];
+  for (int i = 0; i < nw; ++i) { rs += scratch[i]; rm = fmax(rm, scratch[32 + i]); }
+  s = rs; m = rm;
+}
+
 // Kabsch fit of one fragment instance: parameter atoms `supl` (parameter order) onto the frame atoms
 // they map to through `reord`.  Follows Frag.sup / SVDSuperimposer (solvshift/slvpar.py:641-679):
 // one-atom fragments get the identity and a pure shift (668-671).
