@@ -147,10 +147,11 @@ int slvgpu_set_timing(slvgpu_plan *plan, int on);
 int slvgpu_get_timing(slvgpu_plan *plan, double *ms4, int64_t *launches4);
 
 /* Optional per-frame detail of the LAST evaluated frame range: induced dipoles and fields at the
- * polarisable centres (EFP.get_dipind / get_fields, solvshift/solefp.py:303-313).  Buffers are
+ * polarisable centres and the solvatochromic induced dipoles (EFP.get_dipind / get_fields / get_avec,
+ * solvshift/solefp.py:303-313).  Buffers are
  * [ncent][3]; returns the number of centres written, or a negative error. */
 int slvgpu_get_pol_detail(slvgpu_plan *plan, int64_t frame, double *h_dipind, double *h_flds,
-                          double *h_rpol, int32_t max_centres);
+                          double *h_rpol, double *h_avec, int32_t max_centres);
 
 /* Kabsch superimposition of one fragment (Frag.sup, solvshift/slvpar.py:641-679, libbbg
  * SVDSuperimposer): host pointers, n atoms each; rot[9] row-major with x' = x.rot + transl. */

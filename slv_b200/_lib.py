@@ -47,7 +47,7 @@ def _load():
     lib.slvgpu_last_launches.argtypes = [vp]; lib.slvgpu_last_launches.restype = i64
     lib.slvgpu_set_timing.argtypes = [vp, i32]
     lib.slvgpu_get_timing.argtypes = [vp, vp, vp]
-    lib.slvgpu_get_pol_detail.argtypes = [vp, i64, vp, vp, vp, i32]
+    lib.slvgpu_get_pol_detail.argtypes = [vp, i64, vp, vp, vp, vp, i32]
     lib.slvgpu_kabsch.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.slvgpu_rotate_dma.argtypes = [vp, vp, vp, i64, vp]
     lib.slvgpu_rotate_pol.argtypes = [vp, i64, vp]

@@ -29,6 +29,7 @@ struct PolWork {                 // per-CTA workspace (device pointers already o
   double *fld;        // [cent_cap][3]
   double *xy;         // [cent_cap][PST] BiCG state + [cent_cap][6] final x, y
   double *site;       // [site_cap][SITE_ROW]
+  double *aux;        // [2][cent_cap][3] right-hand sides of the AVEC solve (detail mode)
   int *cent_mol;      // [cent_cap]
   int *ent_coff;      // [list_cap] first centre of a list entry
   int *ent_soff;      // [list_cap] first site of a list entry
@@ -50,7 +51,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     const size_t cb = blockIdx.x;
     const size_t cc = (size_t)p.cent_cap;
     wk.cent_pos += cb * cc * 3; wk.cent_alpha += cb * cc * 9; wk.fld += cb * cc * 3; wk.xy += cb * cc * (PST + 6);
-    wk.site += cb * (size_t)p.site_cap * SITE_ROW; wk.cent_mol += cb * cc;
+    wk.site += cb * (size_t)p.site_cap * SITE_ROW; wk.cent_mol += cb * cc; wk.aux += cb * cc * 6;
     wk.ent_coff += cb * (size_t)p.list_cap; wk.ent_soff += cb * (size_t)p.list_cap;
   }
   const int *tm0 = tmeta(p, p.inst_type[0]);
@@ -197,14 +198,17 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     double resid = 1.0;
     double *stt = wk.xy;                                   // [ncent][PST]
     double *vfin = wk.xy + (size_t)p.cent_cap * PST;        // [ncent][6]  final x, y
+    // b = state slot 0..2 (already alpha-preconditioned), bt = bt_src[c][3]; result x and y = alpha^T xt in vfin
+    auto bicg = [&](const double *bt_src) {
+    iters = 0; resid = 1.0;
     double rho = 0.0, bnorm = 0.0;
     {
       double prho = 0.0, pb = 0.0;
       for (int c = tid; c < ncent; c += NT) {
         double *s_ = stt + (size_t)c * PST;
-        const double *F = wk.fld + (size_t)c * 3;
+        const double *F = bt_src + (size_t)c * 3;
         for (int i = 0; i < 3; ++i) {
-          const double bi = s_[i];                         // alpha F (written in phase b)
+          const double bi = s_[i];                         // preconditioned right-hand side
           s_[6 + i] = bi; s_[12 + i] = bi;                 // r = p = b
           s_[9 + i] = F[i]; s_[15 + i] = F[i];             // rt = pt = F
           s_[i] = 0.0; s_[3 + i] = 0.0;                    // x = xt = 0
@@ -329,8 +333,10 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       }
     }
     __syncthreads();
-    const double *vxy = vfin;
     if (broke) resid = 1.0;
+    };
+    bicg(wk.fld);
+    const double *vxy = vfin;
 
     // ---- (d) contractions with the solute rows: y^T dD x - (x+y).dF
     // solute tables in shared memory: centres [npolc][21]: pos3 r1(3) G(9) x3 y3 ; sites [ndmac][46]: pos3 mom20 dma1(20) L3
@@ -408,14 +414,69 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     if (pass < 0) { shift_main = -0.5 * acc; iters_out = iters; resid_out = resid; ncent_out = ncent; nsite_out = nsite; }
     else { shift_add += -0.5 * acc; resid_out = fmax(resid_out, resid); }
     if (detail && pass < 0) {
-      double *dd = detail + (size_t)fi * ((size_t)p.cent_cap * 9 + 1);
+      const size_t drow = (size_t)p.cent_cap * 12 + 1;
+      double *dd = detail + (size_t)fi * drow;
       for (int c = tid; c < ncent; c += NT)
         for (int d = 0; d < 3; ++d) {
-          dd[(size_t)c * 9 + d] = vxy[(size_t)c * 6 + d];
-          dd[(size_t)c * 9 + 3 + d] = wk.fld[(size_t)c * 3 + d];
-          dd[(size_t)c * 9 + 6 + d] = wk.cent_pos[(size_t)c * 3 + d];
+          dd[(size_t)c * 12 + d] = vxy[(size_t)c * 6 + d];
+          dd[(size_t)c * 12 + 3 + d] = wk.fld[(size_t)c * 3 + d];
+          dd[(size_t)c * 12 + 6 + d] = wk.cent_pos[(size_t)c * 3 + d];
         }
-      if (tid == 0) dd[(size_t)p.cent_cap * 9] = (double)ncent;
+      if (tid == 0) dd[(size_t)p.cent_cap * 12] = (double)ncent;
+      // ---- solvatochromic induced dipoles AVEC = sum_m g_m MIVEC_m = D^-T (dD^T y - dF) - D^-1 dF (solpol2.f:1122-1143):
+      //      the vectors dF and w = dD^T y, then one more BiCG run with the right-hand sides (dF, w - dF)
+      double *dFv = wk.aux, *btv = wk.aux + (size_t)p.cent_cap * 3;
+      auto Bapply = [&](const double *R, const double *r1, const double *v, double *o) {   // o += B_ij v
+        const double r2 = R[0] * R[0] + R[1] * R[1] + R[2] * R[2];
+        const double u = rsqrt64(r2), u2 = u * u, u5 = u2 * u2 * u, f = -1.5 * u5;
+        const double R1R = R[0] * r1[0] + R[1] * r1[1] + R[2] * r1[2];
+        const double Rv = R[0] * v[0] + R[1] * v[1] + R[2] * v[2], r1v = r1[0] * v[0] + r1[1] * v[1] + r1[2] * v[2];
+        for (int a = 0; a < 3; ++a) o[a] += f * (R1R * (v[a] - 5.0 * u2 * R[a] * Rv) + R[a] * r1v + r1[a] * Rv);
+      };
+      for (int j = npolc + tid; j < ncent; j += NT) {                 // solvent centres
+        const double rj[3] = {wk.cent_pos[(size_t)j * 3], wk.cent_pos[(size_t)j * 3 + 1], wk.cent_pos[(size_t)j * 3 + 2]};
+        double dF[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+        for (int a = 0; a < ndmac; ++a) {
+          const double *row = s_s + (size_t)a * 46;
+          const double R[3] = {rj[0] - row[0], rj[1] - row[1], rj[2] - row[2]};
+          site_field(R, row + 23, 7.0, dF);
+          site_dfield(R, row + 43, row + 3, -1.0, dF);
+        }
+        for (int i = 0; i < npolc; ++i) {
+          const double *row = s_c + (size_t)i * 21;
+          const double R[3] = {row[0] - rj[0], row[1] - rj[1], row[2] - rj[2]};
+          Bapply(R, row + 3, row + 18, w);
+        }
+        for (int d = 0; d < 3; ++d) { dFv[(size_t)j * 3 + d] = dF[d]; btv[(size_t)j * 3 + d] = w[d] - dF[d]; }
+      }
+      for (int i = tid; i < npolc; i += NT) {                          // solute centres
+        const double *row = s_c + (size_t)i * 21, *G = row + 6, *yi = row + 18;
+        double dF[3] = {0, 0, 0}, w[3];
+        for (int a = 0; a < 3; ++a) w[a] = G[a] * yi[0] + G[3 + a] * yi[1] + G[6 + a] * yi[2];      // G^T y
+        for (int sidx = ndmac; sidx < nsite; ++sidx) {
+          const double *srow = wk.site + (size_t)sidx * SITE_ROW;
+          const double R[3] = {row[0] - srow[0], row[1] - srow[1], row[2] - srow[2]};
+          site_dfield(R, row + 3, srow + 3, 1.0, dF);
+        }
+        for (int j = npolc; j < ncent; ++j) {
+          const double R[3] = {row[0] - wk.cent_pos[(size_t)j * 3], row[1] - wk.cent_pos[(size_t)j * 3 + 1], row[2] - wk.cent_pos[(size_t)j * 3 + 2]};
+          Bapply(R, row + 3, vxy + (size_t)j * 6 + 3, w);
+        }
+        for (int d = 0; d < 3; ++d) { dFv[(size_t)i * 3 + d] = dF[d]; btv[(size_t)i * 3 + d] = w[d] - dF[d]; }
+      }
+      __syncthreads();
+      for (int c = tid; c < ncent; c += NT) {                          // preconditioned rhs b = alpha dF
+        const double *a = wk.cent_alpha + (size_t)c * 9, *F = dFv + (size_t)c * 3;
+        double *v = wk.xy + (size_t)c * PST;
+        for (int i = 0; i < 3; ++i) v[i] = a[i * 3] * F[0] + a[i * 3 + 1] * F[1] + a[i * 3 + 2] * F[2];
+      }
+      __syncthreads();
+      const int it1 = iters; const double res1 = resid;
+      bicg(btv);
+      for (int c = tid; c < ncent; c += NT)
+        for (int d = 0; d < 3; ++d) dd[(size_t)c * 12 + 9 + d] = vfin[(size_t)c * 6 + 3 + d] - vfin[(size_t)c * 6 + d];
+      resid = fmax(res1, resid); iters = it1;
+      iters_out = iters; resid_out = resid;
     }
     } while (0);
     // next removable fragment inside pcut, if any

@@ -213,12 +213,13 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
     TRY(dalloc(pl, &pl->pw.fld, nc * cc * 3));
     TRY(dalloc(pl, &pl->pw.xy, nc * cc * (PST + 6)));
     TRY(dalloc(pl, &pl->pw.site, nc * (size_t)p.site_cap * SITE_ROW));
+    TRY(dalloc(pl, &pl->pw.aux, nc * cc * 6));
     TRY(dalloc(pl, &pl->pw.cent_mol, nc * cc));
     TRY(dalloc(pl, &pl->pw.ent_coff, nc * (size_t)p.list_cap));
     TRY(dalloc(pl, &pl->pw.ent_soff, nc * (size_t)p.list_cap));
     if (pl->want_detail) {
       pl->detail_frames = pl->max_chunk;
-      TRY(dalloc(pl, &pl->d_detail, (size_t)pl->detail_frames * (cc * 9 + 1)));
+      TRY(dalloc(pl, &pl->d_detail, (size_t)pl->detail_frames * (cc * 12 + 1)));
     }
   }
   if (d->flags & SLVGPU_REP) {
@@ -347,20 +348,21 @@ extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, 
 extern "C" int64_t slvgpu_last_launches(const slvgpu_plan *pl) { return pl ? pl->last_launches : 0; }
 
 extern "C" int slvgpu_get_pol_detail(slvgpu_plan *pl, int64_t frame, double *h_dipind, double *h_flds, double *h_rpol,
-                                     int32_t max_centres) {
+                                     double *h_avec, int32_t max_centres) {
   if (!pl || !pl->d_detail) return fail(SLVGPU_EINVAL, "plan was created without want_detail / pol");
   if (frame < 0 || frame >= pl->detail_frames) return fail(SLVGPU_EINVAL, "frame outside the last chunk");
   const int cc = pl->dp.cent_cap;
-  std::vector<double> buf((size_t)cc * 9 + 1);
+  std::vector<double> buf((size_t)cc * 12 + 1);
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(buf.data(), pl->d_detail + (size_t)frame * ((size_t)cc * 9 + 1), buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  const int ncent = (int)buf[(size_t)cc * 9];
+  CK(cudaMemcpy(buf.data(), pl->d_detail + (size_t)frame * ((size_t)cc * 12 + 1), buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  const int ncent = (int)buf[(size_t)cc * 12];
   const int n = max_centres < ncent ? max_centres : ncent;
   for (int c = 0; c < n; ++c)
     for (int d = 0; d < 3; ++d) {
-      if (h_dipind) h_dipind[c * 3 + d] = buf[(size_t)c * 9 + d];
-      if (h_flds) h_flds[c * 3 + d] = buf[(size_t)c * 9 + 3 + d];
-      if (h_rpol) h_rpol[c * 3 + d] = buf[(size_t)c * 9 + 6 + d];
+      if (h_dipind) h_dipind[c * 3 + d] = buf[(size_t)c * 12 + d];
+      if (h_flds) h_flds[c * 3 + d] = buf[(size_t)c * 12 + 3 + d];
+      if (h_rpol) h_rpol[c * 3 + d] = buf[(size_t)c * 12 + 6 + d];
+      if (h_avec) h_avec[c * 3 + d] = buf[(size_t)c * 12 + 9 + d];
     }
   return n;
 }

@@ -230,6 +230,7 @@ class Plan(object):
         k = self._keep
         tot = int(sum(k['meta'][t][_lib.M['NPOL']] for t in k['inst_type']))
         n = min(max_centres or tot, tot)
-        dip = numpy.zeros((n, 3)); fld = numpy.zeros((n, 3)); rp = numpy.zeros((n, 3))
-        got = _lib.check(_lib.lib.slvgpu_get_pol_detail(self._h, frame, dip.ctypes.data, fld.ctypes.data, rp.ctypes.data, n))
-        return dip[:got], fld[:got], rp[:got]
+        dip = numpy.zeros((n, 3)); fld = numpy.zeros((n, 3)); rp = numpy.zeros((n, 3)); av = numpy.zeros((n, 3))
+        got = _lib.check(_lib.lib.slvgpu_get_pol_detail(self._h, frame, dip.ctypes.data, fld.ctypes.data, rp.ctypes.data,
+                                                          av.ctypes.data, n))
+        return dip[:got], fld[:got], rp[:got], av[:got]

@@ -338,13 +338,18 @@ class EFP(UNITS):
 
     def get_dipind(self):
         """(induced dipoles, centres) at the polarisable centres inside pcut (solefp.py:307-309)."""
-        dip, fld, rp = self._pol_detail()
+        dip, fld, rp, av = self._pol_detail()
         return dip, rp
 
     def get_fields(self):
         """(fields, centres) at the polarisable centres inside pcut (solefp.py:303-305)."""
-        dip, fld, rp = self._pol_detail()
+        dip, fld, rp, av = self._pol_detail()
         return fld, rp
+
+    def get_avec(self):
+        """(solvatochromic induced dipoles, centres) at the polarisable centres inside pcut (solefp.py:311-313)."""
+        dip, fld, rp, av = self._pol_detail()
+        return av, rp
 
     def _pol_detail(self):
         if not self.want_detail:

@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    # the in-tree CUDA library, the host build of the device math and the transpiled reference are git-ignored build
+    # products: (re)build whatever is missing or stale before the tests import them (nvcc cross-compiles without a GPU)
+    try:
+        import __graft_entry__
+        __graft_entry__.build()
+    except Exception as exc:          # tests that need the products will fail loudly on import
+        print('conftest: build() failed: %r' % (exc,))
 
 
 @pytest.fixture(scope='session')

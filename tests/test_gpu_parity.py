@@ -251,6 +251,9 @@ def test_dipind_and_fields_detail(frags, golden):
     dip, rp = efp.get_dipind(); fld, _ = efp.get_fields()
     ref = O.eval_frame(xyz, [0, 1], [12, 3], [frags('nma').get(), frags('water').get()], SCAN_SUPL, SCAN_REORD, 8, elect=True, pol=True)
     assert dip.shape == (25, 3) and np.abs(dip - ref['dipind']).max() < 1e-9 * np.abs(ref['dipind']).max() + 1e-12
+    av, _ = efp.get_avec()
+    assert av.shape == (25, 3) and np.abs(av - ref['avec']).max() < 1e-8 * np.abs(ref['avec']).max()
+    assert abs(efp.get_shifts()['pol_mea'] - ref['pol_mea'] * O.HartreePerHbarToCmRec) < TOL
 
 
 def test_md_run_report_format(frags, golden, tmp_path):
