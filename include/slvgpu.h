@@ -76,7 +76,8 @@ enum {
   SLVGPU_M_REMOVABLE, /* 1: polarisation of this type is treated pair-wise (remove_clashes)          */
   SLVGPU_M_NSHELL,    /* number of basis shells                                                  */
   SLVGPU_M_IO_SHELL,  /* itab: [nshell][4] atom, first function, functions in shell, primitives  */
-  SLVGPU_M_IO_PAIRORDER, /* itab: [nbasis_solute * nbasis] (solute AO, this type's AO) pairs in evaluation order */
+  SLVGPU_M_IO_PAIRORDER, /* itab: [10] class offsets + [nbasis_solute * nbasis] (solute AO, this type's AO) pairs,
+                          * grouped by angular-momentum class (3 L_bra + L_ket), heavy pairs first            */
   SLVGPU_NMETA = 32
 };
 

@@ -48,9 +48,33 @@ inline int rep_alloc(RepWork &rw, std::vector<void *> &allocs, std::string &err,
 }
 
 // shared memory: solute [posA natA*3][LcA natA*3][riA nmosA*3][ri1A nmosA*3] + solvent [posB max_nat*3][riB max_nmos*3]
-inline size_t rep_smem_bytes(int nmosc, int max_nmos, int natc, int max_nat) {
-  return sizeof(double) * (size_t)(6 * natc + 6 * nmosc + 3 * max_nat + 3 * max_nmos + 8);
+inline size_t rep_smem_bytes(int nmosc, int max_nmos, int natc, int max_nat, int nbasc, int max_nbas) {
+  // + basis tables of the solute (staged once) and of the current solvent fragment: per function 6 exponents,
+  //   6 coefficients and 5 ints (atom, lx, ly, lz, nprim) -- the integral loop reads them from shared memory
+  return sizeof(double) * (size_t)(6 * natc + 6 * nmosc + 3 * max_nat + 3 * max_nmos + 8 + 15 * (nbasc + max_nbas));
 }
+
+// phase 1 of k_rep for one angular-momentum class: pairs order[lo..hi) -> V[(k*nbsB + l)*4 + q]; basis tables in smem
+struct RepPhase1 {
+  const double *posA, *posB, *LcA; double *V; int nbsB; const int *order;
+  const int *iA; const double *eA, *cA;
+  const int *iB; const double *eB, *cB;
+  template <int LA, int LB>
+  __device__ __forceinline__ void run(int lo, int hi) const {
+    for (int wi = lo + threadIdx.x; wi < hi; wi += blockDim.x) {
+      const int w = order[wi];
+      const int k = w / nbsB, l = w % nbsB;
+      const int *ik = iA + k * 5, *il = iB + l * 5;
+      const int ak = ik[0], al = il[0];
+      const int la[3] = {ik[1], ik[2], ik[3]}, lb[3] = {il[1], il[2], il[3]};
+      double o[4];
+      ao_pair_t<LA, LB>(posA + ak * 3, la, ik[4], eA + k * 6, cA + k * 6, posB + al * 3, lb, il[4], eB + l * 6, cB + l * 6,
+                        LcA + ak * 3, o);
+      double *v = V + (size_t)w * 4;
+      v[0] = o[0]; v[1] = o[1]; v[2] = o[2]; v[3] = o[3];
+    }
+  }
+};
 
 // rotate the AO->LMO rows of one fragment type: dst[i][k] for i < nrows, from src (body frame)
 __device__ inline void rotate_vecl_rows(const DevPlan &p, const int *tm, const double *src, int nrows, const double R[9], double *dst) {
@@ -68,20 +92,32 @@ __device__ inline void rotate_vecl_rows(const DevPlan &p, const int *tm, const d
 }
 
 __global__ void __launch_bounds__(REP_THREADS, 2)
-k_rep(const DevPlan p, int frame0, int nframes, FrameLists fl, RepWork rw, double *__restrict__ out) {
+k_rep(const DevPlan p, int frame0, int nframes, FrameLists fl, RepWork rw, double *__restrict__ out, int max_nbas) {
   extern __shared__ double sm[];
   __shared__ double s_red[32];
   __shared__ int s_fi;
   const int tid = threadIdx.x, NT = blockDim.x;
   const int *tm0 = tmeta(p, p.inst_type[0]);
   const int natA = tm0[SLVGPU_M_NATOMS], nmosA = tm0[SLVGPU_M_NMOS], nbsA = tm0[SLVGPU_M_NBASIS];
-  double *posA = sm, *LcA = posA + 3 * natA, *riA = LcA + 3 * natA, *ri1A = riA + 3 * nmosA, *solv = ri1A + 3 * nmosA;
+  double *posA = sm, *LcA = posA + 3 * natA, *riA = LcA + 3 * natA, *ri1A = riA + 3 * nmosA;
+  double *s_eA = ri1A + 3 * nmosA, *s_cA = s_eA + 6 * nbsA;                 // solute basis: exponents, coefficients
+  int *s_iA = reinterpret_cast<int *>(s_cA + 6 * nbsA);                      // [nbsA][5] atom, lx, ly, lz, nprim
+  double *s_eB = s_cA + 6 * nbsA + 3 * nbsA, *s_cB = s_eB + 6 * max_nbas;    // current solvent fragment's basis
+  int *s_iB = reinterpret_cast<int *>(s_cB + 6 * max_nbas);
+  double *solv = s_cB + 6 * max_nbas + 3 * max_nbas;
   double *CA = rw.CA + blockIdx.x * rw.sCA, *CA1 = CA + (size_t)nmosA * nbsA;
   double *CB = rw.CB + blockIdx.x * rw.sCB, *V = rw.V + blockIdx.x * rw.sV, *X = rw.X + blockIdx.x * rw.sX, *IJ = rw.IJ + blockIdx.x * rw.sIJ;
   const double *FA = p.dtab + tm0[SLVGPU_M_O_FOCK], *FA1 = p.dtab + p.sol_meta[SLVGPU_S_FOCK1], *ZA = p.dtab + tm0[SLVGPU_M_O_ZNUC];
-  const int *bcA = p.itab + tm0[SLVGPU_M_IO_BFC], *blA = p.itab + tm0[SLVGPU_M_IO_BFL], *bnA = p.itab + tm0[SLVGPU_M_IO_BFNP];
+  const int *blA = p.itab + tm0[SLVGPU_M_IO_BFL];
   const double *beA = p.dtab + tm0[SLVGPU_M_O_BFEXP], *bfA = p.dtab + tm0[SLVGPU_M_O_BFCOEF];
 
+  {
+    const int *bcA = p.itab + tm0[SLVGPU_M_IO_BFC], *bnA = p.itab + tm0[SLVGPU_M_IO_BFNP];
+    for (int w = tid; w < nbsA * 6; w += NT) { s_eA[w] = beA[w]; s_cA[w] = bfA[w]; }
+    for (int k = tid; k < nbsA; k += NT) {
+      s_iA[k * 5] = bcA[k]; s_iA[k * 5 + 1] = blA[k * 3]; s_iA[k * 5 + 2] = blA[k * 3 + 1]; s_iA[k * 5 + 3] = blA[k * 3 + 2]; s_iA[k * 5 + 4] = bnA[k];
+    }
+  }
   for (;;) {
     __syncthreads();
     if (tid == 0) s_fi = atomicAdd(rw.queue, 1);
@@ -134,22 +170,22 @@ k_rep(const DevPlan p, int frame0, int nframes, FrameLists fl, RepWork rw, doubl
         riB[j * 3] = y[0] + t[0]; riB[j * 3 + 1] = y[1] + t[1]; riB[j * 3 + 2] = y[2] + t[2];
       }
       rotate_vecl_rows(p, tm, p.dtab + tm[SLVGPU_M_O_VECL], nmosB, R, CB);
-      __syncthreads();
-      // ---- phase 1: AO integrals
       {
         const int *bcB = p.itab + tm[SLVGPU_M_IO_BFC], *blB = p.itab + tm[SLVGPU_M_IO_BFL], *bnB = p.itab + tm[SLVGPU_M_IO_BFNP];
         const double *beB = p.dtab + tm[SLVGPU_M_O_BFEXP], *bfB = p.dtab + tm[SLVGPU_M_O_BFCOEF];
-        const int *order = p.itab + tm[SLVGPU_M_IO_PAIRORDER];      // cost/class-sorted: warp lanes run equal-length loops
-        for (int wi = tid; wi < nbsA * nbsB; wi += NT) {
-          const int w = order[wi];
-          const int k = w / nbsB, l = w % nbsB;
-          const int ak = bcA[k], al = bcB[l];
-          const int la[3] = {blA[k * 3], blA[k * 3 + 1], blA[k * 3 + 2]}, lb[3] = {blB[l * 3], blB[l * 3 + 1], blB[l * 3 + 2]};
-          double o[4];
-          ao_pair(posA + ak * 3, la, bnA[k], beA + k * 6, bfA + k * 6, posB + al * 3, lb, bnB[l], beB + l * 6, bfB + l * 6, LcA + ak * 3, o);
-          double *v = V + (size_t)w * 4;
-          v[0] = o[0]; v[1] = o[1]; v[2] = o[2]; v[3] = o[3];
+        for (int w = tid; w < nbsB * 6; w += NT) { s_eB[w] = beB[w]; s_cB[w] = bfB[w]; }
+        for (int l = tid; l < nbsB; l += NT) {
+          s_iB[l * 5] = bcB[l]; s_iB[l * 5 + 1] = blB[l * 3]; s_iB[l * 5 + 2] = blB[l * 3 + 1]; s_iB[l * 5 + 3] = blB[l * 3 + 2]; s_iB[l * 5 + 4] = bnB[l];
         }
+      }
+      __syncthreads();
+      // ---- phase 1: AO integrals, class by class (angular momentum of bra x ket) in primitive-count order
+      {
+        const int *po = p.itab + tm[SLVGPU_M_IO_PAIRORDER];     // [10] class offsets, then the pair list
+        RepPhase1 ph{posA, posB, LcA, V, nbsB, po + 10, s_iA, s_eA, s_cA, s_iB, s_eB, s_cB};
+        ph.run<0, 0>(po[0], po[1]); ph.run<0, 1>(po[1], po[2]); ph.run<0, 2>(po[2], po[3]);
+        ph.run<1, 0>(po[3], po[4]); ph.run<1, 1>(po[4], po[5]); ph.run<1, 2>(po[5], po[6]);
+        ph.run<2, 0>(po[6], po[7]); ph.run<2, 1>(po[7], po[8]); ph.run<2, 2>(po[8], po[9]);
       }
       __syncthreads();
       // ---- phase 2: X[k][q][j] = sum_l V[k][l][q] CB[j][l]

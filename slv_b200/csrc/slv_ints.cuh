@@ -168,4 +168,97 @@ SLV_HD void shell_pair(const double A[3], int nfa, const int *la, int npa, const
   }
 }
 
+// ---- angular-momentum-specialised form: LA, LB = total angular momentum of the bra / ket function (0 s, 1 p, 2 d).
+// The 1-D tables shrink to (LA+2) x (LB+3) entries and the entry selection to the powers that can occur; k_rep walks
+// the AO pairs class by class, so a CTA executes one specialisation at a time.
+template <int N>
+SLV_HD double selN(int i, const double *v) {      // v[i] for i in 0..N without dynamic indexing
+  if (N == 0) return v[0];
+  if (N == 1) return i == 0 ? v[0] : v[1];
+  return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]);
+}
+
+template <int LA, int LB>
+SLV_HD void axis_factors_t(double PA, double PB, double h, double b, int la, int lb,
+                           double &S0, double &Sp, double &Sm, double &T0, double &Tp, double &Tm) {
+  constexpr int NI = LA + 2, NJ = LB + 3;
+  double s[NI][NJ];
+  s[0][0] = 1.0;
+  s[0][1] = PB;
+#pragma unroll
+  for (int j = 1; j < NJ - 1; ++j) s[0][j + 1] = PB * s[0][j] + h * j * s[0][j - 1];
+#pragma unroll
+  for (int i = 0; i < NI - 1; ++i) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      double v = PA * s[i][j];
+      if (i > 0) v += h * i * s[i - 1][j];
+      if (j > 0) v += h * j * s[i][j - 1];
+      s[i + 1][j] = v;
+    }
+  }
+  double cm[NI], c0[NI], cp[NI];                  // columns lb-2, lb, lb+2 of every row
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    double a0[3], a2[3];
+#pragma unroll
+    for (int j = 0; j <= LB; ++j) { a0[j] = s[i][j]; a2[j] = s[i][j + 2]; }
+    c0[i] = selN<LB>(lb, a0);
+    cp[i] = selN<LB>(lb, a2);
+    cm[i] = (LB == 2 && lb == 2) ? s[i][0] : 0.0;
+  }
+  double lo0[3], mid0[3], hi0[3], lo1[3], mid1[3], hi1[3], lo2[3], mid2[3], hi2[3];
+#pragma unroll
+  for (int i = 0; i <= LA; ++i) {
+    mid0[i] = cm[i]; hi0[i] = cm[i + 1]; lo0[i] = i > 0 ? cm[i - 1] : 0.0;
+    mid1[i] = c0[i]; hi1[i] = c0[i + 1]; lo1[i] = i > 0 ? c0[i - 1] : 0.0;
+    mid2[i] = cp[i]; hi2[i] = cp[i + 1]; lo2[i] = i > 0 ? cp[i - 1] : 0.0;
+  }
+  const double r0m = selN<LA>(la, mid0), rpm = selN<LA>(la, hi0), rmm = selN<LA>(la, lo0);
+  const double r00 = selN<LA>(la, mid1), rp0 = selN<LA>(la, hi1), rm0 = selN<LA>(la, lo1);
+  const double r0p = selN<LA>(la, mid2), rpp = selN<LA>(la, hi2), rmp = selN<LA>(la, lo2);
+  const double k0 = b * (2.0 * lb + 1.0), k2 = -2.0 * b * b, km = -0.5 * lb * (lb - 1.0);
+  S0 = r00; Sp = rp0; Sm = rm0;
+  T0 = k0 * r00 + k2 * r0p + km * r0m;
+  Tp = k0 * rp0 + k2 * rpp + km * rpm;
+  Tm = k0 * rm0 + k2 * rmp + km * rmm;
+}
+
+template <int LA, int LB>
+SLV_HD void ao_pair_t(const double A[3], const int la[3], int npa, const double *ea, const double *ca,
+                      const double B[3], const int lb[3], int npb, const double *eb, const double *cb,
+                      const double L[3], double out[4]) {
+  const double ABx = A[0] - B[0], ABy = A[1] - B[1], ABz = A[2] - B[2];
+  const double AB2 = ABx * ABx + ABy * ABy + ABz * ABz;
+  double S = 0.0, T = 0.0, dS = 0.0, dT = 0.0;
+  for (int p = 0; p < npa; ++p) {
+    const double a = ea[p];
+    for (int q = 0; q < npb; ++q) {
+      const double b = eb[q];
+      const double pp = a + b, ip = 1.0 / pp, h = 0.5 * ip;
+      const double mu = a * b * ip;
+      if (mu * AB2 > 46.0) continue;
+      const double pref = ca[p] * cb[q] * exp(-mu * AB2) * (3.14159265358979323846 * ip) * sqrt(3.14159265358979323846 * ip);
+      const double fa = -b * ip, fb = a * ip;
+      double S0[3], Sp[3], Sm[3], T0[3], Tp[3], Tm[3];
+      axis_factors_t<LA, LB>(fa * ABx, fb * ABx, h, b, la[0], lb[0], S0[0], Sp[0], Sm[0], T0[0], Tp[0], Tm[0]);
+      axis_factors_t<LA, LB>(fa * ABy, fb * ABy, h, b, la[1], lb[1], S0[1], Sp[1], Sm[1], T0[1], Tp[1], Tm[1]);
+      axis_factors_t<LA, LB>(fa * ABz, fb * ABz, h, b, la[2], lb[2], S0[2], Sp[2], Sm[2], T0[2], Tp[2], Tm[2]);
+      const double sxy = S0[0] * S0[1], sxz = S0[0] * S0[2], syz = S0[1] * S0[2];
+      S += pref * sxy * S0[2];
+      T += pref * (T0[0] * syz + T0[1] * sxz + T0[2] * sxy);
+      const double a2 = 2.0 * a;
+      const double dsx = a2 * Sp[0] - la[0] * Sm[0], dsy = a2 * Sp[1] - la[1] * Sm[1], dsz = a2 * Sp[2] - la[2] * Sm[2];
+      const double dtx = a2 * Tp[0] - la[0] * Tm[0], dty = a2 * Tp[1] - la[1] * Tm[1], dtz = a2 * Tp[2] - la[2] * Tm[2];
+      const double gSx = dsx * syz, gSy = dsy * sxz, gSz = dsz * sxy;
+      const double gTx = dtx * syz + dsx * (T0[1] * S0[2] + S0[1] * T0[2]);
+      const double gTy = dty * sxz + dsy * (T0[0] * S0[2] + S0[0] * T0[2]);
+      const double gTz = dtz * sxy + dsz * (T0[0] * S0[1] + S0[0] * T0[1]);
+      dS += pref * (L[0] * gSx + L[1] * gSy + L[2] * gSz);
+      dT += pref * (L[0] * gTx + L[1] * gTy + L[2] * gTz);
+    }
+  }
+  out[0] = S; out[1] = T; out[2] = dS; out[3] = dT;
+}
+
 }  // namespace slv

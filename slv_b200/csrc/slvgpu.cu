@@ -285,7 +285,7 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
       const int g = nf < pl->rep_ctas ? nf : pl->rep_ctas;
       CK(cudaMemsetAsync(pl->rw.queue, 0, sizeof(int), st));
       ev_begin(pl, 3, st);
-      k_rep<<<g, REP_THREADS, rep_smem_bytes(pl->nmosc, pl->max_nmos, pl->natc, pl->max_nat), st>>>(p, (int)f0, nf, pl->fl, pl->rw, d_out);
+      k_rep<<<g, REP_THREADS, rep_smem_bytes(pl->nmosc, pl->max_nmos, pl->natc, pl->max_nat, pl->nbasc, pl->max_nbas), st>>>(p, (int)f0, nf, pl->fl, pl->rw, d_out, pl->max_nbas);
       ev_end(pl, st);
       ++pl->last_launches;
     }

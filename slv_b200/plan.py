@@ -113,8 +113,9 @@ class Plan(object):
             for t, bB in self._bfs.items():
                 cost = (bA.nprim[:, None] * bB.nprim[None, :]).ravel()
                 cls = (bA.powers.sum(1)[:, None] * 3 + bB.powers.sum(1)[None, :]).ravel()
-                order = numpy.lexsort((cls, -cost)).astype(numpy.int32)
-                meta[t][M['IO_PAIRORDER']] = it.add(order)
+                order = numpy.lexsort((-cost, cls)).astype(numpy.int32)          # class-major, heavy pairs first
+                offs = numpy.searchsorted(cls[order], numpy.arange(10)).astype(numpy.int32)
+                meta[t][M['IO_PAIRORDER']] = it.add(numpy.concatenate([offs, order]))
         # ---- solute: mode-contracted tables
         sol = numpy.full(_lib.NSOL, -1, numpy.int32)
         S = _lib.S
