@@ -304,8 +304,12 @@ extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, 
   if (!pl->own_stream) CK(cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking));
   // Device staging is bounded: two coordinate buffers of one slice each (double buffering), so trajectories far larger
   // than device memory stream through; the result rows of the whole call stay on the device until the end.
-  const int64_t first = pl->max_chunk < 1024 ? pl->max_chunk : 1024;   // a short first slice hides the first copy
+  // slice schedule: a first slice of ~16 MB of coordinates (its copy is the only one not hidden behind compute), then
+  // 8x that, then full-size slices so the persistent kernels keep a long queue
   const int64_t slice = pl->max_chunk;
+  int64_t first = (int64_t)(16.0e6 / ((double)p.natoms_total * 24.0));
+  first = first < 32 ? 32 : (first > 1024 ? 1024 : first);
+  if (first > slice) first = slice;
   const size_t fstride = (size_t)p.natoms_total * 3;
   if (pl->stage_slice < slice) {
     for (int b = 0; b < 2; ++b) { if (pl->d_stage_coords2[b]) cudaFree(pl->d_stage_coords2[b]); pl->d_stage_coords2[b] = nullptr; }
@@ -326,7 +330,9 @@ extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, 
   int64_t launches = 0, f0 = 0;
   for (int64_t c = 0; f0 < nframes; ++c) {
     const int b = (int)(c & 1);
-    const int64_t want = c == 0 ? first : slice, n = (nframes - f0) < want ? (nframes - f0) : want;
+    int64_t want = c == 0 ? first : (c == 1 ? 8 * first : slice);
+    if (want > slice) want = slice;
+    const int64_t n = (nframes - f0) < want ? (nframes - f0) : want;
     if (c >= 2) CK(cudaStreamWaitEvent(pl->copy_stream, pl->copy_ev[2 + b], 0));      // buffer b has been consumed
     CK(cudaMemcpyAsync(pl->d_stage_coords2[b], h_coords + f0 * fstride, (size_t)n * fstride * sizeof(double),
                        cudaMemcpyHostToDevice, pl->copy_stream));
