@@ -4,8 +4,9 @@
 the reference's column format: ``# Frame EL-CAMM EL-MEA EL-EA CORR-MEA CORR-EA POL-MEA POL-EA REP-MEA REP-EA DISP-MEA
 DISP-EA DISP-ISO TOTAL RMS-C RMS-S RMS-AVE`` (13 shifts %10.2f, 3 rms %10.5f).  Trajectories: a NumPy array
 [nframes, natoms, 3], a ``.npy`` file, or a multi-frame ``.xyz`` file; coordinates in Angstrom are converted to Bohr
-like the reference does (slv_md-run_nopp:205).  MDAnalysis readers (XTC/DCD/mdcrd) are not available here; anything
-that yields per-frame coordinate arrays can be passed as an iterable.  Frames may be sharded over ranks
+like the reference does (slv_md-run_nopp:205).  DCD (NAMD/CHARMM) and AMBER mdcrd
+files are read natively (the reference goes through MDAnalysis / its own readers, util/slv_md-run:117-152); GROMACS XTC
+(xdr-compressed) is not -- convert it or pass the coordinates as an array.  Frames may be sharded over ranks
 (``rank``/``world``): each rank evaluates its contiguous block and writes its own rows; frame numbers stay global.
 """
 import sys
@@ -38,6 +39,60 @@ def read_xyz_frames(path):
     return numpy.array(frames, numpy.float64)
 
 
+def read_dcd_frames(path, first=0, last=None):
+    """CHARMM/NAMD DCD trajectory (the `namd-charmm` branch of util/slv_md-run:117-152) -> float64 [nframes, natoms, 3]
+    in the file's units (Angstrom).  Little- or big-endian, with or without unit-cell records, fixed atoms unsupported."""
+    import struct
+    with open(path, 'rb') as fh:
+        raw = fh.read()
+    en = '<' if struct.unpack('<i', raw[:4])[0] == 84 else '>'
+    if struct.unpack(en + 'i', raw[:4])[0] != 84 or raw[4:8] != b'CORD':
+        raise IOError('%s is not a DCD coordinate file' % path)
+    icntrl = struct.unpack(en + '20i', raw[8:88])
+    nset, has_cell, nfixed = icntrl[0], icntrl[10] != 0, icntrl[8]
+    if nfixed:
+        raise NotImplementedError('DCD files with fixed atoms are not supported')
+    pos = 92
+    n = struct.unpack(en + 'i', raw[pos:pos + 4])[0]; pos += 8 + n            # title block
+    pos += 4; natoms = struct.unpack(en + 'i', raw[pos:pos + 4])[0]; pos += 8  # natoms block
+    frame_bytes = (56 if has_cell else 0) + 3 * (8 + 4 * natoms)
+    nset = min(nset, (len(raw) - pos) // frame_bytes) if nset > 0 else (len(raw) - pos) // frame_bytes
+    last = nset if last is None else min(last, nset)
+    out = numpy.empty((max(0, last - first), natoms, 3), numpy.float64)
+    for f in range(first, last):
+        q = pos + f * frame_bytes + (56 if has_cell else 0)
+        for d in range(3):
+            out[f - first, :, d] = numpy.frombuffer(raw, en + 'f4', natoms, q + 4)
+            q += 8 + 4 * natoms
+    return out
+
+
+def read_mdcrd_frames(path, natoms, box=False):
+    """AMBER ASCII trajectory (the `amber` branch of util/slv_md-run:128-130): title line, then 10F8.3 records;
+    `box` skips the three box lengths after every frame."""
+    with open(path) as fh:
+        fh.readline()
+        vals = numpy.array(fh.read().split(), numpy.float64)
+    per = 3 * natoms + (3 if box else 0)
+    nfr = len(vals) // per
+    return vals[:nfr * per].reshape(nfr, per)[:, :3 * natoms].reshape(nfr, natoms, 3).copy()
+
+
+def load_trajectory(traj, natoms=None):
+    """numpy array, .npy, multi-frame .xyz, .dcd or AMBER .mdcrd/.crd (needs natoms)."""
+    if not isinstance(traj, str):
+        return numpy.asarray(traj, numpy.float64)
+    low = traj.lower()
+    if low.endswith('.npy'):
+        return numpy.load(traj)
+    if low.endswith('.dcd'):
+        return read_dcd_frames(traj)
+    if low.endswith('.mdcrd') or low.endswith('.crd'):
+        assert natoms is not None, 'AMBER trajectories need the number of atoms'
+        return read_mdcrd_frames(traj, natoms)
+    return read_xyz_frames(traj)
+
+
 def format_rows(rows, shifts, first_frame=1):
     """Report lines for device output rows (slv_md-run_nopp:148-153)."""
     O = _lib.OUT
@@ -52,21 +107,23 @@ def format_rows(rows, shifts, first_frame=1):
 
 
 def run(solinp, traj, out, mode, nframes=None, cuts=(40.0, 17.0, 12.0), no_elect=False, no_polar=False, no_repul=False,
-        no_disp=False, no_correc=False, no_ea=False, units='angstrom', batch=4096, rank=0, world=1):
-    """Evaluate the SolEFP shifts of every frame and write the report; returns (rows, status) of this rank."""
+        no_disp=False, no_correc=False, no_ea=False, units='angstrom', batch=4096, rank=0, world=1, first_frame=0,
+        append=False, natoms=None):
+    """Evaluate the SolEFP shifts of every frame and write the report; returns (rows, status) of this rank.
+    `first_frame` (0-based) + `append` resume an interrupted run: frames are independent, so a restart just skips the
+    rows already in the report (the reference appends and flushes per frame but has no restart flag)."""
     args, idx = MDInput(solinp).get()
     efp = EFP(elect=not no_elect, pol=not no_polar, rep=not no_repul, disp=not no_disp, corr=not no_correc,
               ccut=cuts[0], pcut=cuts[1], ecut=cuts[2], freq=True, cunit=True, mode=mode, ea=not no_ea)
-    if isinstance(traj, str):
-        traj = numpy.load(traj) if traj.endswith('.npy') else read_xyz_frames(traj)
-    traj = numpy.asarray(traj, numpy.float64)
+    traj = numpy.asarray(load_trajectory(traj, natoms), numpy.float64)
     if nframes is not None:
         traj = traj[:nframes]
-    lo, hi = frame_range(len(traj), rank, world)
+    lo, hi = frame_range(len(traj) - first_frame, rank, world)
+    lo += first_frame; hi += first_frame
     scale = AngstromToBohr if units.lower().startswith('ang') else 1.0
     all_rows, all_status = [], []
-    fh = open(out, 'w') if isinstance(out, str) else out
-    if rank == 0:
+    fh = None if out is None else (open(out, 'a' if append else 'w') if isinstance(out, str) else out)
+    if fh is not None and rank == 0 and not append:
         fh.write(HEADER + '\n'); fh.flush()
     first = True
     for b0 in range(lo, hi, batch):
@@ -74,10 +131,12 @@ def run(solinp, traj, out, mode, nframes=None, cuts=(40.0, 17.0, 12.0), no_elect
         coords = numpy.ascontiguousarray(traj[b0:b1][:, idx, :] * scale)
         rows, status = efp.eval_frames(coords, *args) if first else efp.eval_frames(coords)
         first = False
-        fh.writelines(format_rows(rows, efp.shifts_of(rows), first_frame=b0 + 1)); fh.flush()
+        if fh is not None:
+            fh.writelines(format_rows(rows, efp.shifts_of(rows), first_frame=b0 + 1)); fh.flush()
         all_rows.append(rows.copy()); all_status.append(status.copy())
     if isinstance(out, str):
         fh.close()
+    run.last_efp = efp
     if not all_rows:
         return numpy.zeros((0, _lib.NOUT)), numpy.zeros(0, numpy.int32)
     return numpy.concatenate(all_rows), numpy.concatenate(all_status)
@@ -87,7 +146,10 @@ def main(argv=None):
     import argparse
     ap = argparse.ArgumentParser(description='SolEFP frequency shifts over an MD trajectory (slv_md-run on the B200)')
     ap.add_argument('-i', '--inp', required=True, help='$Frag input file')
-    ap.add_argument('-t', '--traj', required=True, help='.npy [nframes,natoms,3] or multi-frame .xyz')
+    ap.add_argument('-t', '--traj', required=True, help='.npy [nframes,natoms,3], multi-frame .xyz, .dcd or AMBER .mdcrd')
+    ap.add_argument('--natoms', type=int, default=None, help='atoms per frame (AMBER trajectories)')
+    ap.add_argument('--first-frame', type=int, default=0, help='0-based frame to start from (resume)')
+    ap.add_argument('--append', action='store_true', help='append to an existing report (resume)')
     ap.add_argument('-o', '--out', default='shifts.dat')
     ap.add_argument('-m', '--mode', type=int, required=True)
     ap.add_argument('-n', '--nframes', type=int, default=None)
@@ -97,9 +159,41 @@ def main(argv=None):
     ap.add_argument('--bohr', action='store_true', help='trajectory already in Bohr')
     for f in ('no-elect', 'no-polar', 'no-repul', 'no-disp', 'no-correc', 'no-ea'):
         ap.add_argument('--' + f, action='store_true')
+    ap.add_argument('--distributed', action='store_true',
+                    help='under torchrun: frames are sharded over the ranks (one GPU each), rank 0 gathers the rows and writes the report')
     a = ap.parse_args(argv)
+    if a.distributed:
+        return _main_distributed(a)
     run(a.inp, a.traj, a.out, a.mode, a.nframes, (a.ccut, a.pcut, a.ecut), a.no_elect, a.no_polar, a.no_repul, a.no_disp,
-        a.no_correc, a.no_ea, units='bohr' if a.bohr else 'angstrom')
+        a.no_correc, a.no_ea, units='bohr' if a.bohr else 'angstrom', first_frame=a.first_frame, append=a.append,
+        natoms=a.natoms)
+
+
+def _main_distributed(a):
+    import os
+    import torch
+    import torch.distributed as dist
+    from .shard import gather_rows
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+    cuda = torch.cuda.is_available()
+    if cuda:
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    dist.init_process_group('nccl' if cuda else 'gloo')
+    traj = numpy.asarray(load_trajectory(a.traj, a.natoms), numpy.float64)
+    if a.nframes is not None:
+        traj = traj[:a.nframes]
+    rows, status = run(a.inp, traj, None, a.mode, None, (a.ccut, a.pcut, a.ecut), a.no_elect, a.no_polar, a.no_repul, a.no_disp,
+                       a.no_correc, a.no_ea, units='bohr' if a.bohr else 'angstrom', rank=rank, world=world)
+    t = torch.from_numpy(rows)
+    if cuda:
+        t = t.cuda()
+    allrows = gather_rows(t, len(traj), dst=0)          # the run's one collective
+    if rank == 0:
+        allrows = allrows.cpu().numpy()
+        with open(a.out, 'w') as fh:
+            fh.write(HEADER + '\n')
+            fh.writelines(format_rows(allrows, run.last_efp.shifts_of(allrows), first_frame=1))
+    dist.destroy_process_group()
 
 
 if __name__ == '__main__':

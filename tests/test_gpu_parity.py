@@ -274,6 +274,11 @@ def test_md_run_report_format(frags, golden, tmp_path):
     for i in range(5):
         ele = sum(float(lines[1 + i].split()[k]) for k in (2, 3, 4, 5))
         assert abs(ele - golden['dat'][i][1]) < 0.03
+    # resume: three frames, then the rest appended -> the same report
+    out2 = tmp_path / 'resumed.dat'
+    mdrun.run(inp, X, str(out2), 8, nframes=3, cuts=(1e10, 1e10, 1e10), no_repul=True)
+    mdrun.run(inp, X, str(out2), 8, cuts=(1e10, 1e10, 1e10), no_repul=True, first_frame=3, append=True)
+    assert out2.read_text() == out.read_text()
 
 
 def test_protein_like_mixed_fragments(frags):

@@ -25,3 +25,42 @@ def test_read_xyz_frames(tmp_path):
     fn.write_text('2\nc\nO 0 0 0\nH 1 0 0\n2\nc\nO 0 0 1\nH 1 0 1\n')
     X = mdrun.read_xyz_frames(str(fn))
     assert X.shape == (2, 2, 3) and X[1, 1, 2] == 1.0
+
+
+def _write_dcd(path, X, cell=False, endian='<'):
+    import struct
+    nf, na = X.shape[:2]
+    with open(path, 'wb') as fh:
+        ic = [0] * 20; ic[0] = nf; ic[1] = 1; ic[2] = 1; ic[10] = 1 if cell else 0; ic[19] = 24
+        fh.write(struct.pack(endian + 'i', 84) + b'CORD' + struct.pack(endian + '20i', *ic) + struct.pack(endian + 'i', 84))
+        title = b'REMARKS synthetic'.ljust(80)
+        fh.write(struct.pack(endian + 'i', 84) + struct.pack(endian + 'i', 1) + title + struct.pack(endian + 'i', 84))
+        fh.write(struct.pack(endian + 'i', 4) + struct.pack(endian + 'i', na) + struct.pack(endian + 'i', 4))
+        for f in range(nf):
+            if cell:
+                fh.write(struct.pack(endian + 'i', 48) + struct.pack(endian + '6d', 30, 0, 30, 0, 0, 30) + struct.pack(endian + 'i', 48))
+            for d in range(3):
+                fh.write(struct.pack(endian + 'i', 4 * na) + X[f, :, d].astype(endian + 'f4').tobytes() + struct.pack(endian + 'i', 4 * na))
+
+
+def test_dcd_and_mdcrd_readers(tmp_path):
+    from slv_b200 import mdrun
+    rng = np.random.default_rng(0)
+    X = np.round(rng.normal(0, 10, (5, 7, 3)), 3)
+    for cell in (False, True):
+        for en in ('<', '>'):
+            fn = str(tmp_path / ('t%d%s.dcd' % (cell, 'l' if en == '<' else 'b')))
+            _write_dcd(fn, X, cell, en)
+            Y = mdrun.read_dcd_frames(fn)
+            assert Y.shape == X.shape and np.abs(Y - X).max() < 1e-5
+            assert np.abs(mdrun.read_dcd_frames(fn, 2, 4) - X[2:4]).max() < 1e-5
+    fn = tmp_path / 't.mdcrd'
+    vals = X.reshape(5, -1)
+    with open(fn, 'w') as fh:
+        fh.write('title\n')
+        for f in range(5):
+            row = list(vals[f]) + [30.0, 30.0, 30.0]
+            for i in range(0, len(row), 10):
+                fh.write(''.join('%8.3f' % v for v in row[i:i + 10]) + '\n')
+    Y = mdrun.read_mdcrd_frames(str(fn), 7, box=True)
+    assert Y.shape == X.shape and np.abs(Y - X).max() < 1e-9
