@@ -136,7 +136,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   memset(&p, 0, sizeof(p));
   p.ntypes = d->ntypes; p.ninst = d->ninst; p.natoms_total = d->natoms_total; p.flags = d->flags;
   p.ccut = d->ccut; p.pcut = d->pcut; p.ecut = d->ecut;
-  p.pol_maxit = d->pol_maxit > 0 ? d->pol_maxit : 200;
+  p.pol_maxit = d->pol_maxit > 0 ? d->pol_maxit : 1000;
   p.pol_tol = d->pol_tol > 0 ? d->pol_tol : 1e-10;
   int rc = 0;
 #define TRY(x) do { rc = (x); if (rc) { slvgpu_plan_destroy(pl); return rc; } } while (0)

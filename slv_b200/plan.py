@@ -55,7 +55,7 @@ class Plan(object):
     """Device-resident evaluation plan (owns the slvgpu_plan handle)."""
 
     def __init__(self, ind, nmol, bsm, supl, reord, mode, flags, ccut, pcut, ecut,
-                 max_chunk=4096, pol_maxit=200, pol_tol=1e-10, pol_cent_cap=0, want_detail=False,
+                 max_chunk=4096, pol_maxit=1000, pol_tol=1e-10, pol_cent_cap=0, want_detail=False,
                  g_override=None, removable=None):
         ind = numpy.asarray(ind, int); nmol = numpy.asarray(nmol, int)
         assert len(ind) == len(nmol) and len(ind) >= 1

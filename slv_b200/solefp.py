@@ -124,7 +124,7 @@ class EFP(UNITS):
         self.shift_terms = SHIFT_TERMS
         self._rms_central = None; self._rms_solvent_max = None; self._rms_ave = None
         self._bsm = None; self._supl = None; self._reord = None; self._ind = None; self._nmol = None
-        self.pol_maxit = 200; self.pol_tol = 1e-10; self.max_chunk = 4096; self.pol_cent_cap = 0
+        self.pol_maxit = 1000; self.pol_tol = 1e-10; self.max_chunk = 4096; self.pol_cent_cap = 0
         self.want_detail = False
         self._removable = None
 

@@ -401,3 +401,22 @@ def test_large_polarisation_system_multi_tile(frags):
     c = O.HartreePerHbarToCmRec
     for k in TERMS:
         assert abs(got[k][0] - ref[k] * c) < TOL, (k, got[k][0], ref[k] * c)
+
+
+def test_ill_conditioned_polarisation_still_converges(frags):
+    """Overlapping fragments (an unphysically dense water/DMSO lattice) make the induction matrix ill-conditioned: the
+    reference's LU still returns a number, so the BiCG solve has to get there too (hundreds of iterations, status 0)."""
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O
+    sol, wat, dmso = frags('mescn'), frags('water'), frags('dmso')
+    types = np.random.default_rng(3).integers(0, 2, 60)
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos(), dmso.get_pos()], types, 3, seed=3, spacing=7.2)
+    ind = [0] + [1 + int(t) for t in types]; nmol = [7] + [3 if t == 0 else 10 for t in types]
+    efp = _efp(mode=4, disp=False, ccut=40.0, pcut=17.0, ecut=12.0)
+    rows, st = efp.eval_frames(X, ind, nmol, [sol, wat, dmso], [None] * 3, [None] * 3)
+    assert int(st.max()) == 0 and rows[:, 14].max() > 100
+    c = O.HartreePerHbarToCmRec
+    for f in range(3):
+        ref = O.eval_frame(X[f], ind, nmol, [sol.get(), wat.get(), dmso.get()], [None] * 3, [None] * 3, 4, 40.0, 17.0, 12.0,
+                           elect=True, pol=True)
+        assert abs(rows[f, 4] * c - ref['pol_mea'] * c) < max(TOL, 1e-8 * abs(ref['pol_mea'] * c)), (f, rows[f, 4] * c, ref['pol_mea'] * c)
