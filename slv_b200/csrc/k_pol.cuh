@@ -19,7 +19,7 @@
 namespace slv {
 
 constexpr int POL_THREADS = 256;
-constexpr int POL_TILE = 512;    // centres staged per shared-memory tile of the sweep (== POL_THREADS)
+constexpr int POL_TILE = 512;    // centres staged per shared-memory tile of the sweep (strided load by the 256 threads)
 constexpr int SITE_ROW = 24;     // pos3, mom20, molecule id
 constexpr int PST = 30;          // BiCG state per centre: x xt r rt p pt u ut q qt (3 each)
 
