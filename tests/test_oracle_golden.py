@@ -59,3 +59,28 @@ def test_one_atom_fragment_is_pure_shift():
     from oracle import solefp_oracle as O
     rot, tr, rms = O.kabsch(np.array([[1.0, 2.0, 3.0]]), np.array([[4.0, 4.0, 4.0]]))
     assert np.allclose(rot, np.eye(3)) and np.allclose(tr, [3.0, 2.0, 1.0]) and rms == 0.0
+
+
+def test_wavefunction_fixtures_pin_basis_and_overlap_derivatives(frags):
+    """The reference's own parameter files pin the integral conventions of the repulsion path: the LMO
+    coefficients (`vecl`) must be orthonormal under the restated overlap, C S C^T = I, and their mode
+    derivatives (`vecl1`, finite differences in the .frg) must satisfy d/dQ (C S C^T) = 0, i.e.
+    C1 S C^T + C S C1^T + C dS C^T = 0 with dS built from the centre derivatives the way shftex.f:157-206
+    contracts them.  This fixes basis data, function order, normalisation, and the sign/centre convention of
+    getSA1B (solefp.py:1521-1524) without PyQuante."""
+    from oracle import ints_oracle as IO
+    from slv_b200 import basis
+    for name in ('nma', 'water', 'meoh'):
+        p = frags(name).get()
+        b = basis.BasisSet(p['atno'], p['pos'])
+        S, T, S1, T1 = IO.one_electron(b, p['pos'], b, p['pos'])
+        C = p['vecl']
+        assert np.abs(C @ S @ C.T - np.eye(len(C))).max() < 1e-8, name
+        if p.get('vecl1') is None:
+            continue
+        for m in range(len(p['vecl1'])):
+            dS = np.einsum('ka,kla->kl', p['lvec'][m][b.center], S1)
+            dS = dS + dS.T
+            C1 = p['vecl1'][m]
+            assert np.abs(C1 @ S @ C.T).max() > 1e-3          # the relation is not trivially satisfied
+            assert np.abs(C1 @ S @ C.T + C @ S @ C1.T + C @ dS @ C.T).max() < 2e-6, (name, m)
