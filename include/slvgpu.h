@@ -74,10 +74,12 @@ enum {
   SLVGPU_M_O_BFEXP,   /* dtab: [nbasis][6] exponents                                             */
   SLVGPU_M_O_BFCOEF,  /* dtab: [nbasis][6] normalised contraction coefficients                   */
   SLVGPU_M_REMOVABLE, /* 1: polarisation of this type is treated pair-wise (remove_clashes)          */
-  SLVGPU_M_NSHELL,    /* number of basis shells                                                  */
-  SLVGPU_M_IO_SHELL,  /* itab: [nshell][4] atom, first function, functions in shell, primitives  */
-  SLVGPU_M_IO_PAIRORDER, /* itab: [10] class offsets + [nbasis_solute * nbasis] (solute AO, this type's AO) pairs,
-                          * grouped by angular-momentum class (3 L_bra + L_ket), heavy pairs first            */
+  SLVGPU_M_NSUBSH,   /* number of basis sub-shells (an SP shell counts as an S and a P sub-shell)  */
+  SLVGPU_M_IO_SUBSH, /* itab: [nsubsh][4] atom, first function, angular momentum, primitives      */
+  SLVGPU_M_IO_SHPAIR, /* itab: exchange-repulsion integral work list against the solute: [24] class offsets, then the
+                       * work items a * nsubsh + b (a: solute sub-shell, b: this type's), grouped by the 23
+                       * (L_bra, L_ket, bra component) specialisations of slv_ints.cuh SLV_SUBSHELL_CLASSES,
+                       * heavy primitive-pair counts first inside a class                                    */
   SLVGPU_NMETA = 32
 };
 

@@ -55,7 +55,8 @@ class BasisSet(object):
     Attributes (numpy): center[nbf] atom index, powers[nbf,3], nprim[nbf], exps[nbf,MAXPRIM],
     coefs[nbf,MAXPRIM] (contraction coefficient x primitive norm x contracted norm; zero padded);
     shells[nshell,4] = atom, first function, number of functions (S 1, P 3, D 6, L = SP 4), primitives --
-    all functions of a shell share the exponents of its first function."""
+    all functions of a shell share the exponents of its first function; subshells[nsub,4] = atom, first function,
+    angular momentum, primitives (L shells split into their S and P parts)."""
 
     def __init__(self, atno, pos, name='6-311++G**'):
         tab = _table()
@@ -76,6 +77,14 @@ class BasisSet(object):
                 shells.append((ia, f0, len(center) - f0, len(prims)))
         self.atno = numpy.asarray(atno, int)
         self.shells = numpy.array(shells, numpy.int32).reshape(-1, 4)
+        # sub-shells: (atom, first function, angular momentum, primitives); an L shell is an S and a P sub-shell
+        sub = []
+        for ia, f0, nf, npr in shells:
+            if nf == 4:
+                sub += [(ia, f0, 0, npr), (ia, f0 + 1, 1, npr)]
+            else:
+                sub.append((ia, f0, {1: 0, 3: 1, 6: 2}[nf], npr))
+        self.subshells = numpy.array(sub, numpy.int32).reshape(-1, 4)
         self.pos = numpy.asarray(pos, numpy.float64)
         self.center = numpy.array(center, numpy.int32)
         self.powers = numpy.array(powers, numpy.int32)

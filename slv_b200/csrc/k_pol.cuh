@@ -18,7 +18,14 @@
 
 namespace slv {
 
-constexpr int POL_THREADS = 256;
+#ifndef SLV_POL_THREADS
+#define SLV_POL_THREADS 256
+#endif
+#ifndef SLV_POL_CTAS_PER_SM
+#define SLV_POL_CTAS_PER_SM 2
+#endif
+constexpr int POL_THREADS = SLV_POL_THREADS;
+constexpr int POL_CTAS_PER_SM = SLV_POL_CTAS_PER_SM;
 constexpr int POL_TILE = 512;    // centres staged per shared-memory tile of the sweep (strided load by the 256 threads)
 constexpr int SITE_ROW = 24;     // pos3, mom20, molecule id
 constexpr int PST = 30;          // BiCG state per centre: x xt r rt p pt u ut q qt (3 each)
@@ -35,7 +42,21 @@ struct PolWork {                 // per-CTA workspace (device pointers already o
   int *ent_soff;      // [list_cap] first site of a list entry
 };
 
-__global__ void __launch_bounds__(POL_THREADS, 2)
+// One ordered centre pair of the BiCG sweep: dipole tensor of R = rc - r_j applied to the two search directions
+// held in the tile entry tt = {r_j(3), p_j(3), ut_j(3)}; same-molecule pairs (incl. self) are masked branch-free.
+__device__ __forceinline__ void sweep_pair(const double rc[3], const bool same, const double tt[9], double ax[3], double ay[3]) {
+  const double Rx = rc[0] - tt[0], Ry = rc[1] - tt[1], Rz = rc[2] - tt[2];
+  const double r2 = same ? 1.0 : (Rx * Rx + Ry * Ry + Rz * Rz);
+  const double u = rsqrt_fast(r2), u2 = u * u;
+  const double u3 = same ? 0.0 : u2 * u, t5 = 3.0 * u3 * u2;
+  const double Rxj = fma(Rz, tt[5], fma(Ry, tt[4], Rx * tt[3]));
+  const double Ryj = fma(Rz, tt[8], fma(Ry, tt[7], Rx * tt[6]));
+  const double fx = -t5 * Rxj, fy = -t5 * Ryj;
+  ax[0] = fma(fx, Rx, fma(u3, tt[3], ax[0])); ax[1] = fma(fx, Ry, fma(u3, tt[4], ax[1])); ax[2] = fma(fx, Rz, fma(u3, tt[5], ax[2]));
+  ay[0] = fma(fy, Rx, fma(u3, tt[6], ay[0])); ay[1] = fma(fy, Ry, fma(u3, tt[7], ay[1])); ay[2] = fma(fy, Rz, fma(u3, tt[8], ay[2]));
+}
+
+__global__ void __launch_bounds__(POL_THREADS, POL_CTAS_PER_SM)
 k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, double *__restrict__ out, int *__restrict__ status,
       double *__restrict__ detail /* optional [nframes][cent_cap][9]: dipind, flds, rpol */, int *__restrict__ queue) {
   __shared__ double s_red[64];
@@ -244,12 +265,17 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
         }
         if (resident) __syncthreads();
         double pq = 0.0;
-        for (int c0 = 0; c0 < ncent; c0 += NT) {
-          const int c = c0 + tid;
-          const bool act = c < ncent;
-          double rc[3] = {0, 0, 0}; int mc = -1;
-          if (act) { rc[0] = wk.cent_pos[(size_t)c * 3]; rc[1] = wk.cent_pos[(size_t)c * 3 + 1]; rc[2] = wk.cent_pos[(size_t)c * 3 + 2]; mc = wk.cent_mol[c]; }
-          double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0};
+        // Two rows (centres c and c + NT) per thread and sweep pass: the tile entry of column j is read from shared
+        // memory once for both, and the twelve independent accumulation chains keep the FP64 pipe fed with only
+        // four warps per scheduler.  A warp whose second row is empty everywhere runs the one-row loop.
+        for (int c0 = 0; c0 < ncent; c0 += 2 * NT) {
+          const int ca = c0 + tid, cb = ca + NT;
+          const bool acta = ca < ncent, actb = cb < ncent;
+          const bool anyb = __any_sync(0xffffffffu, actb);
+          double ra[3] = {0, 0, 0}, rb[3] = {0, 0, 0}; int ma = -1, mb = -1;
+          if (acta) { ra[0] = wk.cent_pos[(size_t)ca * 3]; ra[1] = wk.cent_pos[(size_t)ca * 3 + 1]; ra[2] = wk.cent_pos[(size_t)ca * 3 + 2]; ma = wk.cent_mol[ca]; }
+          if (actb) { rb[0] = wk.cent_pos[(size_t)cb * 3]; rb[1] = wk.cent_pos[(size_t)cb * 3 + 1]; rb[2] = wk.cent_pos[(size_t)cb * 3 + 2]; mb = wk.cent_mol[cb]; }
+          double axa[3] = {0, 0, 0}, aya[3] = {0, 0, 0}, axb[3] = {0, 0, 0}, ayb[3] = {0, 0, 0};
           for (int j0 = 0; j0 < ncent; j0 += POL_TILE) {
             if (!resident) {
               __syncthreads();
@@ -265,27 +291,29 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
               }
               __syncthreads();
             }
-            if (act) {
-              const int jn = min(POL_TILE, ncent - j0);
-#pragma unroll 4
+            const int jn = min(POL_TILE, ncent - j0);
+            if (anyb) {
+#pragma unroll 2
               for (int jj = 0; jj < jn; ++jj) {
-                const bool same = (s_tmol[jj] == mc);          // same molecule (incl. self): no interaction, branch-free
                 const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
                 const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
                 const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
-                const double Rx = rc[0] - tt[0], Ry = rc[1] - tt[1], Rz = rc[2] - tt[2];
-                const double r2 = same ? 1.0 : (Rx * Rx + Ry * Ry + Rz * Rz);
-                const double u = rsqrt_fast(r2), u2 = u * u;
-                const double u3 = same ? 0.0 : u2 * u, t5 = 3.0 * u3 * u2;
-                const double Rxj = fma(Rz, tt[5], fma(Ry, tt[4], Rx * tt[3]));
-                const double Ryj = fma(Rz, tt[8], fma(Ry, tt[7], Rx * tt[6]));
-                const double fx = -t5 * Rxj, fy = -t5 * Ryj;
-                ax[0] = fma(fx, Rx, fma(u3, tt[3], ax[0])); ax[1] = fma(fx, Ry, fma(u3, tt[4], ax[1])); ax[2] = fma(fx, Rz, fma(u3, tt[5], ax[2]));
-                ay[0] = fma(fy, Rx, fma(u3, tt[6], ay[0])); ay[1] = fma(fy, Ry, fma(u3, tt[7], ay[1])); ay[2] = fma(fy, Rz, fma(u3, tt[8], ay[2]));
+                const int mj = s_tmol[jj];
+                sweep_pair(ra, mj == ma, tt, axa, aya);
+                sweep_pair(rb, mj == mb, tt, axb, ayb);
+              }
+            } else if (acta) {
+#pragma unroll 4
+              for (int jj = 0; jj < jn; ++jj) {
+                const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
+                const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
+                const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
+                sweep_pair(ra, s_tmol[jj] == ma, tt, axa, aya);
               }
             }
           }
-          if (act) {      // q = p + alpha (T p), qt = pt + T ut
+          // q = p + alpha (T p), qt = pt + T ut
+          auto finish = [&](int c, const double *ax, const double *ay) {
             double *s_ = stt + (size_t)c * PST;
             const double *a = wk.cent_alpha + (size_t)c * 9;
             for (int i = 0; i < 3; ++i) {
@@ -294,7 +322,9 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
               pq += s_[15 + i] * q;
               s_[24 + i] = q; s_[27 + i] = qt;
             }
-          }
+          };
+          if (acta) finish(ca, axa, aya);
+          if (actb) finish(cb, axb, ayb);
         }
         pq = block_sum(pq, s_red);
         ++iters;

@@ -261,4 +261,168 @@ SLV_HD void ao_pair_t(const double A[3], const int la[3], int npa, const double 
   out[0] = S; out[1] = T; out[2] = dS; out[3] = dT;
 }
 
+
+// ---- sub-shell-pair form (the one k_rep runs).  A sub-shell is the set of Cartesian components of one angular
+// momentum on one atom sharing the primitive exponents (an SP "L" shell counts as an S and a P sub-shell).  One call
+// handles all ket components and either all bra components (IA < 0; used when the ket is an s sub-shell) or the single
+// bra component IA, so the exponential, the prefactor and the 1-D Obara-Saika tables of a primitive pair are computed
+// once for up to six AO pairs, and every power is a compile-time constant: no table selects, no dynamic indexing.
+// Contraction uses the coefficients of the FIRST component of each sub-shell; the caller rescales the other
+// components (d_xy.. carry sqrt(3) relative to d_xx.., slv_b200/basis.py).
+SLV_HD constexpr int cart_ncomp(int L) { return L == 0 ? 1 : (L == 1 ? 3 : 6); }
+// power along axis ax of component c: s; x,y,z; xx,yy,zz,xy,xz,yz (efprot.f:17-20 order)
+SLV_HD constexpr int cart_pow(int L, int c, int ax) {
+  return L == 0 ? 0
+       : L == 1 ? (c == ax ? 1 : 0)
+       : c < 3  ? (c == ax ? 2 : 0)
+       : c == 3 ? ((ax == 0 || ax == 1) ? 1 : 0)
+       : c == 4 ? ((ax == 0 || ax == 2) ? 1 : 0)
+                : ((ax == 1 || ax == 2) ? 1 : 0);
+}
+
+// One axis of one primitive pair.  IMAX: highest bra power handled on this axis; ALLI: values for every bra power
+// 0..IMAX (else only IMAX).  Outputs [bra power slot][ket power 0..LB]: overlap s, kinetic t, and the centre
+// derivatives ds = 2a s(i+1,j) - i s(i-1,j), dt likewise.
+template <int IMAX, int LB, bool ALLI>
+struct AxisVals {
+  static constexpr int NI = ALLI ? IMAX + 1 : 1;
+  double s[NI][LB + 1], t[NI][LB + 1], ds[NI][LB + 1], dt[NI][LB + 1];
+  SLV_HD void build(double PA, double PB, double h, double a, double b) {
+    constexpr int R = IMAX + 2, C = LB + 3;
+    double e[R][C];
+    e[0][0] = 1.0;
+    e[0][1] = PB;
+#pragma unroll
+    for (int j = 1; j < C - 1; ++j) e[0][j + 1] = PB * e[0][j] + h * j * e[0][j - 1];
+#pragma unroll
+    for (int i = 0; i < R - 1; ++i) {
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        double v = PA * e[i][j];
+        if (i > 0) v += h * i * e[i - 1][j];
+        if (j > 0) v += h * j * e[i][j - 1];
+        e[i + 1][j] = v;
+      }
+    }
+    const double k2 = -2.0 * b * b;
+    double k[R][LB + 1];                         // kinetic 1-D factor for every row
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+#pragma unroll
+      for (int j = 0; j <= LB; ++j) {
+        double v = b * (2.0 * j + 1.0) * e[i][j] + k2 * e[i][j + 2];
+        if (j >= 2) v += -0.5 * j * (j - 1.0) * e[i][j - 2];
+        k[i][j] = v;
+      }
+    }
+    const double a2 = 2.0 * a;
+#pragma unroll
+    for (int ii = 0; ii < NI; ++ii) {
+      const int i = ALLI ? ii : IMAX;
+#pragma unroll
+      for (int j = 0; j <= LB; ++j) {
+        s[ii][j] = e[i][j]; t[ii][j] = k[i][j];
+        double d1 = a2 * e[i + 1][j], d2 = a2 * k[i + 1][j];
+        if (i > 0) { d1 -= i * e[i - 1][j]; d2 -= i * k[i - 1][j]; }
+        ds[ii][j] = d1; dt[ii][j] = d2;
+      }
+    }
+  }
+  SLV_HD void scale(double f) {
+#pragma unroll
+    for (int ii = 0; ii < NI; ++ii) {
+#pragma unroll
+      for (int j = 0; j <= LB; ++j) { s[ii][j] *= f; t[ii][j] *= f; ds[ii][j] *= f; dt[ii][j] *= f; }
+    }
+  }
+};
+
+// acc[(ca * NB + cb) * 4 + q] += contributions of all primitive pairs; q = S, T, L.dS/dA, L.dT/dA.
+// ca = bra component slot (component index when IA < 0, else 0), cb = ket component.
+template <int LA, int LB, int IA>
+SLV_HD void subshell_pair_t(const double A[3], int npa, const double *ea, const double *ca,
+                            const double B[3], int npb, const double *eb, const double *cb,
+                            const double L[3], double *acc) {
+  constexpr bool ALL = IA < 0;
+  constexpr int NA = ALL ? cart_ncomp(LA) : 1, NB = cart_ncomp(LB);
+  constexpr int MX = ALL ? LA : cart_pow(LA, IA, 0), MY = ALL ? LA : cart_pow(LA, IA, 1), MZ = ALL ? LA : cart_pow(LA, IA, 2);
+  const double ABx = A[0] - B[0], ABy = A[1] - B[1], ABz = A[2] - B[2];
+  const double AB2 = ABx * ABx + ABy * ABy + ABz * ABz;
+#pragma unroll
+  for (int w = 0; w < NA * NB * 4; ++w) acc[w] = 0.0;
+  for (int p = 0; p < npa; ++p) {
+    const double a = ea[p];
+    for (int q = 0; q < npb; ++q) {
+      const double b = eb[q];
+      const double pp = a + b, ip = 1.0 / pp, h = 0.5 * ip;
+      const double mu = a * b * ip;
+      if (mu * AB2 > 46.0) continue;
+      const double pref = ca[p] * cb[q] * exp(-mu * AB2) * (3.14159265358979323846 * ip) * sqrt(3.14159265358979323846 * ip);
+      const double fa = -b * ip, fb = a * ip;
+      AxisVals<MX, LB, ALL> X; AxisVals<MY, LB, ALL> Y; AxisVals<MZ, LB, ALL> Z;
+      X.build(fa * ABx, fb * ABx, h, a, b); X.scale(pref);       // every term below carries exactly one x factor
+      Y.build(fa * ABy, fb * ABy, h, a, b);
+      Z.build(fa * ABz, fb * ABz, h, a, b);
+#pragma unroll
+      for (int c1 = 0; c1 < NA; ++c1) {
+        const int cc = ALL ? c1 : IA;
+        const int ix = ALL ? cart_pow(LA, cc, 0) : 0, iy = ALL ? cart_pow(LA, cc, 1) : 0, iz = ALL ? cart_pow(LA, cc, 2) : 0;
+#pragma unroll
+        for (int c2 = 0; c2 < NB; ++c2) {
+          const int jx = cart_pow(LB, c2, 0), jy = cart_pow(LB, c2, 1), jz = cart_pow(LB, c2, 2);
+          const double sx = X.s[ix][jx], sy = Y.s[iy][jy], sz = Z.s[iz][jz];
+          const double tx = X.t[ix][jx], ty = Y.t[iy][jy], tz = Z.t[iz][jz];
+          const double dsx = L[0] * X.ds[ix][jx], dsy = L[1] * Y.ds[iy][jy], dsz = L[2] * Z.ds[iz][jz];
+          const double dtx = L[0] * X.dt[ix][jx], dty = L[1] * Y.dt[iy][jy], dtz = L[2] * Z.dt[iz][jz];
+          const double sxy = sx * sy, syz = sy * sz;
+          const double tyz = ty * sz + sy * tz;                 // (T_y S_z + S_y T_z)
+          double *o = acc + (c1 * NB + c2) * 4;
+          o[0] += sxy * sz;
+          o[1] += tx * syz + sx * tyz;
+          o[2] += dsx * syz + sx * (dsy * sz + sy * dsz);
+          o[3] += dtx * syz + dsx * tyz + sx * (dty * sz + dsy * tz + sy * dtz + ty * dsz) + tx * (dsy * sz + sy * dsz);
+        }
+      }
+    }
+  }
+}
+
+// One work item of k_rep phase 1: sub-shells sa = {atom, first function, L, nprim} of the solute and sb of the
+// solvent fragment; writes V[((f0a + ca) * nbsB + f0b + cb) * 4 + q].  eX/cX are the per-function [nbf][6] exponent and
+// coefficient tables (coefficient x primitive norm x contracted norm), LcA the per-atom displacement vectors.
+template <int LA, int LB, int IA>
+SLV_HD void subshell_pair_store(const int *sa, const int *sb, const double *posA, const double *posB,
+                                const double *eA, const double *cA, const double *eB, const double *cB,
+                                const double *LcA, int nbsB, double *V) {
+  constexpr int NA = IA < 0 ? cart_ncomp(LA) : 1, NB = cart_ncomp(LB);
+  const int f0a = sa[1], f0b = sb[1];
+  double acc[NA * NB * 4];
+  subshell_pair_t<LA, LB, IA>(posA + sa[0] * 3, sa[3], eA + f0a * 6, cA + f0a * 6, posB + sb[0] * 3, sb[3], eB + f0b * 6, cB + f0b * 6,
+                              LcA + sa[0] * 3, acc);
+  const double ia0 = 1.0 / cA[f0a * 6], ib0 = 1.0 / cB[f0b * 6];
+#pragma unroll
+  for (int c1 = 0; c1 < NA; ++c1) {
+    const int k = f0a + (IA < 0 ? c1 : IA);
+    const double ra = (LA == 2) ? cA[k * 6] * ia0 : 1.0;          // only d components differ in norm within a sub-shell
+#pragma unroll
+    for (int c2 = 0; c2 < NB; ++c2) {
+      const int l = f0b + c2;
+      const double f = (LB == 2) ? ra * (cB[l * 6] * ib0) : ra;
+      double *v = V + ((size_t)k * nbsB + l) * 4;
+      v[0] = f * acc[(c1 * NB + c2) * 4]; v[1] = f * acc[(c1 * NB + c2) * 4 + 1];
+      v[2] = f * acc[(c1 * NB + c2) * 4 + 2]; v[3] = f * acc[(c1 * NB + c2) * 4 + 3];
+    }
+  }
+}
+
+// The 23 (LA, LB, IA) specialisations in the order of the plan's work list (slv_b200/plan.py, IO_SHPAIR):
+// ket s: all bra components at once; ket p and d: one bra component per item.
+#define SLV_SUBSHELL_CLASSES(X) \
+  X(0, 0, 0, -1) X(1, 1, 0, -1) X(2, 2, 0, -1) \
+  X(3, 0, 1, 0) X(4, 1, 1, 0) X(5, 1, 1, 1) X(6, 1, 1, 2) \
+  X(7, 2, 1, 0) X(8, 2, 1, 1) X(9, 2, 1, 2) X(10, 2, 1, 3) X(11, 2, 1, 4) X(12, 2, 1, 5) \
+  X(13, 0, 2, 0) X(14, 1, 2, 0) X(15, 1, 2, 1) X(16, 1, 2, 2) \
+  X(17, 2, 2, 0) X(18, 2, 2, 1) X(19, 2, 2, 2) X(20, 2, 2, 3) X(21, 2, 2, 4) X(22, 2, 2, 5)
+constexpr int SUBSHELL_NCLASS = 23;
+
 }  // namespace slv

@@ -35,7 +35,10 @@ struct slvgpu_plan {
   std::vector<void *> allocs;
   FrameLists fl{};
   PolWork pw{};
-  RepWork rw{};
+  RepPool rp{};
+  std::vector<int> rep_types;                 // fragment types that carry the wave-function tables
+  std::vector<std::vector<int>> rep_cls;      // per such type: the 24 class offsets of its integral work list
+  std::vector<int> h_pair0;
   double *d_detail = nullptr;
   int *d_queue = nullptr;
   int detail_frames = 0;
@@ -206,7 +209,8 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   TRY(dalloc(pl, &pl->fl.list_flag, ch * p.list_cap));
   TRY(dalloc(pl, &pl->fl.list_xf, ch * p.list_cap * 12));
   if (d->flags & SLVGPU_POL) {
-    pl->pol_ctas = pl->sm_count * 2;    // two persistent 256-thread CTAs per SM: one frame each, their barrier phases interleave
+    pl->pol_ctas = pl->sm_count * POL_CTAS_PER_SM;    // two persistent 256-thread CTAs per SM: one frame each, their barrier phases interleave (4 x 128 measured: better
+    // for ~400 centres, worse at ~500 and a longer tail -- DESIGN.md)
     const size_t nc = (size_t)pl->pol_ctas, cc = (size_t)p.cent_cap;
     TRY(dalloc(pl, &pl->pw.cent_pos, nc * cc * 3));
     TRY(dalloc(pl, &pl->pw.cent_alpha, nc * cc * 9));
@@ -227,15 +231,21 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
       slvgpu_plan_destroy(pl);
       return fail(SLVGPU_EINVAL, "exchange-repulsion needs the wave-function tables (vecl, fock, basis) in the plan");
     }
-    pl->rep_ctas = pl->sm_count * 2;
-    TRY(rep_alloc(pl->rw, pl->allocs, g_err, pl->rep_ctas, pl->nmosc, pl->nbasc, pl->max_nmos, pl->max_nbas));
+    TRY(rep_alloc(pl->rp, pl->allocs, g_err, pl->nmosc, pl->nbasc, pl->natc, pl->max_nbas, pl->max_nat, pl->max_chunk, p.list_cap));
+    for (int t = 0; t < d->ntypes; ++t) {
+      const int32_t *tm = d->type_meta + (size_t)t * SLVGPU_NMETA;
+      if (tm[SLVGPU_M_IO_SHPAIR] < 0) continue;
+      pl->rep_types.push_back(t);
+      pl->rep_cls.emplace_back(d->itab + tm[SLVGPU_M_IO_SHPAIR], d->itab + tm[SLVGPU_M_IO_SHPAIR] + SUBSHELL_NCLASS + 1);
+    }
+    pl->h_pair0.resize((size_t)pl->max_chunk + 1);
   }
 #undef TRY
   // opt in to large dynamic shared memory where needed
   cudaFuncSetAttribute(k_frame_elect, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_disp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_pol, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  cudaFuncSetAttribute(k_rep, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_rep_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   *out = pl;
   return 0;
 }
@@ -282,12 +292,47 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
       ++pl->last_launches;
     }
     if ((p.flags & SLVGPU_REP) && p.ninst > 1) {
-      const int g = nf < pl->rep_ctas ? nf : pl->rep_ctas;
-      CK(cudaMemsetAsync(pl->rw.queue, 0, sizeof(int), st));
+      // Exchange repulsion runs in batches of frames sized by the integral pool.  The batch boundaries need the
+      // per-frame fragment counts on the host: one small copy and a stream synchronisation per chunk.
       ev_begin(pl, 3, st);
-      k_rep<<<g, REP_THREADS, rep_smem_bytes(pl->nmosc, pl->max_nmos, pl->natc, pl->max_nat, pl->nbasc, pl->max_nbas), st>>>(p, (int)f0, nf, pl->fl, pl->rw, d_out, pl->max_nbas);
-      ev_end(pl, st);
+      k_rep_scan<<<1, 1024, 0, st>>>(d_out, (int)f0, nf, pl->rp.pair0);
       ++pl->last_launches;
+      CK(cudaMemcpyAsync(pl->h_pair0.data(), pl->rp.pair0, ((size_t)nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      const int *pair0 = pl->h_pair0.data();
+      const size_t sm_re = rep_smem_bytes(pl->nmosc, pl->nbasc, pl->max_nmos, pl->max_nbas, pl->natc, pl->max_nat);
+      for (int fs = 0; fs < nf;) {
+        int fe = fs;
+        while (fe < nf && pair0[fe + 1] - pair0[fs] <= pl->rp.pair_cap) ++fe;
+        if (fe == fs) return fail(SLVGPU_ENOMEM, "exchange repulsion: one frame has more fragments inside ecut than the integral pool holds");
+        const int nb = fe - fs, npairs = pair0[fe] - pair0[fs];
+        if (npairs > 0) {
+          k_rep_prep<<<nb, 128, 0, st>>>(p, fs, pl->fl, pl->rp);
+          ++pl->last_launches;
+          for (size_t ti = 0; ti < pl->rep_types.size(); ++ti) {
+            const int ty = pl->rep_types[ti];
+            const std::vector<int> &co = pl->rep_cls[ti];
+#define X(ID, LA, LB, IA)                                                                                         \
+            if (co[ID + 1] > co[ID]) {                                                                              \
+              const int n_items = co[ID + 1] - co[ID];                                                              \
+              const long nthr = (long)npairs * n_items;                                                             \
+              k_rep_ints<LA, LB, IA><<<(unsigned)((nthr + REP_INT_THREADS - 1) / REP_INT_THREADS), REP_INT_THREADS, 0, st>>>( \
+                  p, ty, co[ID], n_items, npairs, pl->rp);                                                          \
+              ++pl->last_launches;                                                                                  \
+            }
+            SLV_SUBSHELL_CLASSES(X)
+#undef X
+          }
+        }
+        if (npairs > 0) {
+          k_rep_pair<<<npairs, REP_THREADS, sm_re, st>>>(p, pl->fl, pl->rp, rep_jt(pl->max_nmos));
+          ++pl->last_launches;
+        }
+        k_rep_sum<<<(nb + 127) / 128, 128, 0, st>>>((int)f0, fs, nb, pl->rp, d_out);
+        ++pl->last_launches;
+        fs = fe;
+      }
+      ev_end(pl, st);
     }
   }
   k_status<<<(unsigned)((nframes + 255) / 256), 256, 0, st>>>(d_out, d_status, nframes);

@@ -51,6 +51,11 @@ def mode_weights(par, mode):
     return gijj / (par['redmass'] * par['freq'] ** 2) / den, den
 
 
+# (L_bra, L_ket, bra component or -1 = all) in the order of SLV_SUBSHELL_CLASSES (slv_b200/csrc/slv_ints.cuh)
+SUBSHELL_CLASSES = ([(la, 0, -1) for la in range(3)]
+                    + [(la, lb, ia) for lb in (1, 2) for la in range(3) for ia in range((1, 3, 6)[la])])
+
+
 class Plan(object):
     """Device-resident evaluation plan (owns the slvgpu_plan handle)."""
 
@@ -104,18 +109,25 @@ class Plan(object):
                 m[M['O_VECL']] = dt.add(par['vecl']); m[M['O_ZNUC']] = dt.add(numpy.asarray(par['atno'], float))
                 m[M['IO_BFC']] = it.add(bfs.center); m[M['IO_BFL']] = it.add(bfs.powers); m[M['IO_BFNP']] = it.add(bfs.nprim)
                 m[M['O_BFEXP']] = dt.add(bfs.exps); m[M['O_BFCOEF']] = dt.add(bfs.coefs)
-                m[M['NSHELL']] = len(bfs.shells); m[M['IO_SHELL']] = it.add(bfs.shells)
+                m[M['NSUBSH']] = len(bfs.subshells); m[M['IO_SUBSH']] = it.add(bfs.subshells)
                 self._bfs[t] = bfs
-        # ---- exchange-repulsion work order: for every fragment type B, the (solute AO, B AO) pairs sorted by their
-        #      primitive-pair count and angular-momentum class, so that the 32 lanes of a warp run equal-length loops
+        # ---- exchange-repulsion work list: for every fragment type B, the (solute sub-shell, B sub-shell) pairs
+        #      grouped by the 23 (L_bra, L_ket, bra component) specialisations of slv_ints.cuh (ket s: all bra
+        #      components in one item; ket p, d: one item per bra component) and sorted by primitive-pair count
+        #      inside a class: the integral kernel is launched once per class over all (frame, fragment) pairs of a
+        #      batch, so every warp runs one specialisation with near-equal loop lengths
         if need_rep and int(ind[0]) in self._bfs:
-            bA = self._bfs[int(ind[0])]
+            sA = self._bfs[int(ind[0])].subshells
             for t, bB in self._bfs.items():
-                cost = (bA.nprim[:, None] * bB.nprim[None, :]).ravel()
-                cls = (bA.powers.sum(1)[:, None] * 3 + bB.powers.sum(1)[None, :]).ravel()
-                order = numpy.lexsort((-cost, cls)).astype(numpy.int32)          # class-major, heavy pairs first
-                offs = numpy.searchsorted(cls[order], numpy.arange(10)).astype(numpy.int32)
-                meta[t][M['IO_PAIRORDER']] = it.add(numpy.concatenate([offs, order]))
+                sB = bB.subshells
+                cost = (sA[:, 3][:, None] * sB[:, 3][None, :])
+                items, offs = [], [0]
+                for LA, LB, IA in SUBSHELL_CLASSES:
+                    a, b = numpy.nonzero((sA[:, 2] == LA)[:, None] & (sB[:, 2] == LB)[None, :])
+                    o = numpy.argsort(-cost[a, b], kind='stable')
+                    items.append((a[o] * len(sB) + b[o]).astype(numpy.int32))
+                    offs.append(offs[-1] + len(o))
+                meta[t][M['IO_SHPAIR']] = it.add(numpy.concatenate([numpy.array(offs, numpy.int32)] + items))
         # ---- solute: mode-contracted tables
         sol = numpy.full(_lib.NSOL, -1, numpy.int32)
         S = _lib.S

@@ -122,3 +122,29 @@ def test_lean_field_equals_generic(L):
         assert np.abs(F1 - F2).max() < 1e-14 * np.abs(F1).max()
         L.hm_site_field_acc(P(np.array([1.0, 0.0, 0.0])), P(m), 5.0, 0.0, P(F3))      # masked: no contribution
         assert np.array_equal(F3, np.ones(3))
+
+
+@pytest.mark.parametrize('na,nb', [('water', 'water'), ('mescn', 'dmso'), ('nma', 'meoh')])
+def test_subshell_pair_integrals_match_oracle(L, frags, na, nb):
+    """The sub-shell-pair specialisations k_rep runs (slv_ints.cuh subshell_pair_store, all 23 classes) against
+    oracle/ints_oracle.py for two fragments in contact: S, T and the L-contracted centre derivatives."""
+    from oracle import ints_oracle as IO
+    from slv_b200.basis import BasisSet
+    rng = np.random.default_rng(5)
+    pa, pb = frags(na).get(), frags(nb).get()
+    posA = np.ascontiguousarray(pa['pos'], np.float64)
+    q = rng.normal(size=4); q /= np.linalg.norm(q); w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    posB = np.ascontiguousarray((pb['pos'] - pb['pos'].mean(0)) @ R + posA.mean(0) + np.array([5.5, 1.0, -0.7]))
+    bA, bB = BasisSet(pa['atno'], posA), BasisSet(pb['atno'], posB)
+    Lc = np.ascontiguousarray(rng.normal(size=(len(posA), 3)))
+    S, T, S1, T1 = IO.one_electron(bA, posA, bB, posB)
+    ref = np.stack([S, T, np.einsum('ka,kla->kl', Lc[bA.center], S1), np.einsum('ka,kla->kl', Lc[bA.center], T1)], -1)
+    V = np.full((len(bA), len(bB), 4), np.nan)
+    eA, cA, eB, cB = [np.ascontiguousarray(v, np.float64) for v in (bA.exps, bA.coefs, bB.exps, bB.coefs)]
+    sA, sB = np.ascontiguousarray(bA.subshells, np.int32), np.ascontiguousarray(bB.subshells, np.int32)
+    L.hm_subshell_V(len(sA), P(sA), P(posA), P(eA), P(cA), P(Lc), len(sB), P(sB), P(posB), P(eB), P(cB), len(bB), P(V))
+    assert np.isfinite(V).all()                       # every AO pair is written by exactly the classes walked
+    scale = np.abs(ref).max((0, 1))
+    assert (np.abs(V - ref).max((0, 1)) < 1e-12 * np.maximum(scale, 1.0)).all(), np.abs(V - ref).max((0, 1))

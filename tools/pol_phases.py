@@ -5,7 +5,7 @@ sys.path.insert(0, '.')
 from slv_b200 import synth
 from slv_b200.slvpar import Frag
 from slv_b200.solefp import EFP
-nw, nf = 500, 2048
+nw, nf = 500, 5888
 sol, wat = Frag('nma-d7'), Frag('water')
 X = synth.make_trajectory(sol.get_pos(), [wat.get_pos()], np.zeros(nw, int), 64, seed=2)
 X = np.concatenate([X] * (nf // 64))
