@@ -166,14 +166,21 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
     const int32_t *tm = d->type_meta + (size_t)t * SLVGPU_NMETA;
     if (tm[SLVGPU_M_NPOL] > p.max_npol) p.max_npol = tm[SLVGPU_M_NPOL];
     if (tm[SLVGPU_M_NDMA] > p.max_ndma) p.max_ndma = tm[SLVGPU_M_NDMA];
-    if (tm[SLVGPU_M_NMOS] > pl->max_nmos) pl->max_nmos = tm[SLVGPU_M_NMOS];
-    if (tm[SLVGPU_M_NBASIS] > pl->max_nbas) pl->max_nbas = tm[SLVGPU_M_NBASIS];
-    if (tm[SLVGPU_M_NATOMS] > pl->max_nat) pl->max_nat = tm[SLVGPU_M_NATOMS];
   }
+  std::vector<char> solvent_type((size_t)d->ntypes, 0);        // types that occur among the solvent instances
   for (int i = 0; i < d->ninst; ++i) {
     const int32_t *tm = d->type_meta + (size_t)d->inst_type[i] * SLVGPU_NMETA;
     tot_npol += tm[SLVGPU_M_NPOL]; tot_ndma += tm[SLVGPU_M_NDMA];
+    if (i > 0) {                                               // exchange-repulsion partner dimensions
+      solvent_type[d->inst_type[i]] = 1;
+      if (tm[SLVGPU_M_NMOS] > pl->max_nmos) pl->max_nmos = tm[SLVGPU_M_NMOS];
+      if (tm[SLVGPU_M_NBASIS] > pl->max_nbas) pl->max_nbas = tm[SLVGPU_M_NBASIS];
+      if (tm[SLVGPU_M_NATOMS] > pl->max_nat) pl->max_nat = tm[SLVGPU_M_NATOMS];
+    }
   }
+  if (pl->max_nmos < 1) pl->max_nmos = 1;
+  if (pl->max_nbas < 1) pl->max_nbas = 1;
+  if (pl->max_nat < 1) pl->max_nat = 1;
   const int32_t *tm0 = d->type_meta + (size_t)d->inst_type[0] * SLVGPU_NMETA;
   pl->ndmac = tm0[SLVGPU_M_NDMA]; pl->npolc = tm0[SLVGPU_M_NPOL]; pl->nmosc = tm0[SLVGPU_M_NMOS];
   pl->nbasc = tm0[SLVGPU_M_NBASIS]; pl->natc = tm0[SLVGPU_M_NATOMS];
@@ -234,7 +241,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
     TRY(rep_alloc(pl->rp, pl->allocs, g_err, pl->nmosc, pl->nbasc, pl->natc, pl->max_nbas, pl->max_nat, pl->max_chunk, p.list_cap));
     for (int t = 0; t < d->ntypes; ++t) {
       const int32_t *tm = d->type_meta + (size_t)t * SLVGPU_NMETA;
-      if (tm[SLVGPU_M_IO_SHPAIR] < 0) continue;
+      if (tm[SLVGPU_M_IO_SHPAIR] < 0 || !solvent_type[t]) continue;
       pl->rep_types.push_back(t);
       pl->rep_cls.emplace_back(d->itab + tm[SLVGPU_M_IO_SHPAIR], d->itab + tm[SLVGPU_M_IO_SHPAIR] + SUBSHELL_NCLASS + 1);
     }
