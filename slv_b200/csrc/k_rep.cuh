@@ -209,7 +209,10 @@ k_rep_ints(const DevPlan p, int type, int lo, int n_items, int npairs, RepPool r
 }
 
 // One CTA per (frame, fragment) pair: half transform, LMO integrals, CALCFI -> res[pair]
-__global__ void __launch_bounds__(REP_THREADS)
+#ifndef SLV_REP_PAIR_CTAS
+#define SLV_REP_PAIR_CTAS 4
+#endif
+__global__ void __launch_bounds__(REP_THREADS, SLV_REP_PAIR_CTAS)
 k_rep_pair(const DevPlan p, FrameLists fl, RepPool rp, const int REP_JT) {
   extern __shared__ double sm[];
   __shared__ double s_red[32];
@@ -226,6 +229,10 @@ k_rep_pair(const DevPlan p, FrameLists fl, RepPool rp, const int REP_JT) {
   const double *V = rp.V + (size_t)pr * rp.sV;
   const double *CA = rp.CA + (size_t)fi * 2 * nmosA * nbsA, *CA1 = CA + (size_t)nmosA * nbsA;
   const double *FA = p.dtab + tm0[SLVGPU_M_O_FOCK], *FA1 = p.dtab + p.sol_meta[SLVGPU_S_FOCK1], *ZA = p.dtab + tm0[SLVGPU_M_O_ZNUC];
+  // the pair's integrals were written by the previous kernels of the batch and the pool is far larger than L2: start
+  // pulling them in now, so that the half transform below finds them in L2 instead of paying DRAM latency per record
+  for (size_t b = (size_t)tid * 128; b < (size_t)nbsA * nbsB * 32; b += (size_t)NT * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(V) + b));
   double R[9], t[3];
   {
     const double *xf = fl.list_xf + ((size_t)fi * p.list_cap + e) * 12;
@@ -273,7 +280,7 @@ k_rep_pair(const DevPlan p, FrameLists fl, RepPool rp, const int REP_JT) {
         for (int q = 0; q < 4; ++q)
 #pragma unroll
           for (int jj = 0; jj < JB; ++jj) acc[q][jj] = 0.0;
-#pragma unroll 2
+#pragma unroll 4
         for (int l = 0; l < nbsB; ++l) {
           const double2 va = v2[2 * l], vb = v2[2 * l + 1];
 #pragma unroll
