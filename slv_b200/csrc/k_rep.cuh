@@ -20,6 +20,7 @@
 //                4  CALCFI per (i,j), block sum.
 // AO->LMO coefficients are rotated into the lab frame per fragment (VECROT, efprot.f:22-151).
 #pragma once
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "slv_common.cuh"
@@ -55,6 +56,10 @@ inline int rep_alloc(RepPool &rp, std::vector<void *> &allocs, std::string &err,
   size_t cap = budget / (rp.sV * sizeof(double));
   const size_t want = (size_t)max_chunk * (size_t)list_cap;
   if (cap > want) cap = want;
+  if (const char *ev = getenv("SLVGPU_REP_POOL_PAIRS")) {      // testing knob: force small batches
+    const long v = atol(ev);
+    if (v > 0 && (size_t)v < cap) cap = (size_t)v;
+  }
   if (cap < 1) cap = 1;
   rp.pair_cap = (int)(cap > 0x3fffffff ? 0x3fffffff : cap);
   void *q = nullptr;

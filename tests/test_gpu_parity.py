@@ -181,6 +181,35 @@ def test_exchange_repulsion_mixed_types(frags):
     assert abs(got['rep_mea'][0] - ref['rep_mea'] * c) < TOL * max(1.0, abs(ref['rep_mea'] * c) * 1e-3), (got['rep_mea'][0], ref['rep_mea'] * c)
 
 
+def test_exchange_repulsion_batches_are_bitwise_identical(frags, monkeypatch):
+    """The exchange-repulsion pipeline works in batches of (frame, fragment) pairs sized by its integral pool
+    (slvgpu.cu: k_rep_scan -> host split -> prep / ints / pair / sum per batch).  A pool of 7 pairs forces dozens of
+    batches, chunk boundaries inside the call, and frames with no fragment inside ecut; rows must equal the
+    single-batch result bit for bit (same per-pair arithmetic, ordered per-frame sum), and a pool smaller than one
+    frame's fragment count must fail loudly."""
+    from slv_b200 import synth
+    sol, wat, dmso = frags('mescn'), frags('water'), frags('dmso')
+    types = np.random.default_rng(3).integers(0, 2, 40)
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos(), dmso.get_pos()], types, 48, seed=5, spacing=8.0)
+    X[7, 7:] += 400.0                                   # frame 7: every fragment far outside all cut-offs
+    ind = [0] + [1 + int(t) for t in types]; nmol = [7] + [3 if t == 0 else 10 for t in types]
+
+    def run(max_chunk):
+        efp = _efp(mode=4, rep=True, pol=False, disp=False, ccut=30.0, pcut=15.0, ecut=13.0)
+        efp.max_chunk = max_chunk
+        rows, status = efp.eval_frames(X, ind, nmol, [sol, wat, dmso], [None] * 3, [None] * 3)
+        return np.array(rows), np.array(status)
+
+    ref, st = run(4096)
+    assert st.max() == 0 and ref[7, 13] == 0 and ref[7, 5] == 0.0 and ref[:, 13].max() >= 3
+    monkeypatch.setenv('SLVGPU_REP_POOL_PAIRS', str(int(ref[:, 13].max()) + 2))
+    got, st2 = run(20)                                  # 3 chunks, each split into many batches
+    assert st2.max() == 0 and np.array_equal(got, ref)
+    monkeypatch.setenv('SLVGPU_REP_POOL_PAIRS', '1')
+    with pytest.raises(Exception, match='integral pool'):
+        run(4096)
+
+
 def test_remove_clashes_additive_polarisation(frags):
     """EFP.eval(remove_clashes=True): NMA fragments ('N-methylacethamide' is on the reference's removable list)
     leave the many-body induction and are treated pair-wise; water stays."""
