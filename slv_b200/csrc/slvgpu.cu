@@ -35,7 +35,8 @@ struct slvgpu_plan {
   std::vector<void *> allocs;
   FrameLists fl{};
   PolWork pw{};
-  RepPool rp{};
+  RepPool rp[2] = {};
+  cudaStream_t rep_stream = nullptr; cudaEvent_t rep_ev[2] = {nullptr, nullptr};
   std::vector<int> rep_types;                 // fragment types that carry the wave-function tables
   std::vector<std::vector<int>> rep_cls;      // per such type: the 24 class offsets of its integral work list
   std::vector<int> h_pair0;
@@ -120,6 +121,8 @@ extern "C" void slvgpu_plan_destroy(slvgpu_plan *pl) {
   if (pl->d_stage_status) cudaFree(pl->d_stage_status);
   if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
   if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
+  if (pl->rep_stream) cudaStreamDestroy(pl->rep_stream);
+  for (int b = 0; b < 2; ++b) if (pl->rep_ev[b]) cudaEventDestroy(pl->rep_ev[b]);
   for (cudaEvent_t e : pl->copy_ev) cudaEventDestroy(e);
   delete pl;
 }
@@ -300,21 +303,33 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
     }
     if ((p.flags & SLVGPU_REP) && p.ninst > 1) {
       // Exchange repulsion runs in batches of frames sized by the integral pool.  The batch boundaries need the
-      // per-frame fragment counts on the host: one small copy and a stream synchronisation per chunk.
+      // per-frame fragment counts on the host: one small copy and a stream synchronisation per chunk.  Batches
+      // alternate between the caller's stream and a side stream (two pools): the throughput-bound integral kernels
+      // of one batch share the SMs with the latency-bound transform kernel of the other.
       ev_begin(pl, 3, st);
-      k_rep_scan<<<1, 1024, 0, st>>>(d_out, (int)f0, nf, pl->rp.pair0);
+      k_rep_scan<<<1, 1024, 0, st>>>(d_out, (int)f0, nf, pl->rp[0].pair0);
       ++pl->last_launches;
-      CK(cudaMemcpyAsync(pl->h_pair0.data(), pl->rp.pair0, ((size_t)nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
+      CK(cudaMemcpyAsync(pl->h_pair0.data(), pl->rp[0].pair0, ((size_t)nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));                          // everything the batches read is complete from here on
+      if (!pl->rep_stream) {
+        CK(cudaStreamCreateWithFlags(&pl->rep_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) CK(cudaEventCreateWithFlags(&pl->rep_ev[b], cudaEventDisableTiming));
+      }
       const int *pair0 = pl->h_pair0.data();
       const size_t sm_re = rep_smem_bytes(pl->nmosc, pl->nbasc, pl->max_nmos, pl->max_nbas, pl->natc, pl->max_nat);
-      for (int fs = 0; fs < nf;) {
+      int batch = 0;
+      for (int fs = 0; fs < nf; ++batch) {
+        const RepPool &rp = pl->rp[batch & 1];
+        cudaStream_t sb = (batch & 1) ? pl->rep_stream : st;
         int fe = fs;
-        while (fe < nf && pair0[fe + 1] - pair0[fs] <= pl->rp.pair_cap) ++fe;
-        if (fe == fs) return fail(SLVGPU_ENOMEM, "exchange repulsion: one frame has more fragments inside ecut than the integral pool holds");
+        while (fe < nf && pair0[fe + 1] - pair0[fs] <= rp.pair_cap) ++fe;
+        if (fe == fs) {
+          cudaStreamSynchronize(pl->rep_stream);
+          return fail(SLVGPU_ENOMEM, "exchange repulsion: one frame has more fragments inside ecut than the integral pool holds");
+        }
         const int nb = fe - fs, npairs = pair0[fe] - pair0[fs];
         if (npairs > 0) {
-          k_rep_prep<<<nb, 128, 0, st>>>(p, fs, pl->fl, pl->rp);
+          k_rep_prep<<<nb, 128, 0, sb>>>(p, fs, pl->fl, rp);
           ++pl->last_launches;
           for (size_t ti = 0; ti < pl->rep_types.size(); ++ti) {
             const int ty = pl->rep_types[ti];
@@ -323,21 +338,23 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
             if (co[ID + 1] > co[ID]) {                                                                              \
               const int n_items = co[ID + 1] - co[ID];                                                              \
               const long nthr = (long)npairs * n_items;                                                             \
-              k_rep_ints<LA, LB, IA><<<(unsigned)((nthr + REP_INT_THREADS - 1) / REP_INT_THREADS), REP_INT_THREADS, 0, st>>>( \
-                  p, ty, co[ID], n_items, npairs, pl->rp);                                                          \
+              k_rep_ints<LA, LB, IA><<<(unsigned)((nthr + REP_INT_THREADS - 1) / REP_INT_THREADS), REP_INT_THREADS, 0, sb>>>( \
+                  p, ty, co[ID], n_items, npairs, rp);                                                              \
               ++pl->last_launches;                                                                                  \
             }
             SLV_SUBSHELL_CLASSES(X)
 #undef X
           }
-        }
-        if (npairs > 0) {
-          k_rep_pair<<<npairs, REP_THREADS, sm_re, st>>>(p, pl->fl, pl->rp, rep_jt(pl->max_nmos));
+          k_rep_pair<<<npairs, REP_THREADS, sm_re, sb>>>(p, pl->fl, rp, rep_jt(pl->max_nmos));
           ++pl->last_launches;
         }
-        k_rep_sum<<<(nb + 127) / 128, 128, 0, st>>>((int)f0, fs, nb, pl->rp, d_out);
+        k_rep_sum<<<(nb + 127) / 128, 128, 0, sb>>>((int)f0, fs, nb, rp, d_out);
         ++pl->last_launches;
         fs = fe;
+      }
+      if (batch > 1) {                                        // join the side stream
+        CK(cudaEventRecord(pl->rep_ev[0], pl->rep_stream));
+        CK(cudaStreamWaitEvent(st, pl->rep_ev[0], 0));
       }
       ev_end(pl, st);
     }
