@@ -14,17 +14,7 @@ void hm_site_field(const double* R, const double* m, double f, double* F) { slv:
 void hm_site_dfield(const double* R, const double* v, const double* m, double sg, double* F) { slv::site_dfield(R, v, m, sg, F); }
 }
 #include "../slv_b200/csrc/slv_ints.cuh"
-extern "C" {
-void hm_ao_pair(const double* A, const int* la, int npa, const double* ea, const double* ca,
-                const double* B, const int* lb, int npb, const double* eb, const double* cb, const double* L, double* out) {
-  slv::ao_pair(A, la, npa, ea, ca, B, lb, npb, eb, cb, L, out);
-}
-}
 extern "C" void hm_site_field_acc(const double* R, const double* m, double f, double w, double* F) { slv::site_field_acc(R, m, f, w, F); }
-extern "C" void hm_shell_pair(const double* A, int nfa, const int* la, int npa, const double* ea, const double* ca,
-                              const double* B, int nfb, const int* lb, int npb, const double* eb, const double* cb, const double* L, double* out) {
-  slv::shell_pair(A, nfa, la, npa, ea, ca, B, nfb, lb, npb, eb, cb, L, out);
-}
 
 // all AO integrals between two fragments through the sub-shell-pair specialisations, walking the classes the way
 // k_rep does (tests/test_host_math.py compares with oracle/ints_oracle.py)
