@@ -130,7 +130,11 @@ void slvgpu_plan_destroy(slvgpu_plan *plan);
  * d_out [nframes][SLVGPU_NOUT] FP64, d_status [nframes] int32; `stream` is a cudaStream_t (0 = legacy
  * default).  Replaces, per frame, EFP.set + EFP.eval + get_shifts/get_rms*
  * (solvshift/solefp.py:223, 93-149, 1011-1629; natives: solpol2.f MOLLST/SFTPLI, libbbg clemtp
- * sdmtpm/sdmtpe/dmtcor/sdisp6/tdisp6, shftex.f SHFTEX, PyQuante getSAB/getTAB/getSA1B/getTA1B). */
+ * sdmtpm/sdmtpe/dmtcor/sdisp6/tdisp6, shftex.f SHFTEX, PyQuante getSAB/getTAB/getSA1B/getTA1B).
+ * Work is enqueued on `stream` and the call returns without waiting for it, except when the plan has
+ * SLVGPU_REP: the exchange-repulsion batches are sized from per-frame fragment counts read back on the host, so
+ * the call synchronises `stream` once per chunk of max_chunk frames (and is therefore not graph-capturable); its
+ * batches also use a plan-owned side stream that is joined back into `stream` before the call returns. */
 int slvgpu_eval_frames(slvgpu_plan *plan, const double *d_coords, int64_t nframes,
                        double *d_out, int32_t *d_status, void *stream);
 

@@ -1,5 +1,4 @@
-// k_rep.cuh -- kernel D: exchange-repulsion frequency shift.  Persistent CTAs with a dynamic frame queue;
-// per frame the CTA walks the solvent fragments inside ecut.
+// k_rep.cuh -- kernel group D: exchange-repulsion frequency shift, evaluated in batches of (frame, fragment) pairs.
 //
 // Reference: per solvent molecule B the Python layer builds both basis sets, calls PyQuante for the AO
 // integrals S, T, dS/dA, dT/dA (solvshift/solefp.py:1497-1526) and then SHFTEX (solvshift/src/shftex.f):
@@ -14,11 +13,13 @@
 //   k_rep_ints   AO integrals V[pair][k][l][4] = S, T, L.dS, L.dT: one launch per (fragment type, sub-shell class),
 //                one thread per (pair, sub-shell-pair item), grid-wide -- every warp runs one specialisation of
 //                slv_ints.cuh with near-equal loop lengths, at full occupancy
-//   k_rep        persistent CTAs, dynamic frame queue; per (frame, fragment):
+//   k_rep_pair   one CTA per (frame, fragment) pair:
 //                2  half transform  X[k][q][j] = sum_l V[k][l][q] C_B[j][l]
 //                3  LMO integrals   S_ij, T_ij, Sm_ij, Tm_ij
-//                4  CALCFI per (i,j), block sum.
-// AO->LMO coefficients are rotated into the lab frame per fragment (VECROT, efprot.f:22-151).
+//                4  CALCFI per (i,j), block sum -> res[pair]
+//   k_rep_sum    rep_mea of a frame = -(sum of its pair results, in list order)
+// AO->LMO coefficients are rotated into the lab frame per fragment (VECROT, efprot.f:22-151): the solute's once per
+// frame (k_rep_prep), the fragment's in k_rep_pair.
 #pragma once
 #include <cstdlib>
 #include <string>
