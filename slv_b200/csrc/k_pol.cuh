@@ -26,7 +26,7 @@ namespace slv {
 #endif
 constexpr int POL_THREADS = SLV_POL_THREADS;
 constexpr int POL_CTAS_PER_SM = SLV_POL_CTAS_PER_SM;
-constexpr int POL_TILE = 512;    // centres staged per shared-memory tile of the sweep (strided load by the 256 threads)
+constexpr int POL_TILE = 1024;   // centres the resident sweep tile holds (80 KB of shared memory)
 constexpr int SITE_ROW = 24;     // pos3, mom20, molecule id
 constexpr int PST = 30;          // BiCG state per centre: x xt r rt p pt u ut q qt (3 each)
 
@@ -37,6 +37,7 @@ struct PolWork {                 // per-CTA workspace (device pointers already o
   double *xy;         // [cent_cap][PST] BiCG state + [cent_cap][6] final x, y
   double *site;       // [site_cap][SITE_ROW]
   double *aux;        // [2][cent_cap][3] right-hand sides of the AVEC solve (detail mode)
+  double *part;       // [POL_THREADS/32][2][64][6] partial sums of the balanced sweep
   int *cent_mol;      // [cent_cap]
   int *ent_coff;      // [list_cap] first centre of a list entry
   int *ent_soff;      // [list_cap] first site of a list entry
@@ -74,6 +75,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     wk.cent_pos += cb * cc * 3; wk.cent_alpha += cb * cc * 9; wk.fld += cb * cc * 3; wk.xy += cb * cc * (PST + 6);
     wk.site += cb * (size_t)p.site_cap * SITE_ROW; wk.cent_mol += cb * cc; wk.aux += cb * cc * 6;
     wk.ent_coff += cb * (size_t)p.list_cap; wk.ent_soff += cb * (size_t)p.list_cap;
+    wk.part += cb * (size_t)(POL_THREADS / 32) * 2 * 64 * 6;
   }
   const int *tm0 = tmeta(p, p.inst_type[0]);
   const int npolc = tm0[SLVGPU_M_NPOL], ndmac = tm0[SLVGPU_M_NDMA];
@@ -265,19 +267,91 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
         }
         if (resident) __syncthreads();
         double pq = 0.0;
-        // Two rows (centres c and c + NT) per thread and sweep pass: the tile entry of column j is read from shared
-        // memory once for both, and the twelve independent accumulation chains keep the FP64 pipe fed with only
-        // four warps per scheduler.  A warp whose second row is empty everywhere runs the one-row loop.
-        for (int c0 = 0; c0 < ncent; c0 += 2 * NT) {
-          const int ca = c0 + tid, cb = ca + NT;
-          const bool acta = ca < ncent, actb = cb < ncent;
-          const bool anyb = __any_sync(0xffffffffu, actb);
-          double ra[3] = {0, 0, 0}, rb[3] = {0, 0, 0}; int ma = -1, mb = -1;
-          if (acta) { ra[0] = wk.cent_pos[(size_t)ca * 3]; ra[1] = wk.cent_pos[(size_t)ca * 3 + 1]; ra[2] = wk.cent_pos[(size_t)ca * 3 + 2]; ma = wk.cent_mol[ca]; }
-          if (actb) { rb[0] = wk.cent_pos[(size_t)cb * 3]; rb[1] = wk.cent_pos[(size_t)cb * 3 + 1]; rb[2] = wk.cent_pos[(size_t)cb * 3 + 2]; mb = wk.cent_mol[cb]; }
-          double axa[3] = {0, 0, 0}, aya[3] = {0, 0, 0}, axb[3] = {0, 0, 0}, ayb[3] = {0, 0, 0};
-          for (int j0 = 0; j0 < ncent; j0 += POL_TILE) {
-            if (!resident) {
+        // q = p + alpha (T p), qt = pt + T ut for one row, from the accumulated tensor applications
+        auto finish = [&](int c, const double *ax, const double *ay) {
+          double *s_ = stt + (size_t)c * PST;
+          const double *a = wk.cent_alpha + (size_t)c * 9;
+          for (int i = 0; i < 3; ++i) {
+            const double q = s_[12 + i] + a[i * 3] * ax[0] + a[i * 3 + 1] * ax[1] + a[i * 3 + 2] * ax[2];
+            const double qt = s_[15 + i] + ay[i];
+            pq += s_[15 + i] * q;
+            s_[24 + i] = q; s_[27 + i] = qt;
+          }
+        };
+        if (resident) {
+          // Balanced sweep.  Rows are taken in blocks of 64 (two per lane: the tile entry of column j is read from
+          // shared memory once for both rows and the twelve independent accumulation chains keep the FP64 pipe fed
+          // with four warps per scheduler).  The (block, column) index space, nb2 x ncent, is cut into equal
+          // contiguous ranges, one per warp, so the sweep costs ncent^2 / 256 per thread for every ncent instead of
+          // whole passes of 512 rows (403 centres: 0.79 of two passes used; 520 centres: a third pass for 8 rows).
+          // A range that covers a block only partly leaves partial sums in the workspace (head = slot 0, tail =
+          // slot 1); after one barrier they are added in ascending warp order -- deterministic.
+          const int warp = tid >> 5, lane = tid & 31, nwarp = NT >> 5;
+          const int nb2 = (ncent + 63) >> 6;
+          const int W = nb2 * ncent, Q = (W + nwarp - 1) / nwarp;
+          const bool split = (Q % ncent) != 0;
+          const int u1 = min(W, (warp + 1) * Q);
+          for (int u = warp * Q; u < u1;) {
+            const int b = u / ncent, ja = u - b * ncent, jb = min(ncent, ja + (u1 - u));
+            const int ca = (b << 6) + lane, cb = ca + 32;
+            const bool acta = ca < ncent, actb = cb < ncent;
+            const bool anyb = __any_sync(0xffffffffu, actb);
+            double ra[3] = {0, 0, 0}, rb[3] = {0, 0, 0}; int ma = -1, mb = -1;
+            if (acta) { ra[0] = s_tile[ca * 10]; ra[1] = s_tile[ca * 10 + 1]; ra[2] = s_tile[ca * 10 + 2]; ma = s_tmol[ca]; }
+            if (actb) { rb[0] = s_tile[cb * 10]; rb[1] = s_tile[cb * 10 + 1]; rb[2] = s_tile[cb * 10 + 2]; mb = s_tmol[cb]; }
+            double axa[3] = {0, 0, 0}, aya[3] = {0, 0, 0}, axb[3] = {0, 0, 0}, ayb[3] = {0, 0, 0};
+            if (anyb) {
+#pragma unroll 2
+              for (int jj = ja; jj < jb; ++jj) {
+                const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
+                const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
+                const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
+                const int mj = s_tmol[jj];
+                sweep_pair(ra, mj == ma, tt, axa, aya);
+                sweep_pair(rb, mj == mb, tt, axb, ayb);
+              }
+            } else if (acta) {
+#pragma unroll 4
+              for (int jj = ja; jj < jb; ++jj) {
+                const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
+                const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
+                const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
+                sweep_pair(ra, s_tmol[jj] == ma, tt, axa, aya);
+              }
+            }
+            if (ja == 0 && jb == ncent) {                       // the whole block: finish its rows here
+              if (acta) finish(ca, axa, aya);
+              if (actb) finish(cb, axb, ayb);
+            } else {
+              double *pp = wk.part + ((size_t)(warp * 2 + (ja > 0 ? 0 : 1)) * 64 + lane) * 6;
+              for (int d = 0; d < 3; ++d) { pp[d] = axa[d]; pp[3 + d] = aya[d]; pp[192 + d] = axb[d]; pp[195 + d] = ayb[d]; }
+            }
+            u += jb - ja;
+          }
+          if (split) {                                            // CTA-uniform
+            __syncthreads();
+            for (int b = warp; b < nb2; b += nwarp) {
+              const int wf = (b * ncent) / Q, wl = (b * ncent + ncent - 1) / Q;
+              if (wf == wl) continue;                             // one warp had the whole block
+              double axa[3] = {0, 0, 0}, aya[3] = {0, 0, 0}, axb[3] = {0, 0, 0}, ayb[3] = {0, 0, 0};
+              for (int w2 = wf; w2 <= wl; ++w2) {
+                const double *pp = wk.part + ((size_t)(w2 * 2 + (b * ncent < w2 * Q ? 0 : 1)) * 64 + lane) * 6;
+                for (int d = 0; d < 3; ++d) { axa[d] += pp[d]; aya[d] += pp[3 + d]; axb[d] += pp[192 + d]; ayb[d] += pp[195 + d]; }
+              }
+              const int ca = (b << 6) + lane, cb = ca + 32;
+              if (ca < ncent) finish(ca, axa, aya);
+              if (cb < ncent) finish(cb, axb, ayb);
+            }
+          }
+        } else {
+          // more centres than the resident tile holds: one row per thread, columns tile by tile
+          for (int c0 = 0; c0 < ncent; c0 += NT) {
+            const int ca = c0 + tid;
+            const bool acta = ca < ncent;
+            double ra[3] = {0, 0, 0}; int ma = -1;
+            if (acta) { ra[0] = wk.cent_pos[(size_t)ca * 3]; ra[1] = wk.cent_pos[(size_t)ca * 3 + 1]; ra[2] = wk.cent_pos[(size_t)ca * 3 + 2]; ma = wk.cent_mol[ca]; }
+            double axa[3] = {0, 0, 0}, aya[3] = {0, 0, 0};
+            for (int j0 = 0; j0 < ncent; j0 += POL_TILE) {
               __syncthreads();
               for (int tl = tid; tl < POL_TILE; tl += NT) {
                 const int j = j0 + tl;
@@ -290,41 +364,19 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
                 } else s_tmol[tl] = -2;
               }
               __syncthreads();
-            }
-            const int jn = min(POL_TILE, ncent - j0);
-            if (anyb) {
+              const int jn = min(POL_TILE, ncent - j0);
+              if (acta) {
 #pragma unroll 2
-              for (int jj = 0; jj < jn; ++jj) {
-                const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
-                const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
-                const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
-                const int mj = s_tmol[jj];
-                sweep_pair(ra, mj == ma, tt, axa, aya);
-                sweep_pair(rb, mj == mb, tt, axb, ayb);
-              }
-            } else if (acta) {
-#pragma unroll 4
-              for (int jj = 0; jj < jn; ++jj) {
-                const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
-                const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
-                const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
-                sweep_pair(ra, s_tmol[jj] == ma, tt, axa, aya);
+                for (int jj = 0; jj < jn; ++jj) {
+                  const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
+                  const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
+                  const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
+                  sweep_pair(ra, s_tmol[jj] == ma, tt, axa, aya);
+                }
               }
             }
+            if (acta) finish(ca, axa, aya);
           }
-          // q = p + alpha (T p), qt = pt + T ut
-          auto finish = [&](int c, const double *ax, const double *ay) {
-            double *s_ = stt + (size_t)c * PST;
-            const double *a = wk.cent_alpha + (size_t)c * 9;
-            for (int i = 0; i < 3; ++i) {
-              const double q = s_[12 + i] + a[i * 3] * ax[0] + a[i * 3 + 1] * ax[1] + a[i * 3 + 2] * ax[2];
-              const double qt = s_[15 + i] + ay[i];
-              pq += s_[15 + i] * q;
-              s_[24 + i] = q; s_[27 + i] = qt;
-            }
-          };
-          if (acta) finish(ca, axa, aya);
-          if (actb) finish(cb, axb, ayb);
         }
         pq = block_sum(pq, s_red);
         ++iters;

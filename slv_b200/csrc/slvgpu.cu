@@ -228,6 +228,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
     TRY(dalloc(pl, &pl->pw.xy, nc * cc * (PST + 6)));
     TRY(dalloc(pl, &pl->pw.site, nc * (size_t)p.site_cap * SITE_ROW));
     TRY(dalloc(pl, &pl->pw.aux, nc * cc * 6));
+    TRY(dalloc(pl, &pl->pw.part, nc * (size_t)(POL_THREADS / 32) * 2 * 64 * 6));
     TRY(dalloc(pl, &pl->pw.cent_mol, nc * cc));
     TRY(dalloc(pl, &pl->pw.ent_coff, nc * (size_t)p.list_cap));
     TRY(dalloc(pl, &pl->pw.ent_soff, nc * (size_t)p.list_cap));

@@ -413,7 +413,7 @@ def test_full_size_batch_properties(frags):
 
 
 def test_large_polarisation_system_multi_tile(frags):
-    """No pcut: 230 waters -> 1170 polarisable centres (NDIM 3510), more than one 512-centre tile per sweep and more
+    """No pcut: 230 waters -> 1170 polarisable centres (NDIM 3510), more than the 1024-centre resident sweep tile (tiled fallback) and more
     than one centre per thread; polarisation and dispersion against the dense LU oracle."""
     from slv_b200 import synth
     from oracle import solefp_oracle as O
