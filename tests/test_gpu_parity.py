@@ -412,13 +412,14 @@ def test_full_size_batch_properties(frags):
         assert abs(s[k][0] - ref[k] * c) < TOL, (k, s[k][0], ref[k] * c)         # (5)
 
 
-def test_large_polarisation_system_multi_tile(frags):
-    """No pcut: 230 waters -> 1170 polarisable centres (NDIM 3510), more than the 1024-centre resident sweep tile (tiled fallback) and more
-    than one centre per thread; polarisation and dispersion against the dense LU oracle."""
+@pytest.mark.parametrize('nw', [77, 130, 230])
+def test_large_polarisation_system_multi_tile(frags, nw):
+    """No pcut, polarisation and dispersion against the dense LU oracle: 77 waters -> 405 centres (7 row blocks cut
+    into 8 uneven warp ranges of the balanced sweep), 130 -> 670 (more row blocks than warps: ranges span blocks, head
+    and tail partial sums), 230 -> 1170 (NDIM 3510: more than the 1024-centre resident tile, tiled fallback)."""
     from slv_b200 import synth
     from oracle import solefp_oracle as O
     sol, wat = frags('nma'), frags('water')
-    nw = 230
     X = synth.make_trajectory(sol.get_pos(), [wat.get_pos()], np.zeros(nw, int), 1, seed=61)
     ind = [0] + [1] * nw; nmol = [12] + [3] * nw
     efp = _efp(ccut=1e10, pcut=1e10, ecut=8.0)
