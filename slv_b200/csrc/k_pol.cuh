@@ -254,17 +254,17 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       }
     }
     if (bnorm > 0.0) {
-      for (; iters < p.pol_maxit;) {
-        // u = p, ut = alpha^T pt
-        for (int c = tid; c < ncent; c += NT) {
-          double *s_ = stt + (size_t)c * PST;
-          const double *a = wk.cent_alpha + (size_t)c * 9;
-          double *dst = resident ? s_tile + c * 10 + 3 : s_ + 18;
-          for (int i = 0; i < 3; ++i) {
-            dst[i] = s_[12 + i];
-            dst[3 + i] = a[i] * s_[15] + a[3 + i] * s_[16] + a[6 + i] * s_[17];
-          }
+      // sweep operands of the first iteration: u = p, ut = alpha^T pt (later iterations write them where p, pt are updated)
+      for (int c = tid; c < ncent; c += NT) {
+        double *s_ = stt + (size_t)c * PST;
+        const double *a = wk.cent_alpha + (size_t)c * 9;
+        double *dst = resident ? s_tile + c * 10 + 3 : s_ + 18;
+        for (int i = 0; i < 3; ++i) {
+          dst[i] = s_[12 + i];
+          dst[3 + i] = a[i] * s_[15] + a[3 + i] * s_[16] + a[6 + i] * s_[17];
         }
+      }
+      for (; iters < p.pol_maxit;) {
         if (resident) __syncthreads();
         double pq = 0.0;
         // q = p + alpha (T p), qt = pt + T ut for one row, from the accumulated tensor applications
@@ -399,9 +399,19 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
         if (!(fabs(rho) > 0.0) || !isfinite(rho1)) { broke = true; break; }
         const double be = rho1 / rho;
         rho = rho1;
-        for (int c = tid; c < ncent; c += NT) {
+        for (int c = tid; c < ncent; c += NT) {                 // new search directions, and the next sweep's operands
           double *s_ = stt + (size_t)c * PST;
-          for (int i = 0; i < 3; ++i) { s_[12 + i] = s_[6 + i] + be * s_[12 + i]; s_[15 + i] = s_[9 + i] + be * s_[15 + i]; }
+          const double *a = wk.cent_alpha + (size_t)c * 9;
+          double *dst = resident ? s_tile + c * 10 + 3 : s_ + 18;
+          double pn[3], ptn[3];
+          for (int i = 0; i < 3; ++i) {
+            pn[i] = s_[6 + i] + be * s_[12 + i]; ptn[i] = s_[9 + i] + be * s_[15 + i];
+            s_[12 + i] = pn[i]; s_[15 + i] = ptn[i];
+          }
+          for (int i = 0; i < 3; ++i) {
+            dst[i] = pn[i];
+            dst[3 + i] = a[i] * ptn[0] + a[3 + i] * ptn[1] + a[6 + i] * ptn[2];
+          }
         }
       }
     } else resid = 0.0;
