@@ -182,7 +182,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     // ---- (b) fields at every centre from the multipoles of all OTHER molecules (FFFFFF); sites staged
     //      through shared memory in tiles, own-molecule sites masked branch-free
     {
-      constexpr int FT = 128;                               // sites per tile (FT * SITE_ROW doubles <= POL_TILE * 10)
+      constexpr int FT = POL_TILE * 10 / SITE_ROW;          // sites per tile: the sweep tile's shared memory, 426 sites
       for (int c0 = 0; c0 < ncent; c0 += NT) {
         const int c = c0 + tid;
         const bool act = c < ncent;
@@ -242,7 +242,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       bnorm = block_max(pb, s_red);
     }
     bool broke = false;
-    // When all centres fit one tile (the usual case: <= 512 inside pcut) the tile stays resident in shared memory for
+    // When all centres fit one tile (the usual case: <= 1024 inside pcut) the tile stays resident in shared memory for
     // the whole solve: positions and molecule ids are staged once, and every iteration the owners write their search
     // directions straight into it -- no per-iteration round trip through the L2 workspace, one barrier per sweep.
     const bool resident = ncent <= POL_TILE;
