@@ -182,6 +182,14 @@ int slvgpu_rotate_vecl(double *h_vec, int64_t nrows, int32_t nbasis, const int32
  * slvgpu_expres: classical line-shape function of util/slv_calc-expres:73-101: re/im [ndel+1]. */
 int slvgpu_tcf(const double *h_a, const double *h_b, int64_t n, int64_t k, int32_t demean, double *h_tcf);
 int slvgpu_expres(const double *h_f, int64_t n, double dt, int64_t ndel, double *h_re, double *h_im);
+/* out[i] = trapezoid integral over y of f(y) cos(x_i y) (kind 0) or f(y) sin(x_i y) (kind 1) on the uniform grid
+ * y_j = y0 + j dy, j < n, for m abscissae x_i: the frequency and time integrals of util/slv_calc-ftir (spectral
+ * density :223-226, line-broadening functions :252-259, classical line shape :399-407). */
+int slvgpu_trig_transform(const double *h_f, int64_t n, double y0, double dy, const double *h_x, int64_t m,
+                          int32_t kind, double *h_out);
+/* counts of h_x in `bins` (<= 8192) equal-width bins over [lo, hi], last bin closed, as numpy / pylab.hist do for
+ * util/slv_hist:60-61. */
+int slvgpu_hist(const double *h_x, int64_t n, double lo, double hi, int32_t bins, int64_t *h_counts);
 
 const char *slvgpu_last_error(void);
 const char *slvgpu_version(void);

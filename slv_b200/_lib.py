@@ -55,6 +55,8 @@ def _load():
     lib.slvgpu_rotate_vecl.argtypes = [vp, i64, i32, vp, vp]
     lib.slvgpu_tcf.argtypes = [vp, vp, i64, i64, i32, vp]
     lib.slvgpu_expres.argtypes = [vp, i64, dbl, i64, vp, vp]
+    lib.slvgpu_trig_transform.argtypes = [vp, i64, dbl, dbl, vp, i64, i32, vp]
+    lib.slvgpu_hist.argtypes = [vp, i64, dbl, dbl, i32, vp]
     lib.slvgpu_last_error.restype = ctypes.c_char_p
     lib.slvgpu_version.restype = ctypes.c_char_p
     return lib

@@ -2,7 +2,9 @@
 //   k_tcf    time-correlation function  TCF(i) = 1/(N-i) sum_j A(j) B(j+i)          (util/lib/genres.f:1-23 GTCF;
 //            util/slv_calc-tcf:17-28 `cf` is the same sum on mean-subtracted series)
 //   k_expres classical line-shape function Jc(t_i) = < exp(-i int_0^{t_i} dw) >       (util/slv_calc-expres:73-101)
-// Both are O(N x delays) streaming sums over an L2-resident series.
+//   k_trig_transform  cosine / sine trapezoid transforms of util/slv_calc-ftir (spectral density, line shape)
+//   k_hist   histogram of a shift series (util/slv_hist)
+// All are streaming sums over an L2-resident series.
 #pragma once
 #include "slv_common.cuh"
 
@@ -89,6 +91,45 @@ k_expres(const double *__restrict__ C, long long n, long long ndel, double *__re
   }
   sc = block_sum(sc, s_red); ss = block_sum(ss, s_red);
   if (threadIdx.x == 0) { re[i] = sc / (double)(n - i); im[i] = -ss / (double)(n - i); }
+}
+
+// out[i] = trapezoid integral over y of f(y) trig(x_i y) on the uniform grid y_j = y0 + j dy, j < n; trig = cos (kind 0)
+// or sin (kind 1).  This is every frequency/time integral of util/slv_calc-ftir: the spectral density
+// (:223-226), the line-broadening functions (:252-259) and the classical line shape (:399-407).  One CTA per x_i.
+__global__ void __launch_bounds__(SPEC_THREADS)
+k_trig_transform(const double *__restrict__ f, long long n, double y0, double dy, const double *__restrict__ x, int kind,
+                 double *__restrict__ out) {
+  __shared__ double s_red[32];
+  const double xi = x[blockIdx.x];
+  double acc = 0.0;
+  for (long long j = threadIdx.x; j < n; j += blockDim.x) {
+    const double w = (j == 0 || j == n - 1) ? 0.5 : 1.0;
+    const double a = xi * (y0 + (double)j * dy);
+    acc = fma(w * f[j], kind ? sin(a) : cos(a), acc);
+  }
+  acc = block_sum(acc, s_red);
+  if (threadIdx.x == 0) out[blockIdx.x] = acc * dy;
+}
+
+// counts of x in `bins` equal-width bins over [lo, hi] with numpy.histogram's edge rule (the last bin is closed);
+// per-CTA shared-memory histograms merged with integer atomics (exact, order-independent)
+__global__ void __launch_bounds__(SPEC_THREADS)
+k_hist(const double *__restrict__ x, long long n, double lo, double hi, int bins, unsigned long long *__restrict__ counts) {
+  extern __shared__ unsigned int s_h[];
+  for (int b = threadIdx.x; b < bins; b += blockDim.x) s_h[b] = 0u;
+  __syncthreads();
+  const double sc = (double)bins / (hi - lo);
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    const double v = x[j];
+    if (v >= lo && v <= hi) {
+      int b = (int)((v - lo) * sc);
+      if (b >= bins) b = bins - 1;
+      atomicAdd(&s_h[b], 1u);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < bins; b += blockDim.x)
+    if (s_h[b]) atomicAdd(&counts[b], (unsigned long long)s_h[b]);
 }
 
 }  // namespace slv

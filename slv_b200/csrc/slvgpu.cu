@@ -588,3 +588,39 @@ extern "C" int slvgpu_expres(const double *h_f, int64_t n, double dt, int64_t nd
   if (e != cudaSuccess) return fail(SLVGPU_ECUDA, cudaGetErrorString(e));
   return 0;
 }
+
+extern "C" int slvgpu_trig_transform(const double *h_f, int64_t n, double y0, double dy, const double *h_x, int64_t m,
+                                     int32_t kind, double *h_out) {
+  if (!h_f || !h_x || !h_out || n < 2 || m < 1 || (kind != 0 && kind != 1)) return fail(SLVGPU_EINVAL, "bad argument");
+  double *d = nullptr;
+  CK(cudaMalloc(&d, (size_t)(n + 2 * m) * sizeof(double)));
+  double *df = d, *dx = d + n, *dout = dx + m;
+  cudaError_t e = cudaMemcpy(df, h_f, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dx, h_x, (size_t)m * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_trig_transform<<<(unsigned)m, SPEC_THREADS>>>(df, n, y0, dy, dx, kind, dout);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(h_out, dout, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(SLVGPU_ECUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int slvgpu_hist(const double *h_x, int64_t n, double lo, double hi, int32_t bins, int64_t *h_counts) {
+  if (!h_x || !h_counts || n < 1 || bins < 1 || bins > 8192 || !(hi > lo)) return fail(SLVGPU_EINVAL, "bad argument");
+  double *dx = nullptr; unsigned long long *dc = nullptr;
+  CK(cudaMalloc(&dx, (size_t)n * sizeof(double)));
+  cudaError_t e = cudaMalloc(&dc, (size_t)bins * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(dc, 0, (size_t)bins * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemcpy(dx, h_x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const int64_t nb = (n + SPEC_THREADS - 1) / SPEC_THREADS;
+    k_hist<<<(unsigned)(nb < 592 ? nb : 592), SPEC_THREADS, (size_t)bins * sizeof(unsigned int)>>>(dx, n, lo, hi, bins, dc);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(h_counts, dc, (size_t)bins * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(dx); if (dc) cudaFree(dc);
+  if (e != cudaSuccess) return fail(SLVGPU_ECUDA, cudaGetErrorString(e));
+  return 0;
+}
