@@ -44,7 +44,7 @@ WORKLOADS = {
 FLOPS_PER_T_PAIR = 49.0      # one (centre, centre) dipole-tensor apply to two vectors: R 3, r^2 5, rsqrt 1, powers 4,
                              # two dots 10, two scalings 2, six accumulations x 4 (DESIGN.md "k_pol")
 FLOPS_PER_FIELD_PAIR = 123.0  # one (centre, site) multipole field through octupoles (slv::site_field_acc, counted)
-POL_DRAM_BYTES_PER_FRAME = (102.993920e6 + 392.649728e6) / 1184.0   # ncu capture of k_pol, profiles/k_pol_r01g_ncu.txt
+POL_DRAM_BYTES_PER_FRAME = (86.834688e6 + 346.631424e6) / 1184.0   # ncu capture of k_pol, profiles/k_pol_r01h_ncu.txt
 SWEEP_BODY_TFLOPS = 20.5     # algorithmic TFLOP/s of the k_pol sweep loop run alone (profiles/sweep_peak_r01.json, two rows/thread)
 FLOPS_PER_ELECT_PAIR = 300.0  # one (solute site, solvent site) pair through R^-4 with two moment sets + corrections
 
@@ -264,7 +264,7 @@ def main():
                      d2h_bytes_per_step=int(nf * (_lib.NOUT * 8 + 4))),
             roofline=dict(bound='fp64', kernel='k_pol', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
                           traffic=(POL_DRAM_BYTES_PER_FRAME * nf if a.config == 2 else None), traffic_source='ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_pol on 1184 '
-                          'frames of this workload (profiles/k_pol_r01g_ncu.txt), scaled per frame to this launch',
+                          'frames of this workload (profiles/k_pol_r01h_ncu.txt), scaled per frame to this launch',
                           ceiling=dict(achieved_by='tools/sweep_peak.cu: the sweep body alone (no solver phases) at the kernel launch shape',
                                        alg_tflops=SWEEP_BODY_TFLOPS, frac_of_ceiling=achieved / SWEEP_BODY_TFLOPS),
                           peak_source='tools/fp64_peak.cu DFMA micro-benchmark on this pool (profiles/fp64_peak_r01.json); '
