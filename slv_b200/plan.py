@@ -56,6 +56,21 @@ SUBSHELL_CLASSES = ([(la, 0, -1) for la in range(3)]
                     + [(la, lb, ia) for lb in (1, 2) for la in range(3) for ia in range((1, 3, 6)[la])])
 
 
+def subshell_work_list(sA, sB):
+    """Work list of the exchange-repulsion integral kernels for solute sub-shells sA against fragment sub-shells sB
+    (rows: atom, first function, L, primitives): class offsets [len(SUBSHELL_CLASSES) + 1] and the items
+    a * len(sB) + b, class by class, heaviest primitive-pair count first.  Every AO pair of the two fragments is
+    produced by exactly one (class, item)."""
+    cost = (sA[:, 3][:, None] * sB[:, 3][None, :])
+    items, offs = [], [0]
+    for LA, LB, IA in SUBSHELL_CLASSES:
+        a, b = numpy.nonzero((sA[:, 2] == LA)[:, None] & (sB[:, 2] == LB)[None, :])
+        o = numpy.argsort(-cost[a, b], kind='stable')
+        items.append((a[o] * len(sB) + b[o]).astype(numpy.int32))
+        offs.append(offs[-1] + len(o))
+    return numpy.array(offs, numpy.int32), numpy.concatenate(items).astype(numpy.int32)
+
+
 class Plan(object):
     """Device-resident evaluation plan (owns the slvgpu_plan handle)."""
 
@@ -119,15 +134,8 @@ class Plan(object):
         if need_rep and int(ind[0]) in self._bfs:
             sA = self._bfs[int(ind[0])].subshells
             for t, bB in self._bfs.items():
-                sB = bB.subshells
-                cost = (sA[:, 3][:, None] * sB[:, 3][None, :])
-                items, offs = [], [0]
-                for LA, LB, IA in SUBSHELL_CLASSES:
-                    a, b = numpy.nonzero((sA[:, 2] == LA)[:, None] & (sB[:, 2] == LB)[None, :])
-                    o = numpy.argsort(-cost[a, b], kind='stable')
-                    items.append((a[o] * len(sB) + b[o]).astype(numpy.int32))
-                    offs.append(offs[-1] + len(o))
-                meta[t][M['IO_SHPAIR']] = it.add(numpy.concatenate([numpy.array(offs, numpy.int32)] + items))
+                offs, items = subshell_work_list(sA, bB.subshells)
+                meta[t][M['IO_SHPAIR']] = it.add(numpy.concatenate([offs, items]))
         # ---- solute: mode-contracted tables
         sol = numpy.full(_lib.NSOL, -1, numpy.int32)
         S = _lib.S

@@ -92,3 +92,34 @@ def test_shift_dictionary_assembly():
     assert abs(s['total'][0] - (s['ele_tot'][0] + s['pol_mea'][0] + s['rep_mea'][0] + s['dis_mea'][0])) < 1e-9
     assert abs(s['total_ele'][0] - (s['total'][0] - s['rep_mea'][0])) < 1e-9 and s['pol_ea'][0] == 0.0
     assert abs(s['solcamm'][0] - 3e-5 * c) < 1e-9 and abs(s['dis_mea_iso'][0] - 8e-5 * c) < 1e-9
+
+
+def test_exchange_repulsion_work_list_covers_every_ao_pair_once(frags):
+    """slv_b200/plan.py subshell_work_list: the 23 (L_bra, L_ket, bra component) classes tile the AO-pair matrix of
+    two fragments exactly once, items are sorted by primitive-pair count inside a class, and the sub-shells rebuild the
+    basis (an SP shell is an S and a P sub-shell with the same exponents)."""
+    import numpy as np
+    from slv_b200.basis import BasisSet
+    from slv_b200.plan import subshell_work_list, SUBSHELL_CLASSES
+    pa, pb = frags('mescn').get(), frags('dmso').get()
+    bA, bB = BasisSet(pa['atno'], pa['pos']), BasisSet(pb['atno'], pb['pos'])
+    for b in (bA, bB):
+        ncomp = np.array([1, 3, 6])[b.subshells[:, 2]]
+        assert ncomp.sum() == len(b) and (b.powers.sum(1)[b.subshells[:, 1]] == b.subshells[:, 2]).all()
+        assert (b.nprim[b.subshells[:, 1]] == b.subshells[:, 3]).all()
+    offs, items = subshell_work_list(bA.subshells, bB.subshells)
+    assert len(offs) == len(SUBSHELL_CLASSES) + 1 and offs[-1] == len(items)
+    hits = np.zeros((len(bA), len(bB)), int)
+    for cid, (LA, LB, IA) in enumerate(SUBSHELL_CLASSES):
+        cost_prev = None
+        for w in items[offs[cid]:offs[cid + 1]]:
+            a, b = divmod(int(w), len(bB.subshells))
+            sa, sb = bA.subshells[a], bB.subshells[b]
+            assert sa[2] == LA and sb[2] == LB
+            rows = range(sa[1], sa[1] + (1, 3, 6)[LA]) if IA < 0 else [sa[1] + IA]
+            for k in rows:
+                hits[k, sb[1]:sb[1] + (1, 3, 6)[LB]] += 1
+            cost = sa[3] * sb[3]
+            assert cost_prev is None or cost <= cost_prev
+            cost_prev = cost
+    assert (hits == 1).all()
