@@ -47,8 +47,12 @@ struct RepPool {            // one batch of (frame, fragment) pairs (V .. pair_t
 };
 
 // Two pools (the batches alternate between two streams, so the integral kernels of one batch overlap the
-// latency-bound transform kernel of the previous one); the per-frame tables are shared.
-inline int rep_alloc(RepPool rp[2], std::vector<void *> &allocs, std::string &err, int nmosc, int nbasc,
+// latency-bound transform kernel of the previous one); the per-frame tables are shared.  rep_alloc creates the
+// per-frame tables and fixes the largest pool the plan may use; the pools themselves grow on demand (rep_reserve),
+// so a plan that only ever sees a few fragments inside ecut does not hold gigabytes.
+struct RepLimits { size_t max_pairs = 0; };
+
+inline int rep_alloc(RepPool rp[2], RepLimits &lim, std::vector<void *> &allocs, std::string &err, int nmosc, int nbasc,
                      int natc, int max_nbas, int max_nat, int max_chunk, int list_cap) {
   // integral pools: together up to 8 GiB and at most a quarter of the free memory, never more than the worst case
   const size_t sV = (size_t)nbasc * max_nbas * 4;
@@ -64,27 +68,45 @@ inline int rep_alloc(RepPool rp[2], std::vector<void *> &allocs, std::string &er
     if (v > 0 && (size_t)v < cap) cap = (size_t)v;
   }
   if (cap < 1) cap = 1;
+  if (cap > 0x3fffffff) cap = 0x3fffffff;
+  lim.max_pairs = cap;
   void *q = nullptr;
 #define RA(ptr, n, T)                                                                                                   \
-  if (cudaMalloc(&q, (size_t)(n) * sizeof(T)) != cudaSuccess) { err = "cudaMalloc(rep integral pool) failed"; return SLVGPU_ENOMEM; } \
+  if (cudaMalloc(&q, (size_t)(n) * sizeof(T)) != cudaSuccess) { err = "cudaMalloc(rep tables) failed"; return SLVGPU_ENOMEM; } \
   allocs.push_back(q); ptr = (T *)q;
   RA(rp[0].posA, (size_t)max_chunk * natc * 3, double)
   RA(rp[0].LcA, (size_t)max_chunk * natc * 3, double)
   RA(rp[0].riA, (size_t)max_chunk * nmosc * 6, double)
   RA(rp[0].CA, (size_t)max_chunk * 2 * nmosc * nbasc, double)
   RA(rp[0].pair0, (size_t)max_chunk + 1, int)
-  rp[1] = rp[0];
-  for (int h = 0; h < 2; ++h) {
-    rp[h].sV = sV; rp[h].max_nat = max_nat;
-    rp[h].pair_cap = (int)(cap > 0x3fffffff ? 0x3fffffff : cap);
-    RA(rp[h].V, (size_t)rp[h].pair_cap * sV, double)
-    RA(rp[h].posB, (size_t)rp[h].pair_cap * max_nat * 3, double)
-    RA(rp[h].res, rp[h].pair_cap, double)
-    RA(rp[h].pair_frame, rp[h].pair_cap, int)
-    RA(rp[h].pair_entry, rp[h].pair_cap, int)
-    RA(rp[h].pair_type, rp[h].pair_cap, int)
-  }
 #undef RA
+  rp[1] = rp[0];
+  for (int h = 0; h < 2; ++h) { rp[h].sV = sV; rp[h].max_nat = max_nat; rp[h].pair_cap = 0; rp[h].V = nullptr; }
+  return 0;
+}
+
+inline void rep_pool_free(RepPool &r) {
+  if (r.pair_cap <= 0) return;
+  cudaFree(r.V); cudaFree(r.posB); cudaFree(r.res); cudaFree(r.pair_frame); cudaFree(r.pair_entry); cudaFree(r.pair_type);
+  r.V = nullptr; r.pair_cap = 0;
+}
+
+// make both pools hold at least `pairs` pairs (clamped to the plan's limit); the caller has synchronised the streams
+inline int rep_reserve(RepPool rp[2], const RepLimits &lim, size_t pairs, std::string &err) {
+  if (pairs > lim.max_pairs) pairs = lim.max_pairs;
+  if (pairs < 64) pairs = lim.max_pairs < 64 ? lim.max_pairs : 64;
+  if ((size_t)rp[0].pair_cap >= pairs) return 0;
+  for (int h = 0; h < 2; ++h) {
+    rep_pool_free(rp[h]);
+    bool ok = cudaMalloc(&rp[h].V, pairs * rp[h].sV * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&rp[h].posB, pairs * rp[h].max_nat * 3 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&rp[h].res, pairs * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&rp[h].pair_frame, pairs * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&rp[h].pair_entry, pairs * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&rp[h].pair_type, pairs * sizeof(int)) == cudaSuccess;
+    if (!ok) { err = "cudaMalloc(rep integral pool) failed"; return SLVGPU_ENOMEM; }
+    rp[h].pair_cap = (int)pairs;
+  }
   return 0;
 }
 

@@ -36,6 +36,7 @@ struct slvgpu_plan {
   FrameLists fl{};
   PolWork pw{};
   RepPool rp[2] = {};
+  RepLimits rep_lim;
   cudaStream_t rep_stream = nullptr; cudaEvent_t rep_ev[2] = {nullptr, nullptr};
   std::vector<int> rep_types;                 // fragment types that carry the wave-function tables
   std::vector<std::vector<int>> rep_cls;      // per such type: the 24 class offsets of its integral work list
@@ -116,6 +117,7 @@ extern "C" void slvgpu_plan_destroy(slvgpu_plan *pl) {
   if (!pl) return;
   for (cudaEvent_t e : pl->ev_pool) cudaEventDestroy(e);
   for (void *q : pl->allocs) cudaFree(q);
+  for (int b = 0; b < 2; ++b) rep_pool_free(pl->rp[b]);
   for (int b = 0; b < 2; ++b) if (pl->d_stage_coords2[b]) cudaFree(pl->d_stage_coords2[b]);
   if (pl->d_stage_out) cudaFree(pl->d_stage_out);
   if (pl->d_stage_status) cudaFree(pl->d_stage_status);
@@ -242,7 +244,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
       slvgpu_plan_destroy(pl);
       return fail(SLVGPU_EINVAL, "exchange-repulsion needs the wave-function tables (vecl, fock, basis) in the plan");
     }
-    TRY(rep_alloc(pl->rp, pl->allocs, g_err, pl->nmosc, pl->nbasc, pl->natc, pl->max_nbas, pl->max_nat, pl->max_chunk, p.list_cap));
+    TRY(rep_alloc(pl->rp, pl->rep_lim, pl->allocs, g_err, pl->nmosc, pl->nbasc, pl->natc, pl->max_nbas, pl->max_nat, pl->max_chunk, p.list_cap));
     for (int t = 0; t < d->ntypes; ++t) {
       const int32_t *tm = d->type_meta + (size_t)t * SLVGPU_NMETA;
       if (tm[SLVGPU_M_IO_SHPAIR] < 0 || !solvent_type[t]) continue;
@@ -317,6 +319,18 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
         for (int b = 0; b < 2; ++b) CK(cudaEventCreateWithFlags(&pl->rep_ev[b], cudaEventDisableTiming));
       }
       const int *pair0 = pl->h_pair0.data();
+      {
+        // pools sized for two concurrent batches covering the chunk, and for the largest single frame
+        int fmax = 0;
+        for (int f = 0; f < nf; ++f) fmax = pair0[f + 1] - pair0[f] > fmax ? pair0[f + 1] - pair0[f] : fmax;
+        size_t need = ((size_t)pair0[nf] + 1) / 2;
+        if (need < (size_t)fmax) need = (size_t)fmax;
+        if (need > (size_t)pl->rp[0].pair_cap && (size_t)pl->rp[0].pair_cap < pl->rep_lim.max_pairs) {
+          CK(cudaStreamSynchronize(pl->rep_stream));
+          const int rc = rep_reserve(pl->rp, pl->rep_lim, need, g_err);
+          if (rc) return rc;
+        }
+      }
       const size_t sm_re = rep_smem_bytes(pl->nmosc, pl->nbasc, pl->max_nmos, pl->max_nbas, pl->natc, pl->max_nat);
       int batch = 0;
       for (int fs = 0; fs < nf; ++batch) {
