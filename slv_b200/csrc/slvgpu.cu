@@ -328,7 +328,7 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
         if (need > (size_t)pl->rp[0].pair_cap && (size_t)pl->rp[0].pair_cap < pl->rep_lim.max_pairs) {
           CK(cudaStreamSynchronize(pl->rep_stream));
           const int rc = rep_reserve(pl->rp, pl->rep_lim, need, g_err);
-          if (rc) return rc;
+          if (rc) { ev_end(pl, st); return rc; }
         }
       }
       const size_t sm_re = rep_smem_bytes(pl->nmosc, pl->nbasc, pl->max_nmos, pl->max_nbas, pl->natc, pl->max_nat);
@@ -340,6 +340,7 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
         while (fe < nf && pair0[fe + 1] - pair0[fs] <= rp.pair_cap) ++fe;
         if (fe == fs) {
           cudaStreamSynchronize(pl->rep_stream);
+          ev_end(pl, st);
           return fail(SLVGPU_ENOMEM, "exchange repulsion: one frame has more fragments inside ecut than the integral pool holds");
         }
         const int nb = fe - fs, npairs = pair0[fe] - pair0[fs];
