@@ -412,6 +412,46 @@ def test_full_size_batch_properties(frags):
         assert abs(s[k][0] - ref[k] * c) < TOL, (k, s[k][0], ref[k] * c)         # (5)
 
 
+def test_full_solefp_batch_properties(frags):
+    """BASELINE config 3 shape (MeSCN in 50/50 water/DMSO, 400 fragments, all four terms) on 3000 frames: the rows are
+    a pure function of the frame -- a permutation of the frames permutes them bit for bit, chunking (which also moves
+    the exchange-repulsion batch boundaries and which stream / pool a pair lands in) changes nothing, host and device
+    entries agree -- and the frames that are copies of an oracle-checked one reproduce it in every term."""
+    import torch
+    from slv_b200 import synth
+    from slv_b200.basis import BasisSet
+    from oracle import solefp_oracle as O
+    sol, wat, dmso = frags('mescn'), frags('water'), frags('dmso')
+    nw, nu, nf = 400, 12, 3000
+    types = np.random.default_rng(3).integers(0, 2, nw)
+    U = synth.make_trajectory(sol.get_pos(), [wat.get_pos(), dmso.get_pos()], types, nu, seed=4, spacing=9.5, jit_lattice=0.3)
+    pick = np.random.default_rng(1).integers(0, nu, nf)
+    X = U[pick]
+    ind = [0] + [1 + int(t) for t in types]; nmol = [7] + [3 if t == 0 else 10 for t in types]
+    bsm = [sol, wat, dmso]
+    kw = dict(mode=4, rep=True, ccut=40.0, pcut=17.0, ecut=12.0)
+    efp = _efp(**kw)
+    d = torch.from_numpy(X).cuda()
+    rows, status = efp.eval_frames(d, ind, nmol, bsm, [None] * 3, [None] * 3)
+    rows = rows.cpu().numpy()
+    assert int(status.max()) == 0 and np.isfinite(rows).all() and rows[:, 13].min() >= 1
+    ru, _ = efp.eval_frames(torch.from_numpy(U).cuda())
+    ru = ru.cpu().numpy()
+    assert np.array_equal(rows[:, :8], ru[pick][:, :8])
+    efp2 = _efp(**kw); efp2.max_chunk = 333
+    r2, _ = efp2.eval_frames(d, ind, nmol, bsm, [None] * 3, [None] * 3)
+    assert np.array_equal(r2.cpu().numpy()[:, :8], rows[:, :8])
+    rh, sh = efp2.eval_frames(X)
+    assert np.array_equal(rh[:, :8], rows[:, :8]) and int(sh.max()) == 0
+    c = O.HartreePerHbarToCmRec
+    ref = O.eval_frame(U[0], ind, nmol, [b.get() for b in bsm], [None] * 3, [None] * 3, 4, 40.0, 17.0, 12.0,
+                       elect=True, ea=True, corr=True, pol=True, disp=True, rep=True, make_basis=lambda a, p: BasisSet(a, p))
+    s = efp.shifts_of(ru[:1])
+    for k in TERMS + ('rep_mea',):
+        assert abs(s[k][0] - ref[k] * c) < TOL * max(1.0, abs(ref[k] * c) * 1e-3), (k, s[k][0], ref[k] * c)
+    assert ru[0, 13] == ref['n_rep']
+
+
 @pytest.mark.parametrize('nw', [77, 130, 230])
 def test_large_polarisation_system_multi_tile(frags, nw):
     """No pcut, polarisation and dispersion against the dense LU oracle: 77 waters -> 405 centres (7 row blocks cut
