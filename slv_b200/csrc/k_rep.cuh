@@ -110,13 +110,11 @@ inline int rep_reserve(RepPool rp[2], const RepLimits &lim, size_t pairs, std::s
   return 0;
 }
 
-// LMOs of the fragment per pass of k_rep_pair: one or two 5-wide register blocks
-inline int rep_jt(int max_nmos) { return max_nmos <= 5 ? 5 : 10; }
-
-// shared memory of k_rep_pair: X[nbsA][4][JT] + CB[JT][max_nbas] + IJ[4][nmosA][max_nmos] + geometry
+// shared memory of k_rep_pair: X tile [<= REP_THREADS rows x 5 LMOs][4] + CB[max_nmos][max_nbas] + IJ[4][nmosA][max_nmos]
+// + geometry
 inline size_t rep_smem_bytes(int nmosc, int nbasc, int max_nmos, int max_nbas, int natc, int max_nat) {
-  const int REP_JT = rep_jt(max_nmos);
-  return sizeof(double) * ((size_t)nbasc * 4 * REP_JT + (size_t)REP_JT * max_nbas + (size_t)4 * nmosc * max_nmos
+  (void)nbasc;
+  return sizeof(double) * ((size_t)REP_THREADS * 4 * 5 + 32 + (size_t)max_nmos * max_nbas + (size_t)4 * nmosc * max_nmos
                            + 6 * natc + 6 * nmosc + 3 * max_nat + 3 * max_nmos + 8);
 }
 
@@ -247,7 +245,7 @@ k_rep_ints(const DevPlan p, int type, int lo, int n_items, int npairs, RepPool r
 #define SLV_REP_PAIR_CTAS 4
 #endif
 __global__ void __launch_bounds__(REP_THREADS, SLV_REP_PAIR_CTAS)
-k_rep_pair(const DevPlan p, FrameLists fl, RepPool rp, const int REP_JT) {
+k_rep_pair(const DevPlan p, FrameLists fl, RepPool rp) {
   extern __shared__ double sm[];
   __shared__ double s_red[32];
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -257,7 +255,7 @@ k_rep_pair(const DevPlan p, FrameLists fl, RepPool rp, const int REP_JT) {
   const int natA = tm0[SLVGPU_M_NATOMS], nmosA = tm0[SLVGPU_M_NMOS], nbsA = tm0[SLVGPU_M_NBASIS];
   const int natB = tm[SLVGPU_M_NATOMS], nmosB = tm[SLVGPU_M_NMOS], nbsB = tm[SLVGPU_M_NBASIS];
   const int nij = nmosA * nmosB;
-  double *X = sm, *CBs = X + (size_t)nbsA * 4 * REP_JT, *IJ = CBs + (size_t)REP_JT * nbsB;
+  double *X = sm, *CBs = X + (size_t)REP_THREADS * 4 * 5 + 32, *IJ = CBs + (size_t)nmosB * nbsB;
   double *posA = IJ + 4 * nij, *LcA = posA + 3 * natA, *riA = LcA + 3 * natA, *ri1A = riA + 3 * nmosA;
   double *posB = ri1A + 3 * nmosA, *riB = posB + 3 * natB;
   const double *V = rp.V + (size_t)pr * rp.sV;
@@ -283,70 +281,70 @@ k_rep_pair(const DevPlan p, FrameLists fl, RepPool rp, const int REP_JT) {
   }
   const int *blB = p.itab + tm[SLVGPU_M_IO_BFL];
   const double *vecB = p.dtab + tm[SLVGPU_M_O_VECL];
-  for (int j0 = 0; j0 < nmosB; j0 += REP_JT) {
-    const int jn = min(REP_JT, nmosB - j0);
-    __syncthreads();                                         // X / CBs of the previous pass are consumed
-    // rotate the AO->LMO rows j0 .. j0+jn of the fragment into the lab frame (VECROT): s copy, p as vectors, d as
-    // symmetric tensors; one thread per leading element of a block
-    for (int w = tid; w < jn * nbsB; w += NT) {
-      const int j = w / nbsB, k = w - j * nbsB;
-      const int lx = blB[k * 3], ly = blB[k * 3 + 1], lz = blB[k * 3 + 2], Ls = lx + ly + lz;
-      const double *c = vecB + (size_t)(j0 + j) * nbsB + k;
-      double *d = CBs + (size_t)j * nbsB + k;
-      if (Ls == 0) d[0] = c[0];
-      else if (Ls == 1 && lx == 1) { double v[3] = {c[0], c[1], c[2]}, o[3]; rot_vec(R, v, o); d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; }
-      else if (Ls == 2 && lx == 2) { double v[6] = {c[0], c[1], c[2], c[3], c[4], c[5]}, o[6]; rot_quad(R, v, o); for (int q = 0; q < 6; ++q) d[q] = o[q]; }
-    }
-    __syncthreads();
-    // ---- phase 2: X[k][q][j] = sum_l V[k][l][q] CB[j][l]; one thread per (k, block of 5 LMOs): the row V[k][.][.] is
-    //      streamed once as 32-byte records, each feeding 20 FMAs
-    {
-      constexpr int JB = 5;
-      const int nblk = (jn + JB - 1) / JB;
-      for (int w = tid; w < nbsA * nblk; w += NT) {
-        const int k = w / nblk, jb = (w - k * nblk) * JB;
-        const double2 *v2 = reinterpret_cast<const double2 *>(V + (size_t)k * nbsB * 4);
-        const double *cb[JB];
+  // rotate the fragment's AO->LMO rows into the lab frame (VECROT): s copy, p as vectors, d as symmetric tensors; one
+  // thread per leading element of a block
+  for (int w = tid; w < nmosB * nbsB; w += NT) {
+    const int j = w / nbsB, k = w - j * nbsB;
+    const int lx = blB[k * 3], ly = blB[k * 3 + 1], lz = blB[k * 3 + 2], Ls = lx + ly + lz;
+    const double *c = vecB + (size_t)j * nbsB + k;
+    double *d = CBs + (size_t)j * nbsB + k;
+    if (Ls == 0) d[0] = c[0];
+    else if (Ls == 1 && lx == 1) { double v[3] = {c[0], c[1], c[2]}, o[3]; rot_vec(R, v, o); d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; }
+    else if (Ls == 2 && lx == 2) { double v[6] = {c[0], c[1], c[2], c[3], c[4], c[5]}, o[6]; rot_quad(R, v, o); for (int q = 0; q < 6; ++q) d[q] = o[q]; }
+  }
+  for (int w = tid; w < 4 * nij; w += NT) IJ[w] = 0.0;
+  // The solute's basis functions are taken in tiles of KT rows sized so that one tile's half transform is one round of
+  // the CTA; a tile's X goes straight into the LMO integrals, so every integral record is read exactly once however
+  // many LMOs the fragment has (three passes over V for DMSO's 21 LMOs cost 1.1 MB of DRAM reads per pair before).
+  constexpr int JB = 5;
+  const int nblk = (nmosB + JB - 1) / JB, JP = nblk * JB;
+  const int KT = max(1, NT / nblk);
+  for (int k0 = 0; k0 < nbsA; k0 += KT) {
+    const int kn = min(KT, nbsA - k0);
+    __syncthreads();                                         // CBs ready / the previous tile's X is consumed
+    // ---- phase 2: X[kk][q][j] = sum_l V[k0+kk][l][q] CB[j][l]; one thread per (row, block of 5 LMOs): the row is
+    //      streamed as 32-byte records, each feeding 20 FMAs (the nblk threads of a row sit in one warp)
+    for (int w = tid; w < kn * nblk; w += NT) {
+      const int kk = w / nblk, jb = (w - kk * nblk) * JB;
+      const double2 *v2 = reinterpret_cast<const double2 *>(V + (size_t)(k0 + kk) * nbsB * 4);
+      const double *cb[JB];
 #pragma unroll
-        for (int jj = 0; jj < JB; ++jj) cb[jj] = CBs + (size_t)min(jb + jj, jn - 1) * nbsB;
-        double acc[4][JB];
+      for (int jj = 0; jj < JB; ++jj) cb[jj] = CBs + (size_t)min(jb + jj, nmosB - 1) * nbsB;
+      double acc[4][JB];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < 4; ++q)
 #pragma unroll
-          for (int jj = 0; jj < JB; ++jj) acc[q][jj] = 0.0;
+        for (int jj = 0; jj < JB; ++jj) acc[q][jj] = 0.0;
 #pragma unroll 8
-        for (int l = 0; l < nbsB; ++l) {
-          const double2 va = v2[2 * l], vb = v2[2 * l + 1];
+      for (int l = 0; l < nbsB; ++l) {
+        const double2 va = v2[2 * l], vb = v2[2 * l + 1];
 #pragma unroll
-          for (int jj = 0; jj < JB; ++jj) {
-            const double c = cb[jj][l];
-            acc[0][jj] = fma(va.x, c, acc[0][jj]); acc[1][jj] = fma(va.y, c, acc[1][jj]);
-            acc[2][jj] = fma(vb.x, c, acc[2][jj]); acc[3][jj] = fma(vb.y, c, acc[3][jj]);
-          }
+        for (int jj = 0; jj < JB; ++jj) {
+          const double c = cb[jj][l];
+          acc[0][jj] = fma(va.x, c, acc[0][jj]); acc[1][jj] = fma(va.y, c, acc[1][jj]);
+          acc[2][jj] = fma(vb.x, c, acc[2][jj]); acc[3][jj] = fma(vb.y, c, acc[3][jj]);
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int jj = 0; jj < JB; ++jj)
-            if (jb + jj < jn) X[((size_t)k * 4 + q) * REP_JT + jb + jj] = acc[q][jj];
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) X[((size_t)kk * 4 + q) * JP + jb + jj] = acc[q][jj];
     }
     __syncthreads();
-    // ---- phase 3: LMO-basis integrals for the LMOs of this pass
-    for (int w = tid; w < nmosA * jn; w += NT) {
-      const int i = w / jn, j = w - i * jn;
-      const double *ca = CA + (size_t)i * nbsA, *ca1 = CA1 + (size_t)i * nbsA;
+    // ---- phase 3: this tile's contribution to the LMO-basis integrals; (i, j) is owned by one thread
+    for (int w = tid; w < nij; w += NT) {
+      const int i = w / nmosB, j = w - i * nmosB;
+      const double *ca = CA + (size_t)i * nbsA + k0, *ca1 = CA1 + (size_t)i * nbsA + k0;
       double sv = 0, tv = 0, smv = 0, tmv = 0;
 #pragma unroll 8
-      for (int k = 0; k < nbsA; ++k) {
-        const double *x = X + (size_t)k * 4 * REP_JT + j;
-        const double xs = x[0], xt = x[REP_JT], xds = x[2 * REP_JT], xdt = x[3 * REP_JT];
-        const double c0 = ca[k], c1 = ca1[k];
+      for (int kk = 0; kk < kn; ++kk) {
+        const double *x = X + (size_t)kk * 4 * JP + j;
+        const double xs = x[0], xt = x[JP], xds = x[2 * JP], xdt = x[3 * JP];
+        const double c0 = ca[kk], c1 = ca1[kk];
         sv = fma(c0, xs, sv); tv = fma(c0, xt, tv);
         smv = fma(c0, xds, fma(c1, xs, smv)); tmv = fma(c0, xdt, fma(c1, xt, tmv));
       }
-      const int o = i * nmosB + j0 + j;
-      IJ[o] = sv; IJ[nij + o] = tv; IJ[2 * nij + o] = smv; IJ[3 * nij + o] = tmv;
+      IJ[w] += sv; IJ[nij + w] += tv; IJ[2 * nij + w] += smv; IJ[3 * nij + w] += tmv;
     }
   }
   __syncthreads();

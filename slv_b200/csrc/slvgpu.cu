@@ -361,7 +361,7 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
             SLV_SUBSHELL_CLASSES(X)
 #undef X
           }
-          k_rep_pair<<<npairs, REP_THREADS, sm_re, sb>>>(p, pl->fl, rp, rep_jt(pl->max_nmos));
+          k_rep_pair<<<npairs, REP_THREADS, sm_re, sb>>>(p, pl->fl, rp);
           ++pl->last_launches;
         }
         k_rep_sum<<<(nb + 127) / 128, 128, 0, sb>>>((int)f0, fs, nb, rp, d_out);
