@@ -261,10 +261,18 @@ k_rep_pair(const DevPlan p, FrameLists fl, RepPool rp) {
   const double *V = rp.V + (size_t)pr * rp.sV;
   const double *CA = rp.CA + (size_t)fi * 2 * nmosA * nbsA, *CA1 = CA + (size_t)nmosA * nbsA;
   const double *FA = p.dtab + tm0[SLVGPU_M_O_FOCK], *FA1 = p.dtab + p.sol_meta[SLVGPU_S_FOCK1], *ZA = p.dtab + tm0[SLVGPU_M_O_ZNUC];
-  // the pair's integrals were written by the previous kernels of the batch and the pool is far larger than L2: start
-  // pulling them in now, so that the half transform below finds them in L2 instead of paying DRAM latency per record
-  for (size_t b = (size_t)tid * 128; b < (size_t)nbsA * nbsB * 32; b += (size_t)NT * 128)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(V) + b));
+  // The pair's integrals were written by earlier kernels of the batch into a pool far larger than L2: rows are pulled
+  // into L2 two tiles ahead of the half transform (all of them at once would be 0.55 MB per DMSO pair x 3 CTAs x 148
+  // SMs -- more than L2 holds).
+  auto prefetch_rows = [&](int r0, int r1) {
+    r1 = min(r1, nbsA);
+    if (r0 >= r1) return;
+    const char *base = reinterpret_cast<const char *>(V) + (size_t)r0 * nbsB * 32;
+    const size_t bytes = (size_t)(r1 - r0) * nbsB * 32;
+    for (size_t b = (size_t)tid * 128; b < bytes; b += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + b));
+  };
+  const int nblk0 = (nmosB + 4) / 5, KT0 = max(1, NT / nblk0);
+  prefetch_rows(0, 2 * KT0);
   double R[9], t[3];
   {
     const double *xf = fl.list_xf + ((size_t)fi * p.list_cap + e) * 12;
@@ -301,6 +309,7 @@ k_rep_pair(const DevPlan p, FrameLists fl, RepPool rp) {
   const int KT = max(1, NT / nblk);
   for (int k0 = 0; k0 < nbsA; k0 += KT) {
     const int kn = min(KT, nbsA - k0);
+    prefetch_rows(k0 + 2 * KT, k0 + 3 * KT);
     __syncthreads();                                         // CBs ready / the previous tile's X is consumed
     // ---- phase 2: X[kk][q][j] = sum_l V[k0+kk][l][q] CB[j][l]; one thread per (row, block of 5 LMOs): the row is
     //      streamed as 32-byte records, each feeding 20 FMAs (the nblk threads of a row sit in one warp)
