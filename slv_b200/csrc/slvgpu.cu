@@ -244,6 +244,12 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
       slvgpu_plan_destroy(pl);
       return fail(SLVGPU_EINVAL, "exchange-repulsion needs the wave-function tables (vecl, fock, basis) in the plan");
     }
+    if (pl->max_nmos > 5 * REP_THREADS ||
+        rep_smem_bytes(pl->nmosc, pl->nbasc, pl->max_nmos, pl->max_nbas, pl->natc, pl->max_nat) > (size_t)200 * 1024) {
+      slvgpu_plan_destroy(pl);
+      return fail(SLVGPU_EINVAL, "exchange repulsion: a fragment type is too large for k_rep_pair's shared-memory tables "
+                                 "(LMOs x basis functions of the fragment, LMOs of solute x fragment)");
+    }
     TRY(rep_alloc(pl->rp, pl->rep_lim, pl->allocs, g_err, pl->nmosc, pl->nbasc, pl->natc, pl->max_nbas, pl->max_nat, pl->max_chunk, p.list_cap));
     for (int t = 0; t < d->ntypes; ++t) {
       const int32_t *tm = d->type_meta + (size_t)t * SLVGPU_NMETA;
