@@ -84,6 +84,7 @@ static void ev_begin(slvgpu_plan *pl, int kind, cudaStream_t st) {
   if (pl->ev_used + 2 > pl->ev_pool.size()) {
     for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); pl->ev_pool.push_back(e); }
   }
+  pl->ev_kind.resize(pl->ev_used / 2);       // an error return between ev_begin and ev_end left an unrecorded entry behind
   cudaEventRecord(pl->ev_pool[pl->ev_used], st);
   pl->ev_kind.push_back(kind);
 }
@@ -103,6 +104,7 @@ extern "C" int slvgpu_set_timing(slvgpu_plan *pl, int on) {
 extern "C" int slvgpu_get_timing(slvgpu_plan *pl, double *ms4, int64_t *launches4) {
   if (!pl || !ms4 || !launches4) return fail(SLVGPU_EINVAL, "null argument");
   CK(cudaDeviceSynchronize());
+  if (pl->ev_kind.size() > pl->ev_used / 2) pl->ev_kind.resize(pl->ev_used / 2);
   for (size_t i = 0; i < pl->ev_kind.size(); ++i) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, pl->ev_pool[2 * i], pl->ev_pool[2 * i + 1]));
@@ -136,6 +138,47 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
     return fail(SLVGPU_EINVAL, "null table pointer");
   for (int i = 0; i < d->ninst; ++i)
     if (d->inst_type[i] < 0 || d->inst_type[i] >= d->ntypes) return fail(SLVGPU_EINVAL, "instance type out of range");
+  // Every table a requested term reads must be present: a missing section of a .frg file leaves its offset at -1,
+  // which the kernels would use as an address.  The reference raises KeyError on the missing parameter
+  // (solvshift/solefp.py:1429 par['dpoli'], 1305 par['dpol'], 1531 par['fock']).
+  {
+    const int32_t *t0 = d->type_meta + (size_t)d->inst_type[0] * SLVGPU_NMETA;
+    auto need_sol = [&](int k) { return d->sol_meta[k] >= 0; };
+    auto miss = [&](const char *term, const char *what, int type) {
+      return fail(SLVGPU_EINVAL, std::string(term) + " needs the '" + what + "' table of fragment type " + std::to_string(type) +
+                                     ", which its parameter file does not provide");
+    };
+    const int ts = d->inst_type[0];
+    if (d->flags & SLVGPU_ELECT) {
+      if (t0[SLVGPU_M_O_RDMA] < 0 || t0[SLVGPU_M_NDMA] < 1) return miss("elect", "distributed multipoles", ts);
+      if (!need_sol(SLVGPU_S_SMEA) || !need_sol(SLVGPU_S_SEA) || !need_sol(SLVGPU_S_CMEA) || !need_sol(SLVGPU_S_CEA))
+        return miss("elect", "multipole derivatives (dma1/dma2, lvec, gijk)", ts);
+    }
+    if (d->flags & SLVGPU_DISP) {
+      if (t0[SLVGPU_M_NPOL] < 1 || t0[SLVGPU_M_O_RPOL] < 0 || t0[SLVGPU_M_O_DPOLI] < 0) return miss("disp", "dpoli", ts);
+      if (!need_sol(SLVGPU_S_DPOLI1)) return miss("disp", "dpoli1", ts);
+      if (!need_sol(SLVGPU_S_LMOC1)) return miss("disp", "lmoc1", ts);
+    }
+    if (d->flags & SLVGPU_POL) {
+      if (t0[SLVGPU_M_NPOL] < 1 || t0[SLVGPU_M_O_RPOL] < 0 || t0[SLVGPU_M_O_POL] < 0) return miss("pol", "dpol", ts);
+      if (t0[SLVGPU_M_O_RDMA] < 0 || t0[SLVGPU_M_O_MOM] < 0) return miss("pol", "distributed multipoles", ts);
+      if (!need_sol(SLVGPU_S_DPOL1)) return miss("pol", "dpol1", ts);
+      if (!need_sol(SLVGPU_S_LMOC1)) return miss("pol", "lmoc1", ts);
+      if (!need_sol(SLVGPU_S_DMA1) || !need_sol(SLVGPU_S_LVEC)) return miss("pol", "dma1 / lvec", ts);
+    }
+    for (int i = 1; i < d->ninst; ++i) {
+      const int ty = d->inst_type[i];
+      const int32_t *tm = d->type_meta + (size_t)ty * SLVGPU_NMETA;
+      if ((d->flags & (SLVGPU_ELECT | SLVGPU_POL)) && tm[SLVGPU_M_NDMA] > 0 && (tm[SLVGPU_M_O_RDMA] < 0 || tm[SLVGPU_M_O_MOM] < 0))
+        return miss("elect/pol", "distributed multipoles", ty);
+      if ((d->flags & (SLVGPU_POL | SLVGPU_DISP)) && tm[SLVGPU_M_NPOL] > 0 && (tm[SLVGPU_M_O_RPOL] < 0 || tm[SLVGPU_M_O_POL] < 0))
+        return miss("pol/disp", "dpol", ty);
+      if ((d->flags & SLVGPU_DISP) && tm[SLVGPU_M_NPOL] > 0 && tm[SLVGPU_M_O_DPOLI] < 0) return miss("disp", "dpoli", ty);
+      if ((d->flags & SLVGPU_REP) && (tm[SLVGPU_M_O_VECL] < 0 || tm[SLVGPU_M_O_FOCK] < 0 || tm[SLVGPU_M_O_LMOC] < 0 ||
+                                      tm[SLVGPU_M_IO_SHPAIR] < 0 || tm[SLVGPU_M_NMOS] < 1))
+        return miss("rep", "wave function (vecl, fock, lmoc, basis)", ty);
+    }
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(SLVGPU_ECUDA, "no CUDA device: this library has no CPU path");

@@ -10,6 +10,7 @@ files are read natively (the reference goes through MDAnalysis / its own readers
 (``rank``/``world``): each rank evaluates its contiguous block and writes its own rows; frame numbers stay global.
 """
 import sys
+import warnings
 
 import numpy
 
@@ -93,6 +94,13 @@ def load_trajectory(traj, natoms=None):
     return read_xyz_frames(traj)
 
 
+def status_text(st):
+    """Names of the per-frame status bits (include/slvgpu.h SLVGPU_ST_*)."""
+    names = [(_lib.ST_NONFINITE, 'non-finite'), (_lib.ST_POL_NOCONV, 'pol-not-converged'), (_lib.ST_SINGULAR, 'singular-fit'),
+             (_lib.ST_OVERFLOW, 'pol-workspace-overflow')]
+    return '+'.join(n for b, n in names if st & b) or 'ok'
+
+
 def format_rows(rows, shifts, first_frame=1):
     """Report lines for device output rows (slv_md-run_nopp:148-153)."""
     O = _lib.OUT
@@ -122,8 +130,11 @@ def run(solinp, traj, out, mode, nframes=None, cuts=(40.0, 17.0, 12.0), no_elect
     lo += first_frame; hi += first_frame
     scale = AngstromToBohr if units.lower().startswith('ang') else 1.0
     all_rows, all_status = [], []
+    if world > 1 and isinstance(out, str):
+        # every rank writes its own block of frames: one file per rank (the ranks would clobber a shared path)
+        out = '%s.rank%d' % (out, rank)
     fh = None if out is None else (open(out, 'a' if append else 'w') if isinstance(out, str) else out)
-    if fh is not None and rank == 0 and not append:
+    if fh is not None and (rank == 0 or world > 1) and not append:
         fh.write(HEADER + '\n'); fh.flush()
     first = True
     for b0 in range(lo, hi, batch):
@@ -131,8 +142,17 @@ def run(solinp, traj, out, mode, nframes=None, cuts=(40.0, 17.0, 12.0), no_elect
         coords = numpy.ascontiguousarray(traj[b0:b1][:, idx, :] * scale)
         rows, status = efp.eval_frames(coords, *args) if first else efp.eval_frames(coords)
         first = False
+        bad = numpy.nonzero(numpy.asarray(status) != 0)[0]
+        if len(bad):
+            # a flagged frame is not an ordinary number: non-finite term, polarisation solve not converged, or more
+            # centres inside pcut than the workspace holds (pol_mea = 0 then); say so next to the rows
+            msg = ', '.join('%d:%s' % (b0 + 1 + int(f), status_text(int(status[f]))) for f in bad[:8])
+            warnings.warn('%d frame(s) of this batch carry a non-zero status (%s%s)' % (len(bad), msg, ', ...' if len(bad) > 8 else ''))
         if fh is not None:
-            fh.writelines(format_rows(rows, efp.shifts_of(rows), first_frame=b0 + 1)); fh.flush()
+            lines = format_rows(rows, efp.shifts_of(rows), first_frame=b0 + 1)
+            for f in bad:
+                lines[f] = lines[f].rstrip('\n') + '   # status: %s\n' % status_text(int(status[f]))
+            fh.writelines(lines); fh.flush()
         all_rows.append(rows.copy()); all_status.append(status.copy())
     if isinstance(out, str):
         fh.close()

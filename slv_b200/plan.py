@@ -126,6 +126,24 @@ class Plan(object):
                 m[M['O_BFEXP']] = dt.add(bfs.exps); m[M['O_BFCOEF']] = dt.add(bfs.coefs)
                 m[M['NSUBSH']] = len(bfs.subshells); m[M['IO_SUBSH']] = it.add(bfs.subshells)
                 self._bfs[t] = bfs
+        # ---- every table a requested term reads must exist: the reference fails with KeyError on the missing parameter
+        #      (solefp.py:1429 par['dpoli'], 1305 par['dpol'], 1531 par['fock']); here a missing table would be a bad address
+        fl = self.flags
+        for i in sorted(set(int(t) for t in ind[1:])):
+            par, nm = pars[i], pars[i].get('name')
+            if fl & _lib.FLAG['disp'] and meta[i][M['NPOL']] > 0 and 'dpoli' not in par:
+                raise KeyError("'dpoli': dispersion needs the polarisabilities at imaginary frequencies of fragment %r" % nm)
+            if fl & _lib.FLAG['rep'] and not ('vecl' in par and 'fock' in par and 'lmoc' in par):
+                raise KeyError("'vecl'/'fock'/'lmoc': exchange repulsion needs the wave function of fragment %r" % nm)
+            if fl & (_lib.FLAG['elect'] | _lib.FLAG['pol']) and 'rdma' not in par:
+                raise KeyError("'rdma': fragment %r has no distributed multipoles" % nm)
+        if len(ind) > 1:
+            pc0 = pars[int(ind[0])]
+            for flag, keys in (('disp', ('dpoli', 'dpoli1', 'lmoc1')), ('pol', ('dpol', 'dpol1', 'lmoc1', 'dmac1', 'lvec')),
+                               ('rep', ('vecl', 'vecl1', 'fock', 'fock1', 'lmoc', 'lmoc1', 'lvec')), ('elect', ('rdma', 'dmac1', 'gijk'))):
+                for k in keys:
+                    if fl & _lib.FLAG[flag] and k not in pc0:
+                        raise KeyError("%r: the %s shift needs this section of the solute's parameter file (%r)" % (k, flag, pc0.get('name')))
         # ---- exchange-repulsion work list: for every fragment type B, the (solute sub-shell, B sub-shell) pairs
         #      grouped by the 23 (L_bra, L_ket, bra component) specialisations of slv_ints.cuh (ket s: all bra
         #      components in one item; ket p, d: one item per bra component) and sorted by primitive-pair count

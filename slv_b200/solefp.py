@@ -209,7 +209,7 @@ class EFP(UNITS):
 
     # ------------------------------------------------------------------ evaluation
     def eval(self, lwrite=False, num=False, step=0.006, theory=0, remove_clashes=False,
-             rcl_algorithm='remove_by_name', include_ions=True, include_polar=True):
+             rcl_algorithm='remove_by_name', include_ions=False, include_polar=False):
         """Evaluate the shifts of the current frame (solefp.py:93-149)."""
         if num:
             raise NotImplementedError('numerical (finite-difference) mode needs the num_0.006/*.frg sets, which are '

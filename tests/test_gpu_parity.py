@@ -329,7 +329,8 @@ def test_protein_like_mixed_fragments(frags):
     pars = [b.get() for b in bsm]
     for f in range(2):
         efp.set(X[f], ind, nmol, bsm, [None] * nt, [None] * nt)
-        efp.eval(0, remove_clashes=True, include_ions=False, include_polar=False)
+        # default arguments: include_ions=False, include_polar=False as in the reference (solefp.py:93-94)
+        efp.eval(0, remove_clashes=True)
         s = efp.get_shifts()
         rem = efp._removable
         assert rem == set(1 + names.index(n) for n in ('mecoo-', 'menh3+', 'meoh', 'methane', 'phenol', 'benzene', 'chonh2', 'nma'))
