@@ -109,7 +109,6 @@ class ClockSampler(threading.Thread):
 
 def cpu_reference_frames(wl, bsm, ind, nmol, X, nsample):
     """Oracle port timed on the host cores: returns (frames/s, seconds, nframes)."""
-    from slv_b200.basis import BasisSet
     from oracle import solefp_oracle as O
     pars = [b.get() for b in bsm]
     nt = len(bsm)
@@ -118,7 +117,7 @@ def cpu_reference_frames(wl, bsm, ind, nmol, X, nsample):
     for f in range(nsample):
         O.eval_frame(X[f % len(X)], ind, nmol, pars, [None] * nt, [None] * nt, wl['mode'], *CUTS,
                      elect=True, ea=True, corr=True, pol=fl.get('pol', False), disp=fl.get('disp', False),
-                     rep=fl.get('rep', False), make_basis=lambda a_, p_: BasisSet(a_, p_), literal_gemm=True)
+                     rep=fl.get('rep', False), literal_gemm=True)
     dt = time.time() - t0
     return nsample / dt, dt, nsample
 

@@ -8,7 +8,7 @@ The reference obtains them from the un-vendored dependency PyQuante "1.0.3-BBG"
   getSA1B -> dS_kl/dA_k (centre of k moves)       [nA,nB,3]
   getTA1B -> dT_kl/dA_k                           [nA,nB,3]
 Restated here with Obara-Saika 1-D recursions over contracted Cartesian Gaussians built from
-the basis tables (slv_b200.basis.BasisSet layout: center, powers, exps, coefs zero-padded).
+the basis tables of oracle/basis_oracle.py (center, powers, exps, coefs zero-padded).
 """
 import numpy as np
 

@@ -135,3 +135,18 @@ def gtcf(a, b, k):
     tcf = np.zeros(int(k))
     lib().gtcf_(_p(a), _p(b), _i(a.size), _i(k), _p(tcf))
     return tcf
+
+
+def exrep(ria, rib, rna, rnb, faij, fbij, cika, cikb, skm, tkm, za, zb):
+    """exrep.exrep(ria, rib, rna, rnb, faij, fbij, cika, cikb, skm, tkm, za, zb) -> eint (Hartree), the EFP2
+    exchange-repulsion energy of one fragment pair (solvshift/src/exrep.f:140-168; call sites solefp.py:1549-1558
+    (commented), 1781-1805).  2-D arguments are Fortran arrays: column-major copies are made here as f2py does."""
+    F = lambda x: np.asfortranarray(x, np.float64)
+    ria, rib, rna, rnb, faij, fbij, cika, cikb, skm, tkm = [F(x) for x in (ria, rib, rna, rnb, faij, fbij, cika, cikb, skm, tkm)]
+    za = _d(za).ravel(); zb = _d(zb).ravel()
+    assert ria.shape[0] <= 40 and rib.shape[0] <= 40, 'COMMON /INTIJ/ holds 40 x 40 LMO pairs (exrep.f:150)'
+    e = ctypes.c_double(0.0)
+    lib().exrep_(_p(ria), _p(rib), _p(rna), _p(rnb), _p(faij), _p(fbij), _p(cika), _p(cikb), _p(skm), _p(tkm), _p(za), _p(zb),
+                 _i(cika.shape[1]), _i(cikb.shape[1]), _i(ria.shape[0]), _i(rib.shape[0]), _i(rna.shape[0]), _i(rnb.shape[0]),
+                 ctypes.byref(e))
+    return e.value

@@ -486,13 +486,16 @@ def vecrot(vec, rot, typ):
     return out
 
 
-def rep_shift(parc, solv, mode, make_basis, rotc=None, rots=None, par0c=None, par0s=None):
+def rep_shift(parc, solv, mode, make_basis=None, rotc=None, rots=None, par0c=None, par0s=None):
     """rep_mea (a.u.) and fi_rep[nmodes]: SHFTEX = CALCIJ + CALCFI (shftex.f:12-438) summed over the solvent
     molecules of the EXREP layer (solefp.py:1497-1560), integrals from oracle/ints_oracle.py.
     parc/solv are superimposed dicts that still carry UNROTATED wave-function arrays; rotc / rots are the
     rotations of their superimpositions (sup_params does not touch vecl/vecl1).  make_basis(atno, pos)
-    returns the basis tables (slv_b200.basis.BasisSet layout)."""
+    returns the basis tables; the default is the oracle's own builder (oracle/basis_oracle.py, parsed from the
+    reference's dat/slvbas) -- never the product's."""
     from . import ints_oracle as IO
+    if make_basis is None:
+        from .basis_oracle import make_basis
     w, den = mode_weights(parc, mode)
     nmodes = len(w)
     bA = make_basis(parc['atno'], parc['pos'])

@@ -146,7 +146,6 @@ def test_exchange_repulsion_vs_oracle(frags, solute, mode, nw, seed):
     """rep_mea: CUDA integrals + SHFTEX against the oracle (integrals restated; SHFTEX restatement validated
     against the transpiled reference Fortran in tests/test_oracle_vs_ref.py)."""
     from slv_b200 import synth
-    from slv_b200.basis import BasisSet
     from oracle import solefp_oracle as O
     sol, wat = frags(solute), frags('water')
     nat = sol.get_natoms()
@@ -159,14 +158,13 @@ def test_exchange_repulsion_vs_oracle(frags, solute, mode, nw, seed):
     c = O.HartreePerHbarToCmRec
     for f in range(len(X)):
         ref = O.eval_frame(X[f], ind, nmol, [sol.get(), wat.get()], [None, None], [None, None], mode, *cuts,
-                           elect=True, ea=True, corr=True, rep=True, make_basis=lambda a, p: BasisSet(a, p))
+                           elect=True, ea=True, corr=True, rep=True)
         assert abs(got['rep_mea'][f] - ref['rep_mea'] * c) < TOL * max(1.0, abs(ref['rep_mea'] * c) * 1e-3), (f, got['rep_mea'][f], ref['rep_mea'] * c)
         assert rows[f, 13] == ref['n_rep']
 
 
 def test_exchange_repulsion_mixed_types(frags):
     from slv_b200 import synth
-    from slv_b200.basis import BasisSet
     from oracle import solefp_oracle as O
     sol, wat, dmso = frags('mescn'), frags('water'), frags('dmso')
     types = np.array([0, 1, 0, 1, 0, 0])
@@ -176,7 +174,7 @@ def test_exchange_repulsion_mixed_types(frags):
     rows, status = efp.eval_frames(X, ind, nmol, [sol, wat, dmso], [None] * 3, [None] * 3)
     got = efp.shifts_of(rows)
     ref = O.eval_frame(X[0], ind, nmol, [sol.get(), wat.get(), dmso.get()], [None] * 3, [None] * 3, 4, 40.0, 17.0, 14.0,
-                       elect=True, rep=True, make_basis=lambda a, p: BasisSet(a, p))
+                       elect=True, rep=True)
     c = O.HartreePerHbarToCmRec
     assert abs(got['rep_mea'][0] - ref['rep_mea'] * c) < TOL * max(1.0, abs(ref['rep_mea'] * c) * 1e-3), (got['rep_mea'][0], ref['rep_mea'] * c)
 
@@ -314,7 +312,6 @@ def test_protein_like_mixed_fragments(frags):
     """BASELINE config 4 shape, small: MeSCN probe among mixed EFP fragment types incl. charged residues and
     one-atom ions (identity superimposition, slvpar.py:668-671), remove_clashes=True, full SolEFP incl. rep."""
     from slv_b200 import synth
-    from slv_b200.basis import BasisSet
     from oracle import solefp_oracle as O
     names = ['water', 'mecoo-', 'menh3+', 'meoh', 'methane', 'phenol', 'benzene', 'chonh2', 'nma', 'na+', 'cl-']
     sol = frags('mescn'); fr = [frags(n) for n in names]
@@ -335,7 +332,7 @@ def test_protein_like_mixed_fragments(frags):
         rem = efp._removable
         assert rem == set(1 + names.index(n) for n in ('mecoo-', 'menh3+', 'meoh', 'methane', 'phenol', 'benzene', 'chonh2', 'nma'))
         ref = O.eval_frame(X[f], ind, nmol, pars, [None] * nt, [None] * nt, 4, *cuts, elect=True, ea=True, corr=True, pol=True,
-                           disp=True, rep=True, make_basis=lambda a, p: BasisSet(a, p), removable=rem)
+                           disp=True, rep=True, removable=rem)
         for k in TERMS + ('rep_mea',):
             tol = TOL * max(1.0, abs(ref[k] * c) * 1e-3)
             assert abs(s[k] - ref[k] * c) < tol, (f, k, s[k], ref[k] * c)
@@ -420,7 +417,6 @@ def test_full_solefp_batch_properties(frags):
     entries agree -- and the frames that are copies of an oracle-checked one reproduce it in every term."""
     import torch
     from slv_b200 import synth
-    from slv_b200.basis import BasisSet
     from oracle import solefp_oracle as O
     sol, wat, dmso = frags('mescn'), frags('water'), frags('dmso')
     nw, nu, nf = 400, 12, 3000
@@ -446,7 +442,7 @@ def test_full_solefp_batch_properties(frags):
     assert np.array_equal(rh[:, :8], rows[:, :8]) and int(sh.max()) == 0
     c = O.HartreePerHbarToCmRec
     ref = O.eval_frame(U[0], ind, nmol, [b.get() for b in bsm], [None] * 3, [None] * 3, 4, 40.0, 17.0, 12.0,
-                       elect=True, ea=True, corr=True, pol=True, disp=True, rep=True, make_basis=lambda a, p: BasisSet(a, p))
+                       elect=True, ea=True, corr=True, pol=True, disp=True, rep=True)
     s = efp.shifts_of(ru[:1])
     for k in TERMS + ('rep_mea',):
         assert abs(s[k][0] - ref[k] * c) < TOL * max(1.0, abs(ref[k] * c) * 1e-3), (k, s[k][0], ref[k] * c)

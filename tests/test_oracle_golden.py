@@ -69,10 +69,10 @@ def test_wavefunction_fixtures_pin_basis_and_overlap_derivatives(frags):
     contracts them.  This fixes basis data, function order, normalisation, and the sign/centre convention of
     getSA1B (solefp.py:1521-1524) without PyQuante."""
     from oracle import ints_oracle as IO
-    from slv_b200 import basis
+    from oracle import basis_oracle as basis
     for name in ('nma', 'water', 'meoh'):
         p = frags(name).get()
-        b = basis.BasisSet(p['atno'], p['pos'])
+        b = basis.OracleBasis(p['atno'], p['pos'])
         S, T, S1, T1 = IO.one_electron(b, p['pos'], b, p['pos'])
         C = p['vecl']
         assert np.abs(C @ S @ C.T - np.eye(len(C))).max() < 1e-8, name

@@ -69,3 +69,98 @@ def test_sftpli(frags, nw, seed):
     assert np.abs(av2.ravel() - avec).max() < 1e-12 * np.abs(avec).max()
     sh3, _, _, _ = O.pol_shift(parc, solv, mode, literal_gemm=True)
     assert abs(sh3 - spol) < 1e-12 * max(1.0, abs(spol) * 1e3)
+
+
+def _rep_pair(frags, solute, partner, seed):
+    """One (solute, partner) pair superimposed onto a synthetic geometry, with the wave-function arrays rotated the way
+    Frag.sup does (slvpar.py:724-733), and the AO integrals of the oracle."""
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O, basis_oracle as B, ints_oracle as IO
+    sol, par = frags(solute).get(), frags(partner).get()
+    X = synth.make_trajectory(sol['pos'], [par['pos']], np.zeros(1, int), 1, seed=seed, spacing=7.5)[0]
+    n = sol['natoms']
+    ra, ta, _ = O.kabsch(sol['pos'], X[:n]); pa = O.sup_params(sol, ra, ta)
+    rb, tb, _ = O.kabsch(par['pos'], X[n:]); pb = O.sup_params(par, rb, tb)
+    bA = B.OracleBasis(pa['atno'], pa['pos']); bB = B.OracleBasis(pb['atno'], pb['pos'])
+    typA, typB = bA.powers.sum(1), bB.powers.sum(1)
+    S, T, S1, T1 = IO.one_electron(bA, pa['pos'], bB, pb['pos'])
+    return dict(pa=pa, pb=pb, ra=ra, rb=rb, bA=bA, bB=bB, typA=typA, typB=typB, S=S, T=T, S1=S1, T1=T1,
+                CA=O.vecrot(pa['vecl'], ra, typA), CA1=O.vecrot(pa['vecl1'], ra, typA), CB=O.vecrot(pb['vecl'], rb, typB))
+
+
+@pytest.mark.parametrize('solute,partner,mode,seed', [('nma', 'water', 8, 3), ('mescn', 'dmso', 4, 5), ('mescn', 'water', 4, 6)])
+def test_shftex_restatement_matches_transpiled(frags, solute, partner, mode, seed):
+    """oracle.rep_shift (einsum restatement of CALCIJ + CALCFI) against the reference's own shftex.f, transpiled, called
+    with the argument list of solefp.py:1542-1545: SHFTMA and every fi_m to 1e-12 relative."""
+    from oracle import solefp_oracle as O
+    d = _rep_pair(frags, solute, partner, seed)
+    pa, pb = d['pa'], d['pb']
+    sh, fi = O.rep_shift(pa, [pb], mode, None, d['ra'], [d['rb']])
+    ma, ea, fi_ref, sij, tij, smij, tmij = RN.shftex(
+        pa['redmass'], pa['freq'], pa['gijk'][:, mode - 1, mode - 1], pa['lvec'], pa['lmoc'], pb['lmoc'], pa['pos'], pb['pos'],
+        pa['lmoc1'], d['CA'], d['CB'], d['CA1'], d['S'], d['T'], d['S1'], d['T1'], pa['atno'], pb['atno'], len(d['bB']),
+        d['bA'].center + 1, pa['fock'], pb['fock'], pa['fock1'], mode)
+    assert ea == 0.0
+    assert abs(sh - ma) < 1e-12 * abs(ma), (sh, ma)
+    assert np.abs(fi - fi_ref).max() < 1e-12 * np.abs(fi_ref).max()
+    assert np.abs(sij.reshape(len(d['CA']), -1) - d['CA'] @ d['S'] @ d['CB'].T).max() < 1e-13
+
+
+def test_vecrot_vc1rot(frags):
+    """VECROT / VC1ROT (efprot.f:22-283) against the oracle's coefficient rotation: p triples as vectors, d sextets as the
+    symmetric matrix whose off-diagonals are the xy/xz/yz coefficients; random proper rotation."""
+    from oracle import solefp_oracle as O, basis_oracle as B
+    rng = np.random.default_rng(11)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    rot = q * np.sign(np.linalg.det(q))
+    for name in ('nma', 'dmso', 'mescn'):
+        p = frags(name).get()
+        typ = B.OracleBasis(p['atno'], p['pos']).powers.sum(1)
+        assert set(typ) == {0, 1, 2}
+        v = RN.vecrot(p['vecl'], rot, typ)
+        assert np.abs(v - O.vecrot(p['vecl'], rot, typ)).max() < 1e-14
+        assert np.abs(v - p['vecl']).max() > 1e-2
+        if 'vecl1' in p:
+            v1 = RN.vc1rot(p['vecl1'], rot, typ)
+            assert np.abs(v1 - O.vecrot(p['vecl1'], rot, typ)).max() < 1e-14
+
+
+def test_product_basis_tables_equal_oracle_basis(frags):
+    """The oracle parses the reference's dat/slvbas itself (oracle/basis_oracle.py); the product reads its own JSON
+    conversion (slv_b200/basis.py).  Same functions, order, exponents and normalised coefficients."""
+    from oracle import basis_oracle as B
+    from slv_b200.basis import BasisSet
+    for name in ('nma', 'water', 'dmso', 'mescn', 'na+', 'cl-', 'li+', 'so3--', 'phenol'):
+        p = frags(name).get()
+        a, b = B.OracleBasis(p['atno'], p['pos']), BasisSet(p['atno'], p['pos'])
+        assert len(a) == len(b) == p['nbasis']
+        assert (a.center == b.center).all() and (a.powers == b.powers).all() and (a.nprim == b.nprim).all()
+        assert np.abs(a.exps - b.exps).max() == 0.0
+        assert np.abs(a.coefs - b.coefs).max() < 1e-14 * np.abs(b.coefs).max()
+
+
+@pytest.mark.parametrize('solute,partner,mode,seed', [('nma', 'water', 8, 3), ('mescn', 'water', 4, 6)])
+def test_rep_force_is_the_derivative_of_the_reference_exrep_energy(frags, solute, partner, mode, seed):
+    """fi_m of SHFTEX must be dE_exrep/dQ_m of the reference's own energy routine (exrep.f:140-260, transpiled): the
+    solute is displaced along each normal mode -- atoms by lvec, LMO centroids by lmoc1, AO->LMO coefficients by vecl1,
+    the Fock matrix by fock1, the basis functions ride on the atoms -- and the energy is differentiated by a 4-point
+    central stencil.  This pins dT/dA (and dS/dA) against T and S: the derivative integrals the golden run took from
+    the un-vendored PyQuante-mod are, in the oracle, the physical derivatives of the integrals EXREP consumes."""
+    from oracle import solefp_oracle as O, basis_oracle as B, ints_oracle as IO
+    d = _rep_pair(frags, solute, partner, seed)
+    pa, pb = d['pa'], d['pb']
+    _, fi = O.rep_shift(pa, [pb], mode, None, d['ra'], [d['rb']])
+
+    def energy(m, h):
+        pos = pa['pos'] + h * pa['lvec'][m]
+        bA = B.OracleBasis(pa['atno'], pos)
+        S, T, _, _ = IO.one_electron(bA, pos, d['bB'], pb['pos'])
+        return RN.exrep(pa['lmoc'] + h * pa['lmoc1'][m], pb['lmoc'], pos, pb['pos'], pa['fock'] + h * pa['fock1'][m], pb['fock'],
+                        d['CA'] + h * d['CA1'][m], d['CB'], S, T, pa['atno'], pb['atno'])
+
+    h = 0.005
+    nm = len(fi)
+    modes = sorted(set(list(np.argsort(-np.abs(fi))[:4]) + [mode - 1, 0, nm - 1]))
+    for m in modes:
+        fd = (8.0 * (energy(m, h) - energy(m, -h)) - (energy(m, 2 * h) - energy(m, -2 * h))) / (12.0 * h)
+        assert abs(fd - fi[m]) < 1e-6 * max(np.abs(fi).max(), abs(fi[m])), (m, fd, fi[m])
