@@ -84,3 +84,21 @@ def test_wavefunction_fixtures_pin_basis_and_overlap_derivatives(frags):
             C1 = p['vecl1'][m]
             assert np.abs(C1 @ S @ C.T).max() > 1e-3          # the relation is not trivially satisfied
             assert np.abs(C1 @ S @ C.T + C @ S @ C1.T + C @ dS @ C.T).max() < 2e-6, (name, m)
+
+
+@pytest.mark.xfail(strict=True, reason="golden rep_mea (examples/1_small-clusters/f:16) is NOT reproduced: the derivative integrals of the "
+                   "golden run came from the un-vendored PyQuante 1.0.3-BBG (getSA1B/getTA1B); see DESIGN.md section 6 and "
+                   "profiles/rep_gap_r02.txt -- the gap stays visible here until it is explained")
+def test_golden_f_rep_mea(frags, golden):
+    from oracle import solefp_oracle as O
+    r = _frame(frags, scan_geometries(golden, 1)[0], elect=True, rep=True)
+    assert abs(r['rep_mea'] * O.HartreePerHbarToCmRec - golden['f']['rep_mea']) < 1e-6
+
+
+def test_rep_mea_value_is_stable(frags, golden):
+    """The number the oracle (and the GPU path) give for the golden geometry: 9.34798 cm-1 against 11.54893 in `f`.
+    Pinned here so that a change of the integrals or of the SHFTEX restatement cannot go unnoticed while the golden
+    comparison above is an expected failure."""
+    from oracle import solefp_oracle as O
+    r = _frame(frags, scan_geometries(golden, 1)[0], elect=True, rep=True)
+    assert abs(r['rep_mea'] * O.HartreePerHbarToCmRec - 9.34798) < 1e-4
