@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- SolEFP frequency-shift throughput on synthetic MD trajectories (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--frames F] [--waters NW]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C] [--only]
 
-Workload (BASELINE.json configs[1]): NMA-d7 in 500 waters, SolEFP Coulomb (MEA+EA+corrections) +
-polarisation, 10 000 synthetic frames per GPU per step (SURVEY.md 8(d) generator, seed 2), mode 8,
-ccut 40 / pcut 17 / ecut 12 Bohr.  One step = one pass of the hot path over the whole frame batch.
-Frames shard across ranks with no data-path collective ("scaling": "weak": every rank gets the same
-number of frames); one gather of the per-frame rows at the end of each step.
+Headline workload = BASELINE.json configs[2] ("config 3"): MeSCN in a 50/50 water/DMSO mix of 400 fragments, FULL
+SolEFP (electrostatics MEA+EA+corrections, polarisation, exchange repulsion, dispersion: all four kernel groups),
+10 000 synthetic frames per GPU per step (SURVEY.md 8(d) generator), mode 4, ccut 40 / pcut 17 / ecut 12 Bohr --
+the configuration BASELINE.json quotes at 1/2/4/8 GPUs.  One step = one pass of the hot path over the whole frame
+batch.  Frames shard across ranks with no data-path collective ("scaling": "weak": every rank gets the same number
+of frames); one gather of the per-frame rows at the end of each step.  Unless --only is given, the same JSON line
+nests complete sub-records for config 2 (NMA-d7 + 500 waters, elect+pol) and config 5 (NMA + 4000 waters, all terms)
+under "configs"; --config 4 runs the protein-like shape (about 2000 mixed EFP fragments, remove_clashes).
 
 value      = frames/s, whole job, coordinates already resident in HBM (CUDA events on the launch stream,
              barrier + synchronize on both sides, max over ranks)
 e2e        = frames/s through EFP.eval_frames with HOST (pinned) coordinates: H2D of the coordinates and
              D2H of the result rows inside the timed region
-roofline   = dominant kernel (k_pol) against the FP64 DFMA peak measured by tools/fp64_peak.cu
-cpu_baseline = oracle port (NumPy + BLAS, reference cost structure: LU inverse + 2 DGEMM per mode) on a
-             bounded sample of the same frames, rank 0 only.
+roofline   = dominant kernel (k_pol) against the FP64 DFMA peak measured by tools/fp64_peak.cu; roofline_elect and
+             roofline_rep are the same figure for the electrostatics and exchange-repulsion kernels
+cpu_baseline / --impl reference = the oracle port (NumPy + BLAS restatement with the reference's cost structure: LU
+             inverse + 2 DGEMM per mode, per-fragment integrals) farmed frame by frame over os.cpu_count() worker
+             processes with one BLAS thread each -- the pp.Server(ncpus) model of util/slv_md-run:96-97, 155-169.
 """
 import argparse
 import json
@@ -28,25 +33,32 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-MODE = 8
 CUTS = (40.0, 17.0, 12.0)
+HEADLINE = 3
 
-# BASELINE.json configs that fit one GPU; 2 is the configuration the metric is quoted on.
+# BASELINE.json configs that fit one GPU; 3 is the configuration the metric is quoted on at 1/2/4/8 GPUs.
 WORKLOADS = {
     2: dict(name='NMA-d7 + %(n)d waters, SolEFP elect(MEA+EA+corr)+pol', solute='nma-d7', solvents=['water'], nsolv=500, mode=8,
             flags=dict(elect=True, corr=True, pol=True), frames=10000, spacing=5.87, seed=2),
     3: dict(name='MeSCN in 50/50 water/DMSO (%(n)d fragments), full SolEFP elect+pol+rep+disp', solute='mescn',
             solvents=['water', 'dmso'], nsolv=400, mode=4, flags=dict(elect=True, corr=True, pol=True, rep=True, disp=True),
             frames=10000, spacing=9.5, seed=3, jit_lattice=0.3),
+    4: dict(name='protein-like: MeSCN probe among %(n)d mixed EFP fragments incl. charged ones, full SolEFP, remove_clashes',
+            solute='mescn', solvents=['water', 'mecoo-', 'menh3+', 'meoh', 'methane', 'phenol', 'benzene', 'chonh2', 'nma'],
+            nsolv=2000, mode=4, flags=dict(elect=True, corr=True, pol=True, rep=True, disp=True), frames=1000, spacing=8.5,
+            seed=4, jit_lattice=0.3, cuts=(45.0, 16.0, 13.0), remove_clashes=True, unique=50, rmin=3.5),
     5: dict(name='NMA + %(n)d waters, full SolEFP elect+pol+rep+disp', solute='nma', solvents=['water'], nsolv=4000, mode=8,
             flags=dict(elect=True, corr=True, pol=True, rep=True, disp=True), frames=2000, spacing=5.87, seed=5),
 }
-FLOPS_PER_T_PAIR = 49.0      # one (centre, centre) dipole-tensor apply to two vectors: R 3, r^2 5, rsqrt 1, powers 4,
-                             # two dots 10, two scalings 2, six accumulations x 4 (DESIGN.md "k_pol")
-FLOPS_PER_FIELD_PAIR = 123.0  # one (centre, site) multipole field through octupoles (slv::site_field_acc, counted)
-POL_DRAM_BYTES_PER_FRAME = (86.834688e6 + 346.631424e6) / 1184.0   # ncu capture of k_pol, profiles/k_pol_r01h_ncu.txt
-SWEEP_BODY_TFLOPS = 20.5     # algorithmic TFLOP/s of the k_pol sweep loop run alone (profiles/sweep_peak_r01.json, two rows/thread)
-FLOPS_PER_ELECT_PAIR = 300.0  # one (solute site, solvent site) pair through R^-4 with two moment sets + corrections
+# Algorithmic FP64 flop counts (frozen): FMA = 2, the reciprocal square root = 1.
+FLOPS_PER_T_PAIR = 49.0       # k_pol sweep: one (centre, centre) dipole-tensor apply to two vectors: R 3, r^2 5, rsqrt 1,
+                              # powers 4, two dots 10, two scalings 2, six accumulations x 4
+FLOPS_PER_FIELD_PAIR = 123.0  # k_pol fields: one (centre, site) multipole field through octupoles (slv::site_field_acc)
+FLOPS_PER_ELECT_PAIR = 248.0  # k_frame_elect: one (solute site, solvent site) pair through R^-4: slv::pair_potentials 154
+                              # (R 3, r^2 5, rsqrt + powers 5, RR 6, RRR 10, mu.R 5, Theta.R 15, R.Theta.R 5, Omega:RRR 21,
+                              # potential 7, field 23, field gradient 34, second gradient 11, charge-only gradient 4) + the
+                              # contraction with the two SolCAMM moment sets and the two correction vectors 94
+SWEEP_BODY_TFLOPS = 20.5      # algorithmic TFLOP/s of the k_pol sweep loop run alone (profiles/sweep_peak_r01.json)
 
 
 def parse():
@@ -55,12 +67,20 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
-    ap.add_argument('--config', type=int, default=2, choices=sorted(WORKLOADS), help='BASELINE.json config number')
+    ap.add_argument('--config', type=int, default=HEADLINE, choices=sorted(WORKLOADS), help='BASELINE.json config number')
+    ap.add_argument('--only', action='store_true', help='no nested config 2 / config 5 sub-records')
     ap.add_argument('--frames', type=int, default=0, help='frames per GPU per step (0 = the config default)')
-    ap.add_argument('--waters', type=int, default=0, help='solvent fragments (0 = the config default)')
-    ap.add_argument('--unique', type=int, default=250, help='distinct generated frames (tiled up to --frames)')
-    ap.add_argument('--cpu-sample', type=int, default=3, help='frames of the cpu_baseline sample')
+    ap.add_argument('--fragments', '--waters', dest='waters', type=int, default=0, help='solvent fragments (0 = the config default)')
+    ap.add_argument('--unique', type=int, default=0, help='distinct generated frames, tiled up to --frames (0 = config default, 250)')
+    ap.add_argument('--cpu-frames', type=int, default=0, help='frames of the cpu_baseline sample (0 = one per worker process)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     return ap.parse_args()
+
+
+def workload_string(cfg, nw, nframes):
+    wl = WORKLOADS[cfg]; cuts = wl.get('cuts', CUTS)
+    return (wl['name'] % dict(n=nw)) + ', mode %d, ccut/pcut/ecut %g/%g/%g Bohr, %d frames per GPU per step' % (
+        wl['mode'], cuts[0], cuts[1], cuts[2], nframes)
 
 
 def make_frames(wl, nw, nunique, nframes, rank):
@@ -72,7 +92,7 @@ def make_frames(wl, nw, nunique, nframes, rank):
     types = np.random.default_rng(wl['seed']).integers(0, len(solv), nw) if len(solv) > 1 else np.zeros(nw, int)
     nu = min(nunique, nframes)
     X = synth.make_trajectory(sol.get_pos(), [f.get_pos() for f in solv], types, nu, seed=wl['seed'] + 1000 * rank,
-                              spacing=wl['spacing'], jit_lattice=wl.get('jit_lattice', 0.6))
+                              spacing=wl['spacing'], jit_lattice=wl.get('jit_lattice', 0.6), rmin=wl.get('rmin', 3.0))
     reps = (nframes + nu - 1) // nu
     X = np.concatenate([X] * reps)[:nframes]
     ind = [0] + [1 + int(t) for t in types]
@@ -107,84 +127,177 @@ class ClockSampler(threading.Thread):
                     samples=len(s))
 
 
-def cpu_reference_frames(wl, bsm, ind, nmol, X, nsample):
-    """Oracle port timed on the host cores: returns (frames/s, seconds, nframes)."""
+# ------------------------------------------------------------------------------------------ CPU arm (oracle port)
+_W = {}
+
+
+def _cpu_worker_init(cfg, nw):
+    """Worker process of the CPU farm: one BLAS/OpenMP thread, its own copy of the parameters (the reference pickles the
+    whole EFP object into every pp job, util/slv_md-run:155-169)."""
+    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMEXPR_NUM_THREADS'):
+        os.environ[k] = '1'
+    try:
+        from threadpoolctl import threadpool_limits
+        _W['limit'] = threadpool_limits(1)
+    except Exception:
+        pass
+    wl = WORKLOADS[cfg]
+    bsm, ind, nmol, X = make_frames(wl, nw, 1, 1, 0)
+    _W.update(wl=wl, pars=[b.get() for b in bsm], ind=ind, nmol=nmol, nt=len(bsm))
+    if wl.get('remove_clashes'):
+        from slv_b200.solefp import EFP
+        names = set(EFP._RCL_BASE + ['Acetamide'] + EFP._RCL_POLAR + EFP._RCL_IONS + ['Methyl Sulphate (VI) -1 anion'])
+        _W['removable'] = set(t for t, p in enumerate(_W['pars']) if t != 0 and p.get('name') in names)
+
+
+def _cpu_worker_frame(xyz):
     from oracle import solefp_oracle as O
-    pars = [b.get() for b in bsm]
-    nt = len(bsm)
-    fl = wl['flags']
+    wl = _W['wl']; fl = wl['flags']; nt = _W['nt']
     t0 = time.time()
-    for f in range(nsample):
-        O.eval_frame(X[f % len(X)], ind, nmol, pars, [None] * nt, [None] * nt, wl['mode'], *CUTS,
-                     elect=True, ea=True, corr=True, pol=fl.get('pol', False), disp=fl.get('disp', False),
-                     rep=fl.get('rep', False), literal_gemm=True)
-    dt = time.time() - t0
-    return nsample / dt, dt, nsample
+    O.eval_frame(xyz, _W['ind'], _W['nmol'], _W['pars'], [None] * nt, [None] * nt, wl['mode'], *wl.get('cuts', CUTS),
+                 elect=True, ea=True, corr=True, pol=fl.get('pol', False), disp=fl.get('disp', False),
+                 rep=fl.get('rep', False), literal_gemm=True, removable=_W.get('removable'))
+    return time.time() - t0
+
+
+class CpuFarm(object):
+    """Frames farmed over worker processes (spawned, so that each imports NumPy with a single BLAS thread whatever the
+    parent's environment says -- torchrun exports OMP_NUM_THREADS=1 to the ranks, and a fork would inherit the parent's
+    already-sized thread pools)."""
+
+    def __init__(self, cfg, nw, nproc=None):
+        import multiprocessing as mp
+        try:
+            avail = len(os.sched_getaffinity(0))
+        except AttributeError:
+            avail = os.cpu_count() or 1
+        self.nproc = nproc or max(1, avail)
+        env_keep = dict((k, os.environ.get(k)) for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'))
+        for k in env_keep:
+            os.environ[k] = '1'                      # inherited by the spawned workers
+        try:
+            self.pool = mp.get_context('spawn').Pool(self.nproc, initializer=_cpu_worker_init, initargs=(cfg, nw))
+            self.pool.map(_noop, range(self.nproc))   # workers up and initialised before anything is timed
+        finally:
+            for k, v in env_keep.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+    def run(self, frames):
+        """Evaluate the frames; returns (wall seconds, per-frame worker seconds)."""
+        t0 = time.time()
+        per = self.pool.map(_cpu_worker_frame, list(frames), chunksize=1)
+        return time.time() - t0, per
+
+    def close(self):
+        self.pool.close(); self.pool.join()
+
+
+def _noop(_):
+    return os.getpid()
+
+
+def cpu_sample_record(cfg, nw, X, nframes_sample):
+    """cpu_baseline object for the main JSON line: a bounded sample of the workload's frames on all host cores."""
+    farm = CpuFarm(cfg, nw)
+    n = nframes_sample or farm.nproc
+    wall, per = farm.run([X[f % len(X)] for f in range(n)])
+    farm.close()
+    return dict(value=n / wall, unit='frames/s', cores=farm.nproc, kind='port',
+                sample='%d frames of the same workload farmed over %d single-threaded worker processes in %.1f s (%.1f s per frame '
+                       'per core); NumPy/BLAS oracle with the reference cost structure (LU inverse + 2 DGEMM per mode, '
+                       'per-fragment AO integrals)' % (n, farm.nproc, wall, sum(per) / len(per)))
 
 
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    wl = WORKLOADS[a.config]; nw = a.waters or wl['nsolv']
-    bsm, ind, nmol, X = make_frames(wl, nw, 8, 8, 0)
-    per_step = 1
+    cfg = a.config; wl = WORKLOADS[cfg]; nw = a.waters or wl['nsolv']; nframes = a.frames or wl['frames']
+    farm = CpuFarm(cfg, nw)
+    per_step = a.cpu_frames or farm.nproc
+    nu = min(4 * per_step, 64)
+    bsm, ind, nmol, X = make_frames(wl, nw, nu, nu, 0)
+    k = 0
     for _ in range(a.warmup):
-        cpu_reference_frames(wl, bsm, ind, nmol, X, per_step)
+        farm.run([X[(k + f) % nu] for f in range(per_step)]); k += per_step
     t0 = time.time()
-    for s in range(a.steps):
-        cpu_reference_frames(wl, bsm, ind, nmol, X[s % len(X):], per_step)
+    per_all = []
+    for _ in range(a.steps):
+        _, per = farm.run([X[(k + f) % nu] for f in range(per_step)]); k += per_step
+        per_all += per
     dt = time.time() - t0
+    farm.close()
     fps = a.steps * per_step / dt
-    cores = os.cpu_count()
+    sample = ('%d frames per step (one per worker process) of the same synthetic workload, farmed over %d single-threaded '
+              'worker processes like pp.Server(ncpus) in util/slv_md-run; %.1f s per frame per core; NumPy/BLAS restatement with '
+              'the reference cost structure (LU inverse + 2 DGEMM per mode, per-fragment AO integrals)'
+              % (per_step, farm.nproc, sum(per_all) / max(1, len(per_all))))
     line = dict(metric='md_frames_per_sec', value=fps, unit='frames/s', n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                 ms_per_step=dt / a.steps * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
                 data='synthetic', impl='reference',
-                config=dict(workload=(wl['name'] % dict(n=nw)) + ', mode %d, ccut/pcut/ecut 40/17/12 Bohr' % wl['mode'],
-                            baseline_config=a.config, frames_per_step=per_step),
-                cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port',
-                                  sample='%d frame(s) per step of the same synthetic workload; NumPy/BLAS restatement with the '
-                                         'reference cost structure (LU inverse + 2 DGEMM per mode)' % per_step),
+                config=dict(workload=workload_string(cfg, nw, nframes), baseline_config=cfg),
+                cpu_baseline=dict(value=fps, unit='frames/s', cores=farm.nproc, kind='port', sample=sample),
                 e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
 
-def main():
-    a = parse()
-    if a.impl == 'reference':
-        return run_reference(a)
+# ------------------------------------------------------------------------------------------ GPU arm
+def fp64_peak():
+    peak, src = 34.0, 'fallback 34.0 TFLOP/s (148 SM x 64 DFMA x 1.965 GHz x 0.91)'
+    for name in ('fp64_peak_r02.json', 'fp64_peak_r01.json'):
+        pk = os.path.join(ROOT, 'profiles', name)
+        if os.path.isfile(pk):
+            peak = json.load(open(pk))['fp64_dfma_tflops']
+            src = 'tools/fp64_peak.cu DFMA micro-benchmark on this pool (profiles/%s); MEASURED_PEAKS.json carries no FP64 figure' % name
+            break
+    return peak, src
+
+
+def ncu_traffic(kernel, cfg):
+    """DRAM bytes per frame of one kernel from the committed ncu --set full capture (profiles/ncu_traffic.json, written by
+    tools/ncu_traffic.py from the .ncu-rep of the same bench command), or None."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if not os.path.isfile(p):
+        return None, None
+    t = json.load(open(p)).get('config%d' % cfg, {}).get(kernel)
+    if not t:
+        return None, None
+    return t['dram_bytes_per_frame'], t['source']
+
+
+def run_config(cfg, a, steps, warmup, world, rank, dev, with_cpu, sampler=None):
+    """One complete measurement of a workload: device-resident value, e2e through the public call, per-kernel times,
+    rooflines.  Returns the record (rank 0) or None."""
     import numpy as np
     import torch
     import torch.distributed as dist
     from slv_b200 import _lib
     from slv_b200.solefp import EFP
-
-    world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    wl = WORKLOADS[a.config]
-    nw = a.waters or wl['nsolv']; nframes = a.frames or wl['frames']
-    bsm, ind, nmol, X = make_frames(wl, nw, a.unique, nframes, rank)
+    wl = WORKLOADS[cfg]
+    cuts = wl.get('cuts', CUTS)
+    main = cfg == a.config
+    nw = (a.waters if main else 0) or wl['nsolv']; nframes = (a.frames if main else 0) or wl['frames']
+    nunique = (a.unique if main else 0) or wl.get('unique', 250)
+    bsm, ind, nmol, X = make_frames(wl, nw, nunique, nframes, rank)
     nt = len(bsm)
-    efp = EFP(freq=True, mode=wl['mode'], ccut=CUTS[0], pcut=CUTS[1], ecut=CUTS[2], cunit=True, **wl['flags'])
+    efp = EFP(freq=True, mode=wl['mode'], ccut=cuts[0], pcut=cuts[1], ecut=cuts[2], cunit=True, **wl['flags'])
     efp.max_chunk = min(nframes, 10240)
+    efp.set(X[0], ind, nmol, bsm, [None] * nt, [None] * nt)
+    if wl.get('remove_clashes'):
+        efp._removable = efp._removable_types('remove_by_name', False, False)
     d_coords = torch.from_numpy(X).to(dev)
     h_coords = torch.from_numpy(X).pin_memory()
     nf = d_coords.shape[0]
     rows = torch.empty((nf, _lib.NOUT), dtype=torch.float64, device=dev)
     status = torch.empty((nf,), dtype=torch.int32, device=dev)
     gathered = [torch.empty_like(rows) for _ in range(world)] if world > 1 and rank == 0 else None
-    plan = None
+    plan = efp._get_plan()
 
     def step_device():
-        nonlocal plan
-        r, s = efp.eval_frames(d_coords, ind, nmol, bsm, [None] * nt, [None] * nt) if plan is None else plan.eval_device(d_coords, rows, status)
-        if plan is None:
-            plan = efp._get_plan()
-            rows.copy_(r); status.copy_(s)
+        plan.eval_device(d_coords, rows, status)
         if world > 1:
             dist.gather(rows, gathered, dst=0)      # the path's one collective: per-frame rows to rank 0
 
@@ -193,24 +306,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(a.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_device()
     barrier()
     launches_per_step = plan.last_launches()
-    sampler = ClockSampler(local); sampler.start()
     # ---- device-resident timing
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
     plan.set_timing(True)
     e0.record()
-    for _ in range(a.steps):
+    for _ in range(steps):
         step_device()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     ktimes = plan.get_timing()
     plan.set_timing(False)
-    ms_pol = ktimes['k_pol'][0]; ms_nopol = ktimes['k_frame_elect'][0]
     # ---- end-to-end: host pinned coordinates -> rows on the host
     h_rows = torch.empty((nf, _lib.NOUT), dtype=torch.float64).pin_memory()
     h_status = torch.empty((nf,), dtype=torch.int32).pin_memory()
@@ -218,64 +329,124 @@ def main():
         efp.eval_frames(h_coords, out=h_rows, status=h_status)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
+    for _ in range(steps):
         efp.eval_frames(h_coords, out=h_rows, status=h_status)     # the public call: pinned host in, host rows out
     barrier()
     e2e_s = time.perf_counter() - t0
-    sampler.stop_flag = True; sampler.join(timeout=2)
 
-    t = torch.tensor([ms, ms_nopol, e2e_s, ms_pol], dtype=torch.float64, device=dev)
+    kn = ('k_frame_elect', 'k_disp', 'k_pol', 'k_rep')
+    t = torch.tensor([ms, e2e_s] + [ktimes[k][0] for k in kn], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_nopol, e2e_s, ms_pol = [float(v) for v in t.cpu()]
+    tv = [float(v) for v in t.cpu()]
+    ms, e2e_s = tv[0], tv[1]
+    kms = dict((k, tv[2 + i] / steps) for i, k in enumerate(kn))
     r = rows.cpu().numpy()
     st = int(status.max().item())
+    same = bool((h_rows.numpy() == r).all())          # the host entry computes the same rows bit for bit
+    del d_coords, h_coords, rows, status
+    efp._plan = None; del plan
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    total_frames = nf * world
+    fps = total_frames * steps / (ms * 1e-3)
+    O = _lib.OUT
+    npol = r[:, O['n_pol']]; nel = r[:, O['n_elect']]; nrep = r[:, O['n_rep']]; its = r[:, O['pol_iters']]
+    ncent = r[:, O['pol_ncent']]; nsite = r[:, O['pol_nsite']]; tpairs = r[:, O['pol_pairs']]
+    peak, peak_src = fp64_peak()
+    step_ms = ms / steps
+    rec = dict(
+        value=fps, unit='frames/s', ms_per_step=step_ms,
+        e2e=dict(value=total_frames * steps / e2e_s, unit='frames/s', h2d_bytes_per_step=int(X.nbytes),
+                 d2h_bytes_per_step=int(nf * (_lib.NOUT * 8 + 4)), rows_identical_to_device_path=same),
+        config=dict(workload=workload_string(cfg, nw, nf), baseline_config=cfg),
+        detail=dict(frames_per_gpu=nf, l2='inputs larger than L2 (%.0f MB of coordinates per step)' % (X.nbytes / 1e6),
+                    distinct_frames='%d generated geometries tiled to %d frames: iteration counts and ragged list sizes sample '
+                                    '%d configurations, no work is skipped' % (min(nunique, nf), nf, min(nunique, nf)),
+                    parallelism='frames sharded over %d rank(s), one gather of the result rows' % world,
+                    mean_fragments_in_ccut=float(nel.mean()), mean_fragments_in_pcut=float(npol.mean()),
+                    mean_fragments_in_ecut=float(nrep.mean()), mean_pol_iters=float(its.mean()), status_max=st,
+                    kernel_ms_per_step=kms, sum_kernel_ms=sum(kms.values()),
+                    overlap='ms_per_step / sum of kernel ms = %.3f' % (step_ms / max(1e-9, sum(kms.values())))),
+        gpu_launches=int(launches_per_step * steps))
+    # ---- rooflines: algorithmic flops of a kernel / its own event-timed duration
+    pol_flops = float((its * tpairs * FLOPS_PER_T_PAIR + ncent * nsite * FLOPS_PER_FIELD_PAIR).sum())
+    if kms['k_pol'] > 0:
+        ach = pol_flops / (kms['k_pol'] * 1e-3) / 1e12
+        tr, trs = ncu_traffic('k_pol', cfg)
+        rec['roofline'] = dict(bound='fp64', kernel='k_pol', achieved=ach, peak=peak, unit='TFLOP/s', frac=ach / peak,
+                               traffic=(tr * nf if tr else None), traffic_source=trs, peak_source=peak_src,
+                               ceiling=dict(achieved_by='tools/sweep_peak.cu: the sweep body alone (no solver phases) at the kernel launch shape',
+                                            alg_tflops=SWEEP_BODY_TFLOPS, frac_of_ceiling=ach / SWEEP_BODY_TFLOPS),
+                               flops_per_step=pol_flops, ms_per_step=kms['k_pol'], share_of_step=kms['k_pol'] / step_ms)
+    ndma_c = int(bsm[0].get()['ndma'])
+    ndma_s = float(np.mean([bsm[i].get()['ndma'] for i in ind[1:]]))
+    elect_pairs = float((ndma_c * ndma_s * nel).sum())
+    ea = elect_pairs * FLOPS_PER_ELECT_PAIR / (kms['k_frame_elect'] * 1e-3) / 1e12
+    rec['roofline_elect'] = dict(bound='fp64', kernel='k_frame_elect', achieved=ea, peak=peak, unit='TFLOP/s', frac=ea / peak,
+                                 flops_per_pair=FLOPS_PER_ELECT_PAIR, pairs_per_step=elect_pairs, ms_per_step=kms['k_frame_elect'],
+                                 hbm_gbs=(X.nbytes + nf * _lib.NOUT * 8) / (kms['k_frame_elect'] * 1e-3) / 1e9,
+                                 note='superimposition (Kabsch) and moment rotation of every instance are inside this kernel and '
+                                      'not in the flop count; HBM traffic is the coordinates once: far below the HBM roofline')
+    rec['pair_interactions_per_sec'] = elect_pairs * world * steps / (ms * 1e-3)
+    rec['pol_tensor_pairs_per_sec'] = float((its * tpairs).sum()) * world * steps / (ms * 1e-3)
+    if kms['k_rep'] > 0:
+        # half transform X = V C_B^T (4 integral kinds) and LMO integrals C_A X (6 products) per (solute, fragment) pair
+        pa = bsm[0].get(); nbA, nmA = int(pa['nbasis']), int(pa['nmos'])
+        per_type = [8.0 * nbA * b.get()['nbasis'] * b.get()['nmos'] + 12.0 * nmA * b.get()['nmos'] * nbA for b in bsm[1:]]
+        import collections
+        cnt = collections.Counter(ind[1:])
+        mean_flop = sum(per_type[t - 1] * c for t, c in cnt.items()) / float(len(ind) - 1)
+        rep_pairs = float(nrep.sum())
+        ra = rep_pairs * mean_flop / (kms['k_rep'] * 1e-3) / 1e12
+        rec['roofline_rep'] = dict(bound='fp64', kernel='k_rep_* (integrals + transform + CALCFI)', achieved=ra, peak=peak, unit='TFLOP/s',
+                                   frac=ra / peak, fragment_pairs_per_step=rep_pairs, fragment_pairs_per_sec=rep_pairs * world * steps / (ms * 1e-3),
+                                   transform_flops_per_pair=mean_flop, ms_per_step=kms['k_rep'],
+                                   note='flops count only the AO->LMO transform (8 nbsA nbsB nmosB + 12 nmosA nmosB nbsA per pair, type-averaged); '
+                                        'the Obara-Saika integrals and CALCFI are not counted')
+    if with_cpu:
+        rec['cpu_baseline'] = cpu_sample_record(cfg, nw, X, a.cpu_frames)
+    return rec
+
+
+def main():
+    a = parse()
+    if a.impl == 'reference':
+        return run_reference(a)
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    sampler = ClockSampler(local); sampler.start()
+    rec = run_config(a.config, a, a.steps, a.warmup, world, rank, dev, with_cpu=False)
+    sub = {}
+    if not a.only and a.config == HEADLINE:
+        for c in (2, 5):
+            s = run_config(c, a, max(2, a.steps // 2), 3, world, rank, dev, with_cpu=False)
+            if s is not None:
+                sub['config%d' % c] = s
+    sampler.stop_flag = True; sampler.join(timeout=2)
     if rank == 0:
-        total_frames = nf * world
-        fps = total_frames * a.steps / (ms * 1e-3)
-        npol = r[:, _lib.OUT['n_pol']]; nel = r[:, _lib.OUT['n_elect']]; its = r[:, _lib.OUT['pol_iters']]
-        ncent = r[:, _lib.OUT['pol_ncent']]; nsite = r[:, _lib.OUT['pol_nsite']]; tpairs = r[:, _lib.OUT['pol_pairs']]
-        pol_flops = float((its * tpairs * FLOPS_PER_T_PAIR + ncent * nsite * FLOPS_PER_FIELD_PAIR).sum())
-        pol_ms = max(ms_pol, 1e-9) / a.steps
-        ndma_c = int(bsm[0].get()['ndma'])
-        ndma_s = float(np.mean([bsm[i].get()['ndma'] for i in ind[1:]]))
-        elect_pairs = float((ndma_c * ndma_s * nel).sum())
-        peak = 34.0
-        pk = os.path.join(ROOT, 'profiles', 'fp64_peak_r01.json')
-        if os.path.isfile(pk):
-            peak = json.load(open(pk))['fp64_dfma_tflops']
-        achieved = pol_flops / (pol_ms * 1e-3) / 1e12
-        hbm = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.isfile(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
-        cpu_fps, cpu_dt, cpu_n = cpu_reference_frames(wl, bsm, ind, nmol, X, a.cpu_sample)
-        line = dict(
-            metric='md_frames_per_sec', value=fps, unit='frames/s', n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
-            ms_per_step=ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
-            config=dict(workload=(wl['name'] % dict(n=nw)) + ', mode %d, ccut/pcut/ecut 40/17/12 Bohr, %d frames per GPU per step' % (wl['mode'], nf),
-                        baseline_config=a.config, frames_per_gpu=nf, l2='inputs larger than L2 (%.0f MB of coordinates per step)' % (X.nbytes / 1e6),
-                        parallelism='frames sharded over %d rank(s), one gather of the result rows' % world,
-                        mean_fragments_in_pcut=float(npol.mean()), mean_pol_iters=float(its.mean()), status_max=st,
-                        kernel_ms_per_step=dict((k, v[0] / a.steps) for k, v in ktimes.items())),
-            pair_interactions_per_sec=elect_pairs * world * a.steps / (ms * 1e-3),
-            pol_tensor_pairs_per_sec=float((its * tpairs).sum()) * world * a.steps / (ms * 1e-3),
-            gpu_launches=int(launches_per_step * a.steps + (1 if world > 1 else 0) * a.steps * 0),
-            clocks=sampler.summary(),
-            e2e=dict(value=total_frames * a.steps / e2e_s, unit='frames/s', h2d_bytes_per_step=int(X.nbytes),
-                     d2h_bytes_per_step=int(nf * (_lib.NOUT * 8 + 4))),
-            roofline=dict(bound='fp64', kernel='k_pol', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
-                          traffic=(POL_DRAM_BYTES_PER_FRAME * nf if a.config == 2 else None), traffic_source='ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_pol on 1184 '
-                          'frames of this workload (profiles/k_pol_r01h_ncu.txt), scaled per frame to this launch',
-                          ceiling=dict(achieved_by='tools/sweep_peak.cu: the sweep body alone (no solver phases) at the kernel launch shape',
-                                       alg_tflops=SWEEP_BODY_TFLOPS, frac_of_ceiling=achieved / SWEEP_BODY_TFLOPS),
-                          peak_source='tools/fp64_peak.cu DFMA micro-benchmark on this pool (profiles/fp64_peak_r01.json); '
-                          'MEASURED_PEAKS.json carries no FP64 figure',
-                          flops_per_step=pol_flops, ms_per_step=pol_ms, launches_per_step=ktimes['k_pol'][1] // a.steps, share_of_step=pol_ms / (ms / a.steps)),
-            roofline_stream=dict(bound='hbm', kernel='k_frame_elect', achieved=(X.nbytes + nf * 128) / (ms_nopol / a.steps * 1e-3) / 1e9,
-                                 peak=hbm, unit='GB/s', note='coordinate streaming kernel is FP64-bound by the pair work, not HBM-bound'),
-            cpu_baseline=dict(value=cpu_fps, unit='frames/s', cores=os.cpu_count(), kind='port',
-                              sample='%d frames of the same workload in %.1f s (NumPy/BLAS oracle with the reference cost '
-                                     'structure: LU inverse + 2 DGEMM per mode)' % (cpu_n, cpu_dt)))
+        wl = WORKLOADS[a.config]
+        line = dict(metric='md_frames_per_sec', value=rec.pop('value'), unit=rec.pop('unit'), n_gpus=world, steps=a.steps,
+                    warmup=max(a.warmup, 3), ms_per_step=rec.pop('ms_per_step'), higher_is_better=True, scaling='weak',
+                    vs_baseline=None, dtype='f64', data='synthetic')
+        line.update(rec)
+        line['clocks'] = sampler.summary()
+        if sub:
+            line['configs'] = sub
+        if not a.no_cpu and world == 1:          # rank 0 at N=1 only
+            nw = a.waters or wl['nsolv']
+            _, _, _, X = make_frames(wl, nw, 64, 64, 0)
+            line['cpu_baseline'] = cpu_sample_record(a.config, nw, X, a.cpu_frames)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
