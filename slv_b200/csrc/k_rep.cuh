@@ -8,15 +8,17 @@
 // fi_m is linear in the mode quantities (S^m, T^m, fock1_m, lmoc1_m, lvec_m), so the plan's g-contracted tables
 // turn the 30-mode loop into one evaluation.  Per batch of frames (as many as the integral pool holds):
 //   k_rep_scan   exclusive scan of the per-frame counts of fragments inside ecut -> pair slots
-//   k_rep_prep   per frame: lab-frame solute atoms and displacement vectors; per (frame, fragment) pair: the
-//                fragment's atoms, and the pair -> (frame, list entry, type) map
-//   k_rep_ints   AO integrals V[pair][k][l][4] = S, T, L.dS, L.dT: one launch per (fragment type, sub-shell class),
-//                one thread per (pair, sub-shell-pair item), grid-wide -- every warp runs one specialisation of
-//                slv_ints.cuh with near-equal loop lengths, at full occupancy
-//   k_rep_pair   one CTA per (frame, fragment) pair:
-//                2  half transform  X[k][q][j] = sum_l V[k][l][q] C_B[j][l]
-//                3  LMO integrals   S_ij, T_ij, Sm_ij, Tm_ij
-//                4  CALCFI per (i,j), block sum -> res[pair]
+//   k_rep_prep   per frame: lab-frame solute atoms and displacement vectors, the solute's rotated AO->LMO coefficients
+//                in k-octet tiles; per (frame, fragment) pair: the fragment's atoms and the pair -> (frame, entry, type) map
+//   k_rep_ints   AO integrals V[pair][k][q][l] (q = S, T, L.dS, L.dT; rows padded to LP): one launch per (fragment
+//                type, sub-shell class), one thread per (pair, sub-shell-pair item), grid-wide -- every warp runs one
+//                specialisation of slv_ints.cuh with near-equal loop lengths
+//   k_rep_pair   one CTA per (frame, fragment) pair, one launch per fragment type.  The pair's integrals stream through
+//                shared memory in tiles of KT solute basis functions (one cp.async.bulk per tile, completion on an
+//                mbarrier, the next tile in flight while the current one is consumed); per tile
+//                  A  X[(k,q)][j] = sum_l V[(k,q)][l] C_B[j][l]        FP64 tensor cores (mma.sync m8n8k4), operands in smem
+//                  B  S_ij, T_ij, Sm_ij, Tm_ij += C_A / C1_A [i][k] X[k][q][j]   FP64 tensor cores, accumulators in registers
+//                then CALCFI from distance tables (every centroid / atom distance evaluated once) -> res[pair]
 //   k_rep_sum    rep_mea of a frame = -(sum of its pair results, in list order)
 // AO->LMO coefficients are rotated into the lab frame per fragment (VECROT, efprot.f:22-151): the solute's once per
 // frame (k_rep_prep), the fragment's in k_rep_pair.
@@ -31,23 +33,34 @@ namespace slv {
 
 constexpr int REP_THREADS = 128;
 constexpr int REP_INT_THREADS = 128;
+constexpr int REP_CS = 12;        // row stride (doubles) of a solute coefficient octet tile: 8 k's + 4 pad, == 4 (mod 8)
+constexpr int REP_MAX_NIT = 3;    // solute LMO tiles of 8 (nmos <= 24)
+constexpr int REP_MAX_NNT = 5;    // fragment LMO tiles of 8 (nmos <= 40)
+
+// Row length (doubles) of the integral records of a fragment with nbs basis functions: a multiple of 4 that is 4 modulo 8,
+// so that the eight rows of a tensor-core A fragment fall on distinct shared-memory banks whatever the tile offset.
+__host__ __device__ inline int rep_lp(int nbs) {
+  int lp = (nbs + 3) & ~3;
+  if ((lp & 7) != 4) lp += 4;
+  return lp;
+}
 
 struct RepPool {            // one batch of (frame, fragment) pairs (V .. pair_type) + per-frame tables of the chunk
-  double *V;       // [pair_cap][nbsA][max_nbas][4]  AO integrals
+  double *V;       // [pair_cap][nbsA16][4][LP(type)]  AO integrals, block stride sV
   double *posA;    // [max_chunk][natA][3]   solute atoms, lab frame
   double *LcA;     // [max_chunk][natA][3]   mode-contracted displacement vectors, lab frame
   double *riA;     // [max_chunk][2][nmosA][3]  LMO centroids and their mode-contracted derivatives
-  double *CA;      // [max_chunk][2][nmosA][nbsA]  rotated vecl and g-contracted vecl1 of the solute
+  double *CA;      // [max_chunk][nbsA16/8][2][IP][REP_CS]  rotated vecl / g-contracted vecl1 of the solute in k-octet tiles
   double *posB;    // [pair_cap][max_nat][3]
   double *res;     // [pair_cap]  sum_ij fi of the pair
   int *pair_frame, *pair_entry, *pair_type;   // [pair_cap]
   int *pair0;      // [max_chunk + 1] exclusive scan of the per-frame pair counts
-  size_t sV;
-  int pair_cap, max_nat;
+  size_t sV, sCA;
+  int pair_cap, max_nat, nbsA16, IP;
 };
 
 // Two pools (the batches alternate between two streams, so the integral kernels of one batch overlap the
-// latency-bound transform kernel of the previous one); the per-frame tables are shared.  rep_alloc creates the
+// transform kernel of the previous one); the per-frame tables are shared.  rep_alloc creates the
 // per-frame tables and fixes the largest pool the plan may use; the pools themselves grow on demand (rep_reserve),
 // so a plan that only ever sees a few fragments inside ecut does not hold gigabytes.
 struct RepLimits { size_t max_pairs = 0; };
@@ -55,7 +68,9 @@ struct RepLimits { size_t max_pairs = 0; };
 inline int rep_alloc(RepPool rp[2], RepLimits &lim, std::vector<void *> &allocs, std::string &err, int nmosc, int nbasc,
                      int natc, int max_nbas, int max_nat, int max_chunk, int list_cap) {
   // integral pools: together up to 8 GiB and at most a quarter of the free memory, never more than the worst case
-  const size_t sV = (size_t)nbasc * max_nbas * 4;
+  const int nbsA16 = (nbasc + 15) & ~15, IP = (nmosc + 7) & ~7;
+  const size_t sV = (size_t)nbsA16 * 4 * rep_lp(max_nbas);
+  const size_t sCA = (size_t)(nbsA16 / 8) * 2 * IP * REP_CS;
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   size_t budget = (size_t)8 << 30;
@@ -77,18 +92,23 @@ inline int rep_alloc(RepPool rp[2], RepLimits &lim, std::vector<void *> &allocs,
   RA(rp[0].posA, (size_t)max_chunk * natc * 3, double)
   RA(rp[0].LcA, (size_t)max_chunk * natc * 3, double)
   RA(rp[0].riA, (size_t)max_chunk * nmosc * 6, double)
-  RA(rp[0].CA, (size_t)max_chunk * 2 * nmosc * nbasc, double)
+  RA(rp[0].CA, (size_t)max_chunk * sCA, double)
   RA(rp[0].pair0, (size_t)max_chunk + 1, int)
 #undef RA
+  // the pad rows / columns of the coefficient tiles are never written again: they must be zero
+  if (cudaMemset(rp[0].CA, 0, (size_t)max_chunk * sCA * sizeof(double)) != cudaSuccess) { err = "cudaMemset(rep tables) failed"; return SLVGPU_ECUDA; }
   rp[1] = rp[0];
-  for (int h = 0; h < 2; ++h) { rp[h].sV = sV; rp[h].max_nat = max_nat; rp[h].pair_cap = 0; rp[h].V = nullptr; }
+  for (int h = 0; h < 2; ++h) {
+    rp[h].sV = sV; rp[h].sCA = sCA; rp[h].max_nat = max_nat; rp[h].pair_cap = 0; rp[h].V = nullptr; rp[h].nbsA16 = nbsA16; rp[h].IP = IP;
+    rp[h].posB = nullptr; rp[h].res = nullptr; rp[h].pair_frame = rp[h].pair_entry = rp[h].pair_type = nullptr;
+  }
   return 0;
 }
 
 inline void rep_pool_free(RepPool &r) {
-  if (r.pair_cap <= 0) return;
-  cudaFree(r.V); cudaFree(r.posB); cudaFree(r.res); cudaFree(r.pair_frame); cudaFree(r.pair_entry); cudaFree(r.pair_type);
-  r.V = nullptr; r.pair_cap = 0;
+  cudaFree(r.V); cudaFree(r.posB); cudaFree(r.res); cudaFree(r.pair_frame); cudaFree(r.pair_entry); cudaFree(r.pair_type);   // cudaFree(nullptr) is a no-op
+  r.V = nullptr; r.posB = nullptr; r.res = nullptr; r.pair_frame = r.pair_entry = r.pair_type = nullptr;
+  r.pair_cap = 0;
 }
 
 // make both pools hold at least `pairs` pairs (clamped to the plan's limit); the caller has synchronised the streams
@@ -99,23 +119,56 @@ inline int rep_reserve(RepPool rp[2], const RepLimits &lim, size_t pairs, std::s
   for (int h = 0; h < 2; ++h) {
     rep_pool_free(rp[h]);
     bool ok = cudaMalloc(&rp[h].V, pairs * rp[h].sV * sizeof(double)) == cudaSuccess;
+    // pad columns of the integral rows and the rows past the solute's last basis function are read by the tile loop
+    // (times zero coefficients): stale finite values are harmless, uninitialised NaN patterns are not
+    ok = ok && cudaMemset(rp[h].V, 0, pairs * rp[h].sV * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&rp[h].posB, pairs * rp[h].max_nat * 3 * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&rp[h].res, pairs * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&rp[h].pair_frame, pairs * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&rp[h].pair_entry, pairs * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&rp[h].pair_type, pairs * sizeof(int)) == cudaSuccess;
-    if (!ok) { err = "cudaMalloc(rep integral pool) failed"; return SLVGPU_ENOMEM; }
+    if (!ok) {                                     // leave no half-built pool behind (a retry starts from scratch)
+      cudaGetLastError();
+      for (int g = 0; g < 2; ++g) rep_pool_free(rp[g]);
+      err = "cudaMalloc(rep integral pool) failed";
+      return SLVGPU_ENOMEM;
+    }
     rp[h].pair_cap = (int)pairs;
   }
   return 0;
 }
 
-// shared memory of k_rep_pair: X tile [<= REP_THREADS rows x 5 LMOs][4] + CB[max_nmos][max_nbas] + IJ[4][nmosA][max_nmos]
-// + geometry
-inline size_t rep_smem_bytes(int nmosc, int nbasc, int max_nmos, int max_nbas, int natc, int max_nat) {
-  (void)nbasc;
-  return sizeof(double) * ((size_t)REP_THREADS * 4 * 5 + 32 + (size_t)max_nmos * max_nbas + (size_t)4 * nmosc * max_nmos
-                           + 6 * natc + 6 * nmosc + 3 * max_nat + 3 * max_nmos + 8);
+// ---- shared-memory plan of k_rep_pair for one fragment type
+struct RepSmem {
+  int KT, NNT, nbuf, LP, LK, JS, IP, nit;
+  int oV, oCA, oX, oCB, oIJ, oTab, oGeo, oBar;     // offsets in doubles
+  size_t bytes;
+};
+
+inline RepSmem rep_smem_plan(int nmosA, int nbsA, int natA, int nmosB, int nbsB, int natB) {
+  RepSmem s;
+  (void)nbsA;
+  s.LP = rep_lp(nbsB); s.LK = (nbsB + 3) & ~3;
+  s.NNT = (nmosB + 7) / 8; s.JS = 8 * s.NNT + 4;
+  s.IP = (nmosA + 7) & ~7; s.nit = s.IP / 8;
+  s.KT = (size_t)16 * 4 * s.LP * 8 <= 24 * 1024 ? 16 : 8;                     // tiles of 16 solute functions while they stay small
+  const size_t tileV = (size_t)s.KT * 4 * s.LP, tileCA = (size_t)(s.KT / 8) * 2 * s.IP * REP_CS, tileX = (size_t)4 * s.KT * s.JS;
+  const int nij = nmosA * nmosB;
+  const size_t fixed = 2 * tileX + (size_t)s.LK * s.JS + (size_t)4 * nij + (size_t)2 * nij + 4 * nmosB + 4 * nmosA
+                     + 6 * natA + 6 * nmosA + 3 * natB + 3 * nmosB + 8;
+  s.nbuf = (fixed + 2 * tileV + 3 * tileCA) * 8 <= (size_t)110 * 1024 ? 2 : 1;  // two tiles in flight when two CTAs still fit an SM
+  int o = 0;
+  s.oV = o; o += (int)(s.nbuf * tileV);
+  s.oCA = o; o += (int)((s.nbuf + 1) * tileCA);      // one coefficient buffer more than tiles in flight: phase B still reads the oldest
+  s.oX = o; o += (int)(2 * tileX);
+  s.oCB = o; o += s.LK * s.JS;
+  s.oIJ = o; o += 4 * nij;
+  s.oTab = o; o += 2 * nij + 4 * nmosB + 4 * nmosA;
+  s.oGeo = o; o += 6 * natA + 6 * nmosA + 3 * natB + 3 * nmosB;
+  o = (o + 1) & ~1;
+  s.oBar = o; o += 4;
+  s.bytes = (size_t)o * 8;
+  return s;
 }
 
 // exclusive scan of the number of fragments inside ecut (k_frame_elect wrote it to the result row) over the frames
@@ -140,18 +193,19 @@ __global__ void __launch_bounds__(1024) k_rep_scan(const double *__restrict__ ou
   if (tid == 1023) pair0[nf] = s_part[1023];
 }
 
-// rotate the AO->LMO rows of one fragment type: dst[i][k] for i < nrows, from src (body frame)
-__device__ inline void rotate_vecl_rows(const DevPlan &p, const int *tm, const double *src, int nrows, const double R[9], double *dst) {
+// rotate the AO->LMO rows of one fragment type into the lab frame (VECROT): s copy, p triples as vectors, d sextets as
+// symmetric tensors; one thread per leading element of a block; element (i, k) goes to dst[index(i, k)]
+template <class Index>
+__device__ inline void rotate_vecl_rows(const DevPlan &p, const int *tm, const double *src, int nrows, const double R[9], double *dst, Index index) {
   const int nb = tm[SLVGPU_M_NBASIS];
   const int *bl = p.itab + tm[SLVGPU_M_IO_BFL];
   for (int w = threadIdx.x; w < nrows * nb; w += blockDim.x) {
     const int i = w / nb, k = w % nb;
     const int lx = bl[k * 3], ly = bl[k * 3 + 1], lz = bl[k * 3 + 2], Ls = lx + ly + lz;
     const double *c = src + (size_t)i * nb + k;
-    double *d = dst + (size_t)i * nb + k;
-    if (Ls == 0) d[0] = c[0];
-    else if (Ls == 1 && lx == 1) { double v[3] = {c[0], c[1], c[2]}, o[3]; rot_vec(R, v, o); d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; }
-    else if (Ls == 2 && lx == 2) { double v[6] = {c[0], c[1], c[2], c[3], c[4], c[5]}, o[6]; rot_quad(R, v, o); for (int t = 0; t < 6; ++t) d[t] = o[t]; }
+    if (Ls == 0) dst[index(i, k)] = c[0];
+    else if (Ls == 1 && lx == 1) { double v[3] = {c[0], c[1], c[2]}, o[3]; rot_vec(R, v, o); for (int t = 0; t < 3; ++t) dst[index(i, k + t)] = o[t]; }
+    else if (Ls == 2 && lx == 2) { double v[6] = {c[0], c[1], c[2], c[3], c[4], c[5]}, o[6]; rot_quad(R, v, o); for (int t = 0; t < 6; ++t) dst[index(i, k + t)] = o[t]; }
   }
 }
 
@@ -173,7 +227,7 @@ __global__ void __launch_bounds__(128) k_rep_prep(const DevPlan p, int fs, Frame
       pa[0] = y[0] + t0[0]; pa[1] = y[1] + t0[1]; pa[2] = y[2] + t0[2];
       rot_vec(R0, p.dtab + p.sol_meta[SLVGPU_S_LVEC] + a * 3, rp.LcA + ((size_t)fi * natA + a) * 3);
     }
-    const int nmosA = tm0[SLVGPU_M_NMOS], nbsA = tm0[SLVGPU_M_NBASIS];
+    const int nmosA = tm0[SLVGPU_M_NMOS];
     double *ri = rp.riA + (size_t)fi * nmosA * 6;
     for (int i = tid; i < nmosA; i += NT) {
       double y[3];
@@ -181,9 +235,13 @@ __global__ void __launch_bounds__(128) k_rep_prep(const DevPlan p, int fs, Frame
       ri[i * 3] = y[0] + t0[0]; ri[i * 3 + 1] = y[1] + t0[1]; ri[i * 3 + 2] = y[2] + t0[2];
       rot_vec(R0, p.dtab + p.sol_meta[SLVGPU_S_LMOC1] + i * 3, ri + (size_t)nmosA * 3 + i * 3);
     }
-    double *ca = rp.CA + (size_t)fi * 2 * nmosA * nbsA;
-    rotate_vecl_rows(p, tm0, p.dtab + tm0[SLVGPU_M_O_VECL], nmosA, R0, ca);
-    rotate_vecl_rows(p, tm0, p.dtab + p.sol_meta[SLVGPU_S_VECL1], nmosA, R0, ca + (size_t)nmosA * nbsA);
+    // k-octet tiles [k / 8][vecl | vecl1][IP][REP_CS]: one contiguous block per tile of the transform kernel
+    double *ca = rp.CA + (size_t)fi * rp.sCA;
+    const int IP = rp.IP;
+    rotate_vecl_rows(p, tm0, p.dtab + tm0[SLVGPU_M_O_VECL], nmosA, R0, ca,
+                     [IP](int i, int k) { return ((size_t)(k >> 3) * 2 * IP + i) * REP_CS + (k & 7); });
+    rotate_vecl_rows(p, tm0, p.dtab + p.sol_meta[SLVGPU_S_VECL1], nmosA, R0, ca,
+                     [IP](int i, int k) { return (((size_t)(k >> 3) * 2 + 1) * IP + i) * REP_CS + (k & 7); });
   }
   const int nl = fl.nlist[fi];
   const size_t lbase = (size_t)fi * p.list_cap;
@@ -237,47 +295,77 @@ k_rep_ints(const DevPlan p, int type, int lo, int n_items, int npairs, RepPool r
                                   rp.posA + fa, rp.posB + (size_t)pr * rp.max_nat * 3,
                                   p.dtab + tm0[SLVGPU_M_O_BFEXP], p.dtab + tm0[SLVGPU_M_O_BFCOEF],
                                   p.dtab + tm[SLVGPU_M_O_BFEXP], p.dtab + tm[SLVGPU_M_O_BFCOEF],
-                                  rp.LcA + fa, nbsB, rp.V + (size_t)pr * rp.sV);
+                                  rp.LcA + fa, rep_lp(nbsB), rp.V + (size_t)pr * rp.sV);
 }
 
-// One CTA per (frame, fragment) pair: half transform, LMO integrals, CALCFI -> res[pair]
-#ifndef SLV_REP_PAIR_CTAS
-#define SLV_REP_PAIR_CTAS 4
-#endif
-__global__ void __launch_bounds__(REP_THREADS, SLV_REP_PAIR_CTAS)
-k_rep_pair(const DevPlan p, FrameLists fl, RepPool rp) {
+// ---- small PTX wrappers: FP64 tensor-core MMA, mbarrier, 1-D bulk asynchronous copy (TMA)
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n"
+               ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// One CTA per (frame, fragment) pair of fragment type `type`: half transform and LMO integrals on the FP64 tensor cores,
+// then CALCFI -> res[pair].  KT: solute basis functions per tile (8 or 16); NNT: fragment LMO tiles of 8.
+template <int KT, int NNT>
+__global__ void __launch_bounds__(REP_THREADS, NNT <= 2 ? 4 : 2)
+k_rep_pair(const DevPlan p, int type, FrameLists fl, RepPool rp, RepSmem L) {
   extern __shared__ double sm[];
   __shared__ double s_red[32];
-  const int tid = threadIdx.x, NT = blockDim.x;
+  const int tid = threadIdx.x, NT = REP_THREADS, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c4 = lane & 3;
   const int pr = blockIdx.x;
+  if (rp.pair_type[pr] != type) return;
   const int fi = rp.pair_frame[pr], e = rp.pair_entry[pr];
-  const int *tm0 = tmeta(p, p.inst_type[0]), *tm = tmeta(p, rp.pair_type[pr]);
+  const int *tm0 = tmeta(p, p.inst_type[0]), *tm = tmeta(p, type);
   const int natA = tm0[SLVGPU_M_NATOMS], nmosA = tm0[SLVGPU_M_NMOS], nbsA = tm0[SLVGPU_M_NBASIS];
   const int natB = tm[SLVGPU_M_NATOMS], nmosB = tm[SLVGPU_M_NMOS], nbsB = tm[SLVGPU_M_NBASIS];
   const int nij = nmosA * nmosB;
-  double *X = sm, *CBs = X + (size_t)REP_THREADS * 4 * 5 + 32, *IJ = CBs + (size_t)nmosB * nbsB;
-  double *posA = IJ + 4 * nij, *LcA = posA + 3 * natA, *riA = LcA + 3 * natA, *ri1A = riA + 3 * nmosA;
+  const int LP = L.LP, JS = L.JS, IP = L.IP, nit = L.nit;
+  double *Vt = sm + L.oV, *CAs = sm + L.oCA, *Xs = sm + L.oX, *CBs = sm + L.oCB, *IJ = sm + L.oIJ;
+  double *RI = sm + L.oTab, *RM = RI + nij, *col1 = RM + nij, *col2 = col1 + nmosB, *u3 = col2 + nmosB, *w3 = u3 + nmosB;
+  double *row1 = w3 + nmosB, *row2 = row1 + nmosA, *u4 = row2 + nmosA, *w4 = u4 + nmosA;
+  double *posA = sm + L.oGeo, *LcA = posA + 3 * natA, *riA = LcA + 3 * natA, *ri1A = riA + 3 * nmosA;
   double *posB = ri1A + 3 * nmosA, *riB = posB + 3 * natB;
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + L.oBar);
   const double *V = rp.V + (size_t)pr * rp.sV;
-  const double *CA = rp.CA + (size_t)fi * 2 * nmosA * nbsA, *CA1 = CA + (size_t)nmosA * nbsA;
-  const double *FA = p.dtab + tm0[SLVGPU_M_O_FOCK], *FA1 = p.dtab + p.sol_meta[SLVGPU_S_FOCK1], *ZA = p.dtab + tm0[SLVGPU_M_O_ZNUC];
-  // The pair's integrals were written by earlier kernels of the batch into a pool far larger than L2: rows are pulled
-  // into L2 two tiles ahead of the half transform (all of them at once would be 0.55 MB per DMSO pair x 3 CTAs x 148
-  // SMs -- more than L2 holds).
-  auto prefetch_rows = [&](int r0, int r1) {
-    r1 = min(r1, nbsA);
-    if (r0 >= r1) return;
-    const char *base = reinterpret_cast<const char *>(V) + (size_t)r0 * nbsB * 32;
-    const size_t bytes = (size_t)(r1 - r0) * nbsB * 32;
-    for (size_t b = (size_t)tid * 128; b < bytes; b += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + b));
+  const double *CAg = rp.CA + (size_t)fi * rp.sCA;
+  const int ntile = (nbsA + KT - 1) / KT;
+  const unsigned tileV_bytes = (unsigned)((size_t)KT * 4 * LP * sizeof(double));
+  const unsigned tileCA_doubles = (unsigned)((KT / 8) * 2 * IP * REP_CS);
+  const size_t tileV_doubles = (size_t)KT * 4 * LP, tileX = (size_t)4 * KT * JS;
+
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  // tile t -> V buffer t % nbuf, coefficient buffer t % (nbuf + 1), both completing on barrier t & 1
+  const int ncab = L.nbuf + 1;
+  auto issue = [&](int t) {
+    unsigned long long *b = bar + (t & 1);
+    mbar_expect_tx(b, tileV_bytes + tileCA_doubles * (unsigned)sizeof(double));
+    bulk_g2s(Vt + (size_t)(t % L.nbuf) * tileV_doubles, V + (size_t)t * tileV_doubles, tileV_bytes, b);
+    bulk_g2s(CAs + (size_t)(t % ncab) * tileCA_doubles, CAg + (size_t)t * tileCA_doubles, tileCA_doubles * (unsigned)sizeof(double), b);
   };
-  const int nblk0 = (nmosB + 4) / 5, KT0 = max(1, NT / nblk0);
-  prefetch_rows(0, 2 * KT0);
-  double R[9], t[3];
+  if (tid == 0) { issue(0); if (L.nbuf == 2 && ntile > 1) issue(1); }
+
+  // ---- geometry, the fragment's rotated AO->LMO coefficients, and the distance tables of CALCFI (while tile 0 is in flight)
+  double R[9], tr[3];
   {
     const double *xf = fl.list_xf + ((size_t)fi * p.list_cap + e) * 12;
     for (int d = 0; d < 9; ++d) R[d] = xf[d];
-    for (int d = 0; d < 3; ++d) t[d] = xf[9 + d];
+    for (int d = 0; d < 3; ++d) tr[d] = xf[9 + d];
   }
   for (int w = tid; w < natA * 3; w += NT) { posA[w] = rp.posA[(size_t)fi * natA * 3 + w]; LcA[w] = rp.LcA[(size_t)fi * natA * 3 + w]; }
   for (int w = tid; w < nmosA * 6; w += NT) riA[w] = rp.riA[(size_t)fi * nmosA * 6 + w];        // riA then ri1A, contiguous
@@ -285,128 +373,168 @@ k_rep_pair(const DevPlan p, FrameLists fl, RepPool rp) {
   for (int j = tid; j < nmosB; j += NT) {
     double y[3];
     rot_vec(R, p.dtab + tm[SLVGPU_M_O_LMOC] + j * 3, y);
-    riB[j * 3] = y[0] + t[0]; riB[j * 3 + 1] = y[1] + t[1]; riB[j * 3 + 2] = y[2] + t[2];
+    riB[j * 3] = y[0] + tr[0]; riB[j * 3 + 1] = y[1] + tr[1]; riB[j * 3 + 2] = y[2] + tr[2];
   }
-  const int *blB = p.itab + tm[SLVGPU_M_IO_BFL];
-  const double *vecB = p.dtab + tm[SLVGPU_M_O_VECL];
-  // rotate the fragment's AO->LMO rows into the lab frame (VECROT): s copy, p as vectors, d as symmetric tensors; one
-  // thread per leading element of a block
-  for (int w = tid; w < nmosB * nbsB; w += NT) {
-    const int j = w / nbsB, k = w - j * nbsB;
-    const int lx = blB[k * 3], ly = blB[k * 3 + 1], lz = blB[k * 3 + 2], Ls = lx + ly + lz;
-    const double *c = vecB + (size_t)j * nbsB + k;
-    double *d = CBs + (size_t)j * nbsB + k;
-    if (Ls == 0) d[0] = c[0];
-    else if (Ls == 1 && lx == 1) { double v[3] = {c[0], c[1], c[2]}, o[3]; rot_vec(R, v, o); d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; }
-    else if (Ls == 2 && lx == 2) { double v[6] = {c[0], c[1], c[2], c[3], c[4], c[5]}, o[6]; rot_quad(R, v, o); for (int q = 0; q < 6; ++q) d[q] = o[q]; }
+  for (int w = tid; w < L.LK * JS; w += NT) CBs[w] = 0.0;
+  __syncthreads();
+  rotate_vecl_rows(p, tm, p.dtab + tm[SLVGPU_M_O_VECL], nmosB, R, CBs, [JS](int j, int l) { return (size_t)l * JS + j; });   // CBs[l][j]
+  for (int w = tid; w < nij; w += NT) {
+    const int i = w / nmosB, j = w - i * nmosB;
+    const double dx = riA[i * 3] - riB[j * 3], dy = riA[i * 3 + 1] - riB[j * 3 + 1], dz = riA[i * 3 + 2] - riB[j * 3 + 2];
+    const double rinv = rsqrt64(dx * dx + dy * dy + dz * dz);
+    RI[w] = rinv; RM[w] = rinv * (dx * ri1A[i * 3] + dy * ri1A[i * 3 + 1] + dz * ri1A[i * 3 + 2]);
   }
-  for (int w = tid; w < 4 * nij; w += NT) IJ[w] = 0.0;
-  // The solute's basis functions are taken in tiles of KT rows sized so that one tile's half transform is one round of
-  // the CTA; a tile's X goes straight into the LMO integrals, so every integral record is read exactly once however
-  // many LMOs the fragment has (three passes over V for DMSO's 21 LMOs cost 1.1 MB of DRAM reads per pair before).
-  constexpr int JB = 5;
-  const int nblk = (nmosB + JB - 1) / JB, JP = nblk * JB;
-  const int KT = max(1, NT / nblk);
-  for (int k0 = 0; k0 < nbsA; k0 += KT) {
-    const int kn = min(KT, nbsA - k0);
-    prefetch_rows(k0 + 2 * KT, k0 + 3 * KT);
-    __syncthreads();                                         // CBs ready / the previous tile's X is consumed
-    // ---- phase 2: X[kk][q][j] = sum_l V[k0+kk][l][q] CB[j][l]; one thread per (row, block of 5 LMOs): the row is
-    //      streamed as 32-byte records, each feeding 20 FMAs (the nblk threads of a row sit in one warp)
-    for (int w = tid; w < kn * nblk; w += NT) {
-      const int kk = w / nblk, jb = (w - kk * nblk) * JB;
-      const double2 *v2 = reinterpret_cast<const double2 *>(V + (size_t)(k0 + kk) * nbsB * 4);
-      const double *cb[JB];
-#pragma unroll
-      for (int jj = 0; jj < JB; ++jj) cb[jj] = CBs + (size_t)min(jb + jj, nmosB - 1) * nbsB;
-      double acc[4][JB];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int jj = 0; jj < JB; ++jj) acc[q][jj] = 0.0;
-#pragma unroll 8
-      for (int l = 0; l < nbsB; ++l) {
-        const double2 va = v2[2 * l], vb = v2[2 * l + 1];
-#pragma unroll
-        for (int jj = 0; jj < JB; ++jj) {
-          const double c = cb[jj][l];
-          acc[0][jj] = fma(va.x, c, acc[0][jj]); acc[1][jj] = fma(va.y, c, acc[1][jj]);
-          acc[2][jj] = fma(vb.x, c, acc[2][jj]); acc[3][jj] = fma(vb.y, c, acc[3][jj]);
-        }
+  __syncthreads();
+  for (int w = tid; w < 2 * (nmosA + nmosB); w += NT) {
+    if (w < nmosB) {                                     // column sums over the solute's LMOs (TA1)
+      double s1 = 0, s2 = 0;
+      for (int k = 0; k < nmosA; ++k) { const double r = RI[k * nmosB + w]; s1 += r; s2 += r * r * RM[k * nmosB + w]; }
+      col1[w] = s1; col2[w] = s2;
+    } else if (w < 2 * nmosB) {                          // solute atoms against fragment LMO j (TA3)
+      const int j = w - nmosB;
+      double su = 0, sw = 0;
+      for (int m = 0; m < natA; ++m) {
+        const double dx = posA[m * 3] - riB[j * 3], dy = posA[m * 3 + 1] - riB[j * 3 + 1], dz = posA[m * 3 + 2] - riB[j * 3 + 2];
+        const double rinv = rsqrt64(dx * dx + dy * dy + dz * dz), z = p.dtab[tm0[SLVGPU_M_O_ZNUC] + m];
+        su += z * rinv * rinv * rinv * (dx * LcA[m * 3] + dy * LcA[m * 3 + 1] + dz * LcA[m * 3 + 2]); sw += z * rinv;
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int jj = 0; jj < JB; ++jj) X[((size_t)kk * 4 + q) * JP + jb + jj] = acc[q][jj];
-    }
-    __syncthreads();
-    // ---- phase 3: this tile's contribution to the LMO-basis integrals; (i, j) is owned by one thread
-    for (int w = tid; w < nij; w += NT) {
-      const int i = w / nmosB, j = w - i * nmosB;
-      const double *ca = CA + (size_t)i * nbsA + k0, *ca1 = CA1 + (size_t)i * nbsA + k0;
-      double sv = 0, tv = 0, smv = 0, tmv = 0;
-#pragma unroll 8
-      for (int kk = 0; kk < kn; ++kk) {
-        const double *x = X + (size_t)kk * 4 * JP + j;
-        const double xs = x[0], xt = x[JP], xds = x[2 * JP], xdt = x[3 * JP];
-        const double c0 = ca[kk], c1 = ca1[kk];
-        sv = fma(c0, xs, sv); tv = fma(c0, xt, tv);
-        smv = fma(c0, xds, fma(c1, xs, smv)); tmv = fma(c0, xdt, fma(c1, xt, tmv));
+      u3[j] = su; w3[j] = sw;
+    } else if (w < 2 * nmosB + nmosA) {                  // row sums over the fragment's LMOs (TA2)
+      const int i = w - 2 * nmosB;
+      double s1 = 0, s2 = 0;
+      for (int l = 0; l < nmosB; ++l) { const double r = RI[i * nmosB + l]; s1 += r; s2 += r * r * RM[i * nmosB + l]; }
+      row1[i] = s1; row2[i] = s2;
+    } else {                                             // fragment atoms against solute LMO i (TA4)
+      const int i = w - 2 * nmosB - nmosA;
+      double su = 0, sw = 0;
+      for (int n = 0; n < natB; ++n) {
+        const double dx = riA[i * 3] - posB[n * 3], dy = riA[i * 3 + 1] - posB[n * 3 + 1], dz = riA[i * 3 + 2] - posB[n * 3 + 2];
+        const double rinv = rsqrt64(dx * dx + dy * dy + dz * dz), z = p.dtab[tm[SLVGPU_M_O_ZNUC] + n];
+        su += z * rinv * rinv * rinv * (dx * ri1A[i * 3] + dy * ri1A[i * 3 + 1] + dz * ri1A[i * 3 + 2]); sw += z * rinv;
       }
-      IJ[w] += sv; IJ[nij + w] += tv; IJ[2 * nij + w] += smv; IJ[3 * nij + w] += tmv;
+      u4[i] = su; w4[i] = sw;
     }
   }
   __syncthreads();
-  // ---- phase 4: CALCFI
+
+  // ---- tile loop.  Phase B units u = kind * nit + itile (kind: S, T, Sm, Tm), unit u belongs to warp u % 4
+  double accB[REP_MAX_NIT][NNT][2];
+#pragma unroll
+  for (int s = 0; s < REP_MAX_NIT; ++s)
+#pragma unroll
+    for (int n = 0; n < NNT; ++n) accB[s][n][0] = accB[s][n][1] = 0.0;
+  const int nunit = 4 * nit, nks = L.LK >> 2;
+  constexpr int MW = KT / 8;                              // M-tiles (8 integral rows = 2 basis functions x 4 kinds) per warp and tile
+  for (int t = 0; t < ntile; ++t) {
+    mbar_wait(bar + (t & 1), (unsigned)((t >> 1) & 1));
+    const double *Vb = Vt + (size_t)(t % L.nbuf) * tileV_doubles;
+    double *Xb = Xs + (size_t)(t & 1) * tileX;
+    // phase A: X[(k,q)][j] = sum_l V[(k,q)][l] CB[j][l]; warp w owns M-tiles w, w + 4
+    {
+      double acc[MW][NNT][2];
+#pragma unroll
+      for (int m = 0; m < MW; ++m)
+#pragma unroll
+        for (int n = 0; n < NNT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+      const double *va = Vb + (size_t)(warp * 8 + g) * LP + c4;
+      const double *cb = CBs + (size_t)c4 * JS + g;
+#pragma unroll 2
+      for (int ks = 0; ks < nks; ++ks) {
+        double a[MW], b[NNT];
+#pragma unroll
+        for (int m = 0; m < MW; ++m) a[m] = va[(size_t)m * 32 * LP + ks * 4];
+#pragma unroll
+        for (int n = 0; n < NNT; ++n) b[n] = cb[(size_t)ks * 4 * JS + n * 8];
+#pragma unroll
+        for (int m = 0; m < MW; ++m)
+#pragma unroll
+          for (int n = 0; n < NNT; ++n) dmma884(acc[m][n][0], acc[m][n][1], a[m], b[n]);
+      }
+#pragma unroll
+      for (int m = 0; m < MW; ++m) {
+        const int row = (m * 4 + warp) * 8 + g, kk = row >> 2, q = row & 3;      // tile row -> (basis function, integral kind)
+        double *x = Xb + ((size_t)q * KT + kk) * JS + 2 * c4;
+#pragma unroll
+        for (int n = 0; n < NNT; ++n) *reinterpret_cast<double2 *>(x + n * 8) = make_double2(acc[m][n][0], acc[m][n][1]);
+      }
+    }
+    __syncthreads();                                       // X complete; every warp is done with this V buffer
+    if (tid == 0 && t + L.nbuf < ntile) issue(t + L.nbuf);
+    // phase B: IJ[kind][i][j] += sum_k C[i][k] X[k][q][j]
+    {
+      const double *cat = CAs + (size_t)(t % ncab) * tileCA_doubles;
+#pragma unroll
+      for (int s = 0; s < REP_MAX_NIT; ++s) {
+        const int u = warp + 4 * s;
+        if (u < nunit) {
+          const int kind = u / nit, itile = u - kind * nit;
+          const double *ca = cat + (size_t)(itile * 8 + g) * REP_CS + c4;
+          const double *x0 = Xb + ((size_t)kind * KT + c4) * JS + g;               // X_kind rows
+          const double *x1 = Xb + ((size_t)(kind & 1) * KT + c4) * JS + g;         // Sm, Tm: the C1 product uses X_S, X_T
+#pragma unroll
+          for (int k4 = 0; k4 < KT / 4; ++k4) {
+            const int o = k4 >> 1, kk0 = (k4 & 1) * 4;
+            const double a0 = ca[(size_t)o * 2 * IP * REP_CS + kk0];
+#pragma unroll
+            for (int n = 0; n < NNT; ++n) dmma884(accB[s][n][0], accB[s][n][1], a0, x0[(size_t)k4 * 4 * JS + n * 8]);
+            if (kind >= 2) {
+              const double a1 = ca[(size_t)(o * 2 + 1) * IP * REP_CS + kk0];
+#pragma unroll
+              for (int n = 0; n < NNT; ++n) dmma884(accB[s][n][0], accB[s][n][1], a1, x1[(size_t)k4 * 4 * JS + n * 8]);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < REP_MAX_NIT; ++s) {
+    const int u = warp + 4 * s;
+    if (u < nunit) {
+      const int kind = u / nit, itile = u - kind * nit, i = itile * 8 + g;
+#pragma unroll
+      for (int n = 0; n < NNT; ++n) {
+        const int j = n * 8 + 2 * c4;
+        if (i < nmosA && j < nmosB) IJ[kind * nij + i * nmosB + j] = accB[s][n][0];
+        if (i < nmosA && j + 1 < nmosB) IJ[kind * nij + i * nmosB + j + 1] = accB[s][n][1];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- CALCFI (shftex.f:69-295): every sum over centroid / atom distances comes from the tables above
   double acc = 0.0;
   {
     const double *Sij = IJ, *Tij = IJ + nij, *Smij = IJ + 2 * nij, *Tmij = IJ + 3 * nij;
-    const double *FB = p.dtab + tm[SLVGPU_M_O_FOCK], *ZB = p.dtab + tm[SLVGPU_M_O_ZNUC];
+    const double *FA = p.dtab + tm0[SLVGPU_M_O_FOCK], *FA1 = p.dtab + p.sol_meta[SLVGPU_S_FOCK1], *FB = p.dtab + tm[SLVGPU_M_O_FOCK];
     const double PI = 3.14159265358979323846;
     for (int w = tid; w < nij; w += NT) {
-      const int i = w / nmosB, j = w % nmosB;
+      const int i = w / nmosB, j = w - i * nmosB;
       const double S = Sij[w], T = Tij[w], Sm = Smij[w], Tm = Tmij[w];
       const double sl = log(fabs(S)), S2 = S * S;
-      const double ri[3] = {riA[i * 3], riA[i * 3 + 1], riA[i * 3 + 2]}, r1i[3] = {ri1A[i * 3], ri1A[i * 3 + 1], ri1A[i * 3 + 2]};
-      const double rj[3] = {riB[j * 3], riB[j * 3 + 1], riB[j * 3 + 2]};
-      double dx = ri[0] - rj[0], dy = ri[1] - rj[1], dz = ri[2] - rj[2];
-      double rinv = rsqrt64(dx * dx + dy * dy + dz * dz);
-      const double rmij = rinv * (dx * r1i[0] + dy * r1i[1] + dz * r1i[2]);
-      const double sdr = S * rinv;
+      const double sdr = S * RI[w];
       const double aux = 2.0 * sqrt(-2.0 * sl / PI);
-      double f = 4.0 * sdr * Sm * (sqrt(-1.0 / (2.0 * PI * sl)) - aux - 1.0) + 2.0 * sdr * sdr * rmij * (aux + 1.0)
+      double f = 4.0 * sdr * Sm * (sqrt(-1.0 / (2.0 * PI * sl)) - aux - 1.0) + 2.0 * sdr * sdr * RM[w] * (aux + 1.0)
                + 4.0 * Sm * T + 4.0 * Tm * S;
-      for (int k = 0; k < nmosA; ++k) {                 // TA1
-        const double skj = Sij[k * nmosB + j], smkj = Smij[k * nmosB + j];
-        dx = riA[k * 3] - rj[0]; dy = riA[k * 3 + 1] - rj[1]; dz = riA[k * 3 + 2] - rj[2];
-        rinv = rsqrt64(dx * dx + dy * dy + dz * dz);
-        const double rmkj = rinv * (dx * ri1A[k * 3] + dy * ri1A[k * 3 + 1] + dz * ri1A[k * 3 + 2]);
-        const double fik = FA[i * nmosA + k], f1ik = FA1[i * nmosA + k];
-        f += -2.0 * Sm * fik * skj + 8.0 * S * rinv * Sm - 2.0 * S * (f1ik * skj + fik * smkj) - 4.0 * S2 * rinv * rinv * rmkj;
+      double g1 = 0, g2 = 0, g3 = 0;                       // (F_A S)_ij, (F1_A S)_ij, (F_A Sm)_ij
+      for (int k = 0; k < nmosA; ++k) {
+        const double fik = FA[i * nmosA + k], skj = Sij[k * nmosB + j];
+        g1 = fma(fik, skj, g1); g2 = fma(FA1[i * nmosA + k], skj, g2); g3 = fma(fik, Smij[k * nmosB + j], g3);
       }
-      for (int l = 0; l < nmosB; ++l) {                 // TA2
-        const double sil = Sij[i * nmosB + l], smil = Smij[i * nmosB + l];
-        dx = ri[0] - riB[l * 3]; dy = ri[1] - riB[l * 3 + 1]; dz = ri[2] - riB[l * 3 + 2];
-        rinv = rsqrt64(dx * dx + dy * dy + dz * dz);
-        const double rmil = rinv * (dx * r1i[0] + dy * r1i[1] + dz * r1i[2]);
+      double h1 = 0, h2 = 0;                               // (S F_B^T)_ij, (Sm F_B^T)_ij
+      for (int l = 0; l < nmosB; ++l) {
         const double fjl = FB[j * nmosB + l];
-        f += -2.0 * Sm * fjl * sil + 8.0 * S * rinv * Sm - 2.0 * S * fjl * smil - 4.0 * S2 * rinv * rinv * rmil;
+        h1 = fma(fjl, Sij[i * nmosB + l], h1); h2 = fma(fjl, Smij[i * nmosB + l], h2);
       }
-      for (int m = 0; m < natA; ++m) {                  // TA3
-        dx = posA[m * 3] - rj[0]; dy = posA[m * 3 + 1] - rj[1]; dz = posA[m * 3 + 2] - rj[2];
-        rinv = rsqrt64(dx * dx + dy * dy + dz * dz);
-        const double rmm = rinv * (dx * LcA[m * 3] + dy * LcA[m * 3 + 1] + dz * LcA[m * 3 + 2]);
-        f += 2.0 * S2 * ZA[m] * rinv * rinv * rmm - 4.0 * S * Sm * ZA[m] * rinv;
-      }
-      for (int n = 0; n < natB; ++n) {                  // TA4
-        dx = ri[0] - posB[n * 3]; dy = ri[1] - posB[n * 3 + 1]; dz = ri[2] - posB[n * 3 + 2];
-        rinv = rsqrt64(dx * dx + dy * dy + dz * dz);
-        const double rmn = rinv * (dx * r1i[0] + dy * r1i[1] + dz * r1i[2]);
-        f += 2.0 * S2 * ZB[n] * rinv * rinv * rmn - 4.0 * S * Sm * ZB[n] * rinv;
-      }
+      f += -2.0 * Sm * g1 - 2.0 * S * (g2 + g3) + 8.0 * S * Sm * col1[j] - 4.0 * S2 * col2[j];       // TA1
+      f += -2.0 * Sm * h1 - 2.0 * S * h2 + 8.0 * S * Sm * row1[i] - 4.0 * S2 * row2[i];              // TA2
+      f += 2.0 * S2 * u3[j] - 4.0 * S * Sm * w3[j];                                                   // TA3
+      f += 2.0 * S2 * u4[i] - 4.0 * S * Sm * w4[i];                                                   // TA4
       acc += f;
     }
   }
+  // the integral kernels store zeros for non-finite values (the pool is recycled and its pad cells are read by later
+  // batches): a pair with non-finite coordinates must still come out non-finite
+  for (int w = tid; w < 3 * (natA + natB); w += NT) acc += 0.0 * (w < 3 * natA ? posA[w] : posB[w - 3 * natA]);
   acc = block_sum(acc, s_red);
   if (tid == 0) rp.res[pr] = acc;
 }

@@ -137,12 +137,12 @@ SLV_HD void subshell_pair_t(const double A[3], int npa, const double *ea, const 
 }
 
 // One work item of k_rep phase 1: sub-shells sa = {atom, first function, L, nprim} of the solute and sb of the
-// solvent fragment; writes V[((f0a + ca) * nbsB + f0b + cb) * 4 + q].  eX/cX are the per-function [nbf][6] exponent and
+// solvent fragment; writes V[((f0a + ca) * 4 + q) * LP + f0b + cb] (rows of LP doubles per (basis function, kind)).  eX/cX are the per-function [nbf][6] exponent and
 // coefficient tables (coefficient x primitive norm x contracted norm), LcA the per-atom displacement vectors.
 template <int LA, int LB, int IA>
 SLV_HD void subshell_pair_store(const int *sa, const int *sb, const double *posA, const double *posB,
                                 const double *eA, const double *cA, const double *eB, const double *cB,
-                                const double *LcA, int nbsB, double *V) {
+                                const double *LcA, int LP, double *V) {
   constexpr int NA = IA < 0 ? cart_ncomp(LA) : 1, NB = cart_ncomp(LB);
   const int f0a = sa[1], f0b = sb[1];
   double acc[NA * NB * 4];
@@ -157,9 +157,12 @@ SLV_HD void subshell_pair_store(const int *sa, const int *sb, const double *posA
     for (int c2 = 0; c2 < NB; ++c2) {
       const int l = f0b + c2;
       const double f = (LB == 2) ? ra * (cB[l * 6] * ib0) : ra;
-      double *v = V + ((size_t)k * nbsB + l) * 4;
-      v[0] = f * acc[(c1 * NB + c2) * 4]; v[1] = f * acc[(c1 * NB + c2) * 4 + 1];
-      v[2] = f * acc[(c1 * NB + c2) * 4 + 2]; v[3] = f * acc[(c1 * NB + c2) * 4 + 3];
+      double *v = V + (size_t)k * 4 * LP + l;                     // V[k][q][l], rows of LP doubles
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double x = f * acc[(c1 * NB + c2) * 4 + q];
+        v[(size_t)q * LP] = (x - x == 0.0) ? x : 0.0;               // non-finite -> 0: the pool is recycled and its cells are
+      }                                                             // read (times zero) by later batches
     }
   }
 }

@@ -37,10 +37,13 @@ struct slvgpu_plan {
   PolWork pw{};
   RepPool rp[2] = {};
   RepLimits rep_lim;
-  cudaStream_t rep_stream = nullptr; cudaEvent_t rep_ev[2] = {nullptr, nullptr};
+  cudaStream_t side[2] = {nullptr, nullptr};  // plan-owned streams: dispersion and exchange repulsion run beside k_pol
+  cudaEvent_t ev_elect = nullptr, ev_side[2] = {nullptr, nullptr}, ev_pol = nullptr;
   std::vector<int> rep_types;                 // fragment types that carry the wave-function tables
   std::vector<std::vector<int>> rep_cls;      // per such type: the 24 class offsets of its integral work list
+  std::vector<RepSmem> rep_sm;                // per such type: shared-memory plan of k_rep_pair
   std::vector<int> h_pair0;
+  int pol_ctas_shared = 0;                    // k_pol grid when other kernels share the SMs with it
   double *d_detail = nullptr;
   int *d_queue = nullptr;
   int detail_frames = 0;
@@ -125,8 +128,9 @@ extern "C" void slvgpu_plan_destroy(slvgpu_plan *pl) {
   if (pl->d_stage_status) cudaFree(pl->d_stage_status);
   if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
   if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
-  if (pl->rep_stream) cudaStreamDestroy(pl->rep_stream);
-  for (int b = 0; b < 2; ++b) if (pl->rep_ev[b]) cudaEventDestroy(pl->rep_ev[b]);
+  for (int b = 0; b < 2; ++b) { if (pl->side[b]) cudaStreamDestroy(pl->side[b]); if (pl->ev_side[b]) cudaEventDestroy(pl->ev_side[b]); }
+  if (pl->ev_elect) cudaEventDestroy(pl->ev_elect);
+  if (pl->ev_pol) cudaEventDestroy(pl->ev_pol);
   for (cudaEvent_t e : pl->copy_ev) cudaEventDestroy(e);
   delete pl;
 }
@@ -287,18 +291,23 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
       slvgpu_plan_destroy(pl);
       return fail(SLVGPU_EINVAL, "exchange-repulsion needs the wave-function tables (vecl, fock, basis) in the plan");
     }
-    if (pl->max_nmos > 5 * REP_THREADS ||
-        rep_smem_bytes(pl->nmosc, pl->nbasc, pl->max_nmos, pl->max_nbas, pl->natc, pl->max_nat) > (size_t)200 * 1024) {
+    if (pl->nmosc > 8 * REP_MAX_NIT) {
       slvgpu_plan_destroy(pl);
-      return fail(SLVGPU_EINVAL, "exchange repulsion: a fragment type is too large for k_rep_pair's shared-memory tables "
-                                 "(LMOs x basis functions of the fragment, LMOs of solute x fragment)");
+      return fail(SLVGPU_EINVAL, "exchange repulsion: the solute has more than 24 LMOs (k_rep_pair keeps its LMO integrals in registers)");
     }
     TRY(rep_alloc(pl->rp, pl->rep_lim, pl->allocs, g_err, pl->nmosc, pl->nbasc, pl->natc, pl->max_nbas, pl->max_nat, pl->max_chunk, p.list_cap));
     for (int t = 0; t < d->ntypes; ++t) {
       const int32_t *tm = d->type_meta + (size_t)t * SLVGPU_NMETA;
       if (tm[SLVGPU_M_IO_SHPAIR] < 0 || !solvent_type[t]) continue;
+      const RepSmem rs = rep_smem_plan(pl->nmosc, pl->nbasc, pl->natc, tm[SLVGPU_M_NMOS], tm[SLVGPU_M_NBASIS], tm[SLVGPU_M_NATOMS]);
+      if (rs.NNT > REP_MAX_NNT || rs.bytes > (size_t)220 * 1024) {
+        slvgpu_plan_destroy(pl);
+        return fail(SLVGPU_EINVAL, "exchange repulsion: fragment type " + std::to_string(t) + " is too large for k_rep_pair "
+                                   "(more than 40 LMOs, or its coefficient table does not fit shared memory)");
+      }
       pl->rep_types.push_back(t);
       pl->rep_cls.emplace_back(d->itab + tm[SLVGPU_M_IO_SHPAIR], d->itab + tm[SLVGPU_M_IO_SHPAIR] + SUBSHELL_NCLASS + 1);
+      pl->rep_sm.push_back(rs);
     }
     pl->h_pair0.resize((size_t)pl->max_chunk + 1);
   }
@@ -307,7 +316,15 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   cudaFuncSetAttribute(k_frame_elect, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_disp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_pol, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  cudaFuncSetAttribute(k_rep_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+#define RPA(KT, NNT) cudaFuncSetAttribute(k_rep_pair<KT, NNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  RPA(8, 1) RPA(8, 2) RPA(8, 3) RPA(8, 4) RPA(8, 5) RPA(16, 1) RPA(16, 2) RPA(16, 3) RPA(16, 4) RPA(16, 5)
+#undef RPA
+  // With dispersion or exchange repulsion in the plan, k_pol leaves part of every SM to their kernels (they run on the
+  // plan's side streams at the same time); SLVGPU_POL_CTAS overrides the grid for experiments.
+  pl->pol_ctas_shared = pl->pol_ctas;
+  if (d->flags & (SLVGPU_REP | SLVGPU_DISP)) pl->pol_ctas_shared = pl->sm_count * POL_CTAS_SHARED_PER_SM;
+  if (const char *ev = getenv("SLVGPU_POL_CTAS")) { const int v = atoi(ev); if (v > 0) pl->pol_ctas_shared = v; }
+  if (pl->pol_ctas_shared > pl->pol_ctas) pl->pol_ctas_shared = pl->pol_ctas;     // the workspace is sized for pol_ctas CTAs
   *out = pl;
   return 0;
 }
@@ -333,40 +350,58 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
   const size_t sm_el = (size_t)pl->ndmac * SOLROW * sizeof(double);
   const size_t sm_di = ((size_t)pl->npolc * DISP_SOLROW + (108 + 4) * DISP_TJ) * sizeof(double) + ((size_t)p.list_cap + 2) * sizeof(int);
   const size_t sm_po = ((size_t)POL_TILE * 10 + (size_t)pl->npolc * 21 + (size_t)pl->ndmac * 46) * sizeof(double);
+  const bool do_disp = (p.flags & SLVGPU_DISP) && p.ninst > 1, do_pol = (p.flags & SLVGPU_POL) && p.ninst > 1;
+  const bool do_rep = (p.flags & SLVGPU_REP) && p.ninst > 1;
+  if ((do_disp || do_rep) && !pl->side[0]) {
+    for (int b = 0; b < 2; ++b) {
+      CK(cudaStreamCreateWithFlags(&pl->side[b], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&pl->ev_side[b], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&pl->ev_elect, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&pl->ev_pol, cudaEventDisableTiming));
+  }
+  // Schedule of a chunk: k_frame_elect on the caller's stream, then k_pol there, while dispersion and the exchange-
+  // repulsion batches run on the plan's two side streams (k_pol is FP64-issue bound and leaves its memory system idle,
+  // the integral kernels and the tile pipeline of k_rep_pair are latency / bandwidth bound: they share the SMs).  The
+  // side streams are joined back into the caller's stream before the next chunk reuses the hand-over lists.
   for (int64_t f0 = 0; f0 < nframes; f0 += pl->max_chunk) {
     const int nf = (int)((nframes - f0) < pl->max_chunk ? (nframes - f0) : pl->max_chunk);
     ev_begin(pl, 0, st);
     k_frame_elect<<<nf, ELECT_THREADS, sm_el, st>>>(p, d_coords, (int)f0, pl->fl, d_out);
     ev_end(pl, st);
     ++pl->last_launches;
-    if ((p.flags & SLVGPU_DISP) && p.ninst > 1) {
-      ev_begin(pl, 1, st);
-      k_disp<<<nf, DISP_THREADS, sm_di, st>>>(p, (int)f0, pl->fl, d_out);
-      ev_end(pl, st);
-      ++pl->last_launches;
+    const bool side_work = do_disp || do_rep;
+    if (side_work) {
+      CK(cudaEventRecord(pl->ev_elect, st));
+      CK(cudaStreamWaitEvent(pl->side[0], pl->ev_elect, 0));
+      CK(cudaStreamWaitEvent(pl->side[1], pl->ev_elect, 0));
     }
-    if ((p.flags & SLVGPU_POL) && p.ninst > 1) {
-      const int g = nf < pl->pol_ctas ? nf : pl->pol_ctas;
+    if (do_pol) {
+      const int cap = side_work ? pl->pol_ctas_shared : pl->pol_ctas;
+      const int g = nf < cap ? nf : cap;
       ev_begin(pl, 2, st);
       CK(cudaMemsetAsync(pl->d_queue, 0, sizeof(int), st));
       k_pol<<<g, POL_THREADS, sm_po, st>>>(p, (int)f0, nf, pl->fl, pl->pw, d_out, d_status, pl->d_detail, pl->d_queue);
       ev_end(pl, st);
       ++pl->last_launches;
     }
-    if ((p.flags & SLVGPU_REP) && p.ninst > 1) {
-      // Exchange repulsion runs in batches of frames sized by the integral pool.  The batch boundaries need the
-      // per-frame fragment counts on the host: one small copy and a stream synchronisation per chunk.  Batches
-      // alternate between the caller's stream and a side stream (two pools): the throughput-bound integral kernels
-      // of one batch share the SMs with the latency-bound transform kernel of the other.
-      ev_begin(pl, 3, st);
-      k_rep_scan<<<1, 1024, 0, st>>>(d_out, (int)f0, nf, pl->rp[0].pair0);
+    if (do_disp) {
+      ev_begin(pl, 1, pl->side[0]);
+      k_disp<<<nf, DISP_THREADS, sm_di, pl->side[0]>>>(p, (int)f0, pl->fl, d_out);
+      ev_end(pl, pl->side[0]);
       ++pl->last_launches;
-      CK(cudaMemcpyAsync(pl->h_pair0.data(), pl->rp[0].pair0, ((size_t)nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));                          // everything the batches read is complete from here on
-      if (!pl->rep_stream) {
-        CK(cudaStreamCreateWithFlags(&pl->rep_stream, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; ++b) CK(cudaEventCreateWithFlags(&pl->rep_ev[b], cudaEventDisableTiming));
-      }
+    }
+    if (do_rep) {
+      // Exchange repulsion runs in batches of frames sized by the integral pool.  The batch boundaries need the
+      // per-frame fragment counts on the host: one small copy and a synchronisation of side stream 1 per chunk (k_pol
+      // and k_disp are already queued and keep the GPU busy meanwhile).  Batches alternate between the two side
+      // streams (two pools): the integral kernels of one batch overlap the transform kernel of the other.
+      cudaStream_t s1 = pl->side[1];
+      ev_begin(pl, 3, s1);
+      k_rep_scan<<<1, 1024, 0, s1>>>(d_out, (int)f0, nf, pl->rp[0].pair0);
+      ++pl->last_launches;
+      CK(cudaMemcpyAsync(pl->h_pair0.data(), pl->rp[0].pair0, ((size_t)nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, s1));
+      CK(cudaStreamSynchronize(s1));
       const int *pair0 = pl->h_pair0.data();
       {
         // pools sized for two concurrent batches covering the chunk, and for the largest single frame
@@ -375,21 +410,20 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
         size_t need = ((size_t)pair0[nf] + 1) / 2;
         if (need < (size_t)fmax) need = (size_t)fmax;
         if (need > (size_t)pl->rp[0].pair_cap && (size_t)pl->rp[0].pair_cap < pl->rep_lim.max_pairs) {
-          CK(cudaStreamSynchronize(pl->rep_stream));
+          CK(cudaStreamSynchronize(pl->side[0]));                 // nothing of an earlier chunk may still use the pools
           const int rc = rep_reserve(pl->rp, pl->rep_lim, need, g_err);
-          if (rc) { ev_end(pl, st); return rc; }
+          if (rc) { ev_end(pl, s1); return rc; }
         }
       }
-      const size_t sm_re = rep_smem_bytes(pl->nmosc, pl->nbasc, pl->max_nmos, pl->max_nbas, pl->natc, pl->max_nat);
       int batch = 0;
       for (int fs = 0; fs < nf; ++batch) {
         const RepPool &rp = pl->rp[batch & 1];
-        cudaStream_t sb = (batch & 1) ? pl->rep_stream : st;
+        cudaStream_t sb = pl->side[(batch & 1) ^ 1];              // batch 0 on side stream 1 (side stream 0 starts with k_disp)
         int fe = fs;
         while (fe < nf && pair0[fe + 1] - pair0[fs] <= rp.pair_cap) ++fe;
         if (fe == fs) {
-          cudaStreamSynchronize(pl->rep_stream);
-          ev_end(pl, st);
+          cudaStreamSynchronize(pl->side[0]); cudaStreamSynchronize(s1);
+          ev_end(pl, s1);
           return fail(SLVGPU_ENOMEM, "exchange repulsion: one frame has more fragments inside ecut than the integral pool holds");
         }
         const int nb = fe - fs, npairs = pair0[fe] - pair0[fs];
@@ -410,18 +444,28 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
             SLV_SUBSHELL_CLASSES(X)
 #undef X
           }
-          k_rep_pair<<<npairs, REP_THREADS, sm_re, sb>>>(p, pl->fl, rp);
-          ++pl->last_launches;
+          for (size_t ti = 0; ti < pl->rep_types.size(); ++ti) {
+            const int ty = pl->rep_types[ti];
+            const RepSmem &rs = pl->rep_sm[ti];
+#define RP(KT_, NNT_) if (rs.KT == KT_ && rs.NNT == NNT_) k_rep_pair<KT_, NNT_><<<npairs, REP_THREADS, rs.bytes, sb>>>(p, ty, pl->fl, rp, rs);
+            RP(8, 1) RP(8, 2) RP(8, 3) RP(8, 4) RP(8, 5) RP(16, 1) RP(16, 2) RP(16, 3) RP(16, 4) RP(16, 5)
+#undef RP
+            ++pl->last_launches;
+          }
         }
         k_rep_sum<<<(nb + 127) / 128, 128, 0, sb>>>((int)f0, fs, nb, rp, d_out);
         ++pl->last_launches;
         fs = fe;
       }
-      if (batch > 1) {                                        // join the side stream
-        CK(cudaEventRecord(pl->rep_ev[0], pl->rep_stream));
-        CK(cudaStreamWaitEvent(st, pl->rep_ev[0], 0));
-      }
-      ev_end(pl, st);
+      CK(cudaEventRecord(pl->ev_side[0], pl->side[0]));          // side stream 1 closes the timing bracket after both finished
+      CK(cudaStreamWaitEvent(s1, pl->ev_side[0], 0));
+      ev_end(pl, s1);
+    }
+    if (side_work) {                                            // join
+      CK(cudaEventRecord(pl->ev_side[0], pl->side[0]));
+      CK(cudaEventRecord(pl->ev_side[1], pl->side[1]));
+      CK(cudaStreamWaitEvent(st, pl->ev_side[0], 0));
+      CK(cudaStreamWaitEvent(st, pl->ev_side[1], 0));
     }
   }
   k_status<<<(unsigned)((nframes + 255) / 256), 256, 0, st>>>(d_out, d_status, nframes);

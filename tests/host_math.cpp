@@ -19,12 +19,12 @@ extern "C" void hm_site_field_acc(const double* R, const double* m, double f, do
 // all AO integrals between two fragments through the sub-shell-pair specialisations, walking the classes the way
 // k_rep does (tests/test_host_math.py compares with oracle/ints_oracle.py)
 extern "C" void hm_subshell_V(int nsubA, const int* subA, const double* posA, const double* eA, const double* cA, const double* LcA,
-                              int nsubB, const int* subB, const double* posB, const double* eB, const double* cB, int nbsB, double* V) {
+                              int nsubB, const int* subB, const double* posB, const double* eB, const double* cB, int LP, double* V) {
   for (int a = 0; a < nsubA; ++a)
     for (int b = 0; b < nsubB; ++b) {
       const int* sa = subA + a * 4; const int* sb = subB + b * 4;
 #define X(ID, LA, LB, IA) \
-      if (sa[2] == LA && sb[2] == LB) slv::subshell_pair_store<LA, LB, IA>(sa, sb, posA, posB, eA, cA, eB, cB, LcA, nbsB, V);
+      if (sa[2] == LA && sb[2] == LB) slv::subshell_pair_store<LA, LB, IA>(sa, sb, posA, posB, eA, cA, eB, cB, LcA, LP, V);
       SLV_SUBSHELL_CLASSES(X)
 #undef X
     }
