@@ -10,7 +10,7 @@
 //   k_rep_scan   exclusive scan of the per-frame counts of fragments inside ecut -> pair slots
 //   k_rep_prep   per frame: lab-frame solute atoms and displacement vectors, the solute's rotated AO->LMO coefficients
 //                in k-octet tiles; per (frame, fragment) pair: the fragment's atoms and the pair -> (frame, entry, type) map
-//   k_rep_ints   AO integrals V[pair][k][q][l] (q = S, T, L.dS, L.dT; rows padded to LP): one launch per (fragment
+//   k_rep_ints   AO integrals V[pair][k][l][q] (q = S, T, L.dS, L.dT; l padded to a multiple of 4): one launch per (fragment
 //                type, sub-shell class), one thread per (pair, sub-shell-pair item), grid-wide -- every warp runs one
 //                specialisation of slv_ints.cuh with near-equal loop lengths
 //   k_rep_pair   one CTA per (frame, fragment) pair, one launch per fragment type.  The pair's integrals stream through
@@ -37,16 +37,12 @@ constexpr int REP_CS = 12;        // row stride (doubles) of a solute coefficien
 constexpr int REP_MAX_NIT = 3;    // solute LMO tiles of 8 (nmos <= 24)
 constexpr int REP_MAX_NNT = 5;    // fragment LMO tiles of 8 (nmos <= 40)
 
-// Row length (doubles) of the integral records of a fragment with nbs basis functions: a multiple of 4 that is 4 modulo 8,
-// so that the eight rows of a tensor-core A fragment fall on distinct shared-memory banks whatever the tile offset.
-__host__ __device__ inline int rep_lp(int nbs) {
-  int lp = (nbs + 3) & ~3;
-  if ((lp & 7) != 4) lp += 4;
-  return lp;
-}
+// Records per row of the integral block of a fragment with nbs basis functions: V[k][l][q], l padded to the k-step of the
+// tensor-core MMA (4).  A fragment of eight (k, q) rows x four l reads 2 x 16 consecutive doubles: no bank conflicts.
+__host__ __device__ inline int rep_lp(int nbs) { return (nbs + 3) & ~3; }
 
 struct RepPool {            // one batch of (frame, fragment) pairs (V .. pair_type) + per-frame tables of the chunk
-  double *V;       // [pair_cap][nbsA16][4][LP(type)]  AO integrals, block stride sV
+  double *V;       // [pair_cap][nbsA16][LP(type)][4]  AO integrals (S, T, L.dS, L.dT per record), block stride sV
   double *posA;    // [max_chunk][natA][3]   solute atoms, lab frame
   double *LcA;     // [max_chunk][natA][3]   mode-contracted displacement vectors, lab frame
   double *riA;     // [max_chunk][2][nmosA][3]  LMO centroids and their mode-contracted derivatives
@@ -127,6 +123,8 @@ inline int rep_reserve(RepPool rp[2], const RepLimits &lim, size_t pairs, std::s
     ok = ok && cudaMalloc(&rp[h].pair_frame, pairs * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&rp[h].pair_entry, pairs * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&rp[h].pair_type, pairs * sizeof(int)) == cudaSuccess;
+    // the memsets ran on the legacy default stream, which the plan's non-blocking streams do not wait for
+    ok = ok && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {                                     // leave no half-built pool behind (a retry starts from scratch)
       cudaGetLastError();
       for (int g = 0; g < 2; ++g) rep_pool_free(rp[g]);
@@ -436,13 +434,14 @@ k_rep_pair(const DevPlan p, int type, FrameLists fl, RepPool rp, RepSmem L) {
       for (int m = 0; m < MW; ++m)
 #pragma unroll
         for (int n = 0; n < NNT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
-      const double *va = Vb + (size_t)(warp * 8 + g) * LP + c4;
+      // A fragment: row g of M-tile mt is (basis function 2 mt + g / 4, kind g % 4), column c4 is l = 4 ks + c4
+      const double *va = Vb + ((size_t)(warp * 2 + (g >> 2)) * LP + c4) * 4 + (g & 3);
       const double *cb = CBs + (size_t)c4 * JS + g;
 #pragma unroll 2
       for (int ks = 0; ks < nks; ++ks) {
         double a[MW], b[NNT];
 #pragma unroll
-        for (int m = 0; m < MW; ++m) a[m] = va[(size_t)m * 32 * LP + ks * 4];
+        for (int m = 0; m < MW; ++m) a[m] = va[(size_t)m * 32 * LP + ks * 16];
 #pragma unroll
         for (int n = 0; n < NNT; ++n) b[n] = cb[(size_t)ks * 4 * JS + n * 8];
 #pragma unroll

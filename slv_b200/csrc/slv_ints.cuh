@@ -137,7 +137,7 @@ SLV_HD void subshell_pair_t(const double A[3], int npa, const double *ea, const 
 }
 
 // One work item of k_rep phase 1: sub-shells sa = {atom, first function, L, nprim} of the solute and sb of the
-// solvent fragment; writes V[((f0a + ca) * 4 + q) * LP + f0b + cb] (rows of LP doubles per (basis function, kind)).  eX/cX are the per-function [nbf][6] exponent and
+// solvent fragment; writes V[((f0a + ca) * LP + f0b + cb) * 4 + q] (LP records of four kinds per solute basis function).  eX/cX are the per-function [nbf][6] exponent and
 // coefficient tables (coefficient x primitive norm x contracted norm), LcA the per-atom displacement vectors.
 template <int LA, int LB, int IA>
 SLV_HD void subshell_pair_store(const int *sa, const int *sb, const double *posA, const double *posB,
@@ -157,11 +157,11 @@ SLV_HD void subshell_pair_store(const int *sa, const int *sb, const double *posA
     for (int c2 = 0; c2 < NB; ++c2) {
       const int l = f0b + c2;
       const double f = (LB == 2) ? ra * (cB[l * 6] * ib0) : ra;
-      double *v = V + (size_t)k * 4 * LP + l;                     // V[k][q][l], rows of LP doubles
+      double *v = V + ((size_t)k * LP + l) * 4;                   // V[k][l][q], LP records per row
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const double x = f * acc[(c1 * NB + c2) * 4 + q];
-        v[(size_t)q * LP] = (x - x == 0.0) ? x : 0.0;               // non-finite -> 0: the pool is recycled and its cells are
+        v[q] = (x - x == 0.0) ? x : 0.0;                            // non-finite -> 0: the pool is recycled and its cells are
       }                                                             // read (times zero) by later batches
     }
   }

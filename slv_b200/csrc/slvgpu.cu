@@ -44,6 +44,7 @@ struct slvgpu_plan {
   std::vector<RepSmem> rep_sm;                // per such type: shared-memory plan of k_rep_pair
   std::vector<int> h_pair0;
   int pol_ctas_shared = 0;                    // k_pol grid when other kernels share the SMs with it
+  int overlap = 0;                            // SLVGPU_OVERLAP=1: dispersion / exchange repulsion beside k_pol (experimental)
   double *d_detail = nullptr;
   int *d_queue = nullptr;
   int detail_frames = 0;
@@ -325,6 +326,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   if (d->flags & (SLVGPU_REP | SLVGPU_DISP)) pl->pol_ctas_shared = pl->sm_count * POL_CTAS_SHARED_PER_SM;
   if (const char *ev = getenv("SLVGPU_POL_CTAS")) { const int v = atoi(ev); if (v > 0) pl->pol_ctas_shared = v; }
   if (pl->pol_ctas_shared > pl->pol_ctas) pl->pol_ctas_shared = pl->pol_ctas;     // the workspace is sized for pol_ctas CTAs
+  if (const char *ev = getenv("SLVGPU_OVERLAP")) pl->overlap = atoi(ev) != 0;
   *out = pl;
   return 0;
 }
@@ -360,24 +362,33 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
     CK(cudaEventCreateWithFlags(&pl->ev_elect, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&pl->ev_pol, cudaEventDisableTiming));
   }
-  // Schedule of a chunk: k_frame_elect on the caller's stream, then k_pol there, while dispersion and the exchange-
-  // repulsion batches run on the plan's two side streams (k_pol is FP64-issue bound and leaves its memory system idle,
-  // the integral kernels and the tile pipeline of k_rep_pair are latency / bandwidth bound: they share the SMs).  The
-  // side streams are joined back into the caller's stream before the next chunk reuses the hand-over lists.
+  // Schedule of a chunk.  Default: k_frame_elect, k_disp, k_pol on the caller's stream, then the exchange-repulsion
+  // batches alternating between it and a plan-owned stream (two integral pools, so the integral kernels of one batch run
+  // beside the transform kernel of the other).  With SLVGPU_OVERLAP=1 dispersion and exchange repulsion run on the two
+  // side streams at the same time as k_pol -- measured and not the default: k_pol at two CTAs per SM holds the whole
+  // register file, at one CTA per SM it loses more than the side kernels gain, and the FP64 tensor-core instructions of
+  // k_rep_pair share the FP64 pipe with k_pol's DFMAs (profiles/overlap_pol_ctas_r02.jsonl, profiles/dmma_mix_r02.json).
+  const bool overlap = pl->overlap && do_pol && (do_disp || do_rep);
   for (int64_t f0 = 0; f0 < nframes; f0 += pl->max_chunk) {
     const int nf = (int)((nframes - f0) < pl->max_chunk ? (nframes - f0) : pl->max_chunk);
     ev_begin(pl, 0, st);
     k_frame_elect<<<nf, ELECT_THREADS, sm_el, st>>>(p, d_coords, (int)f0, pl->fl, d_out);
     ev_end(pl, st);
     ++pl->last_launches;
-    const bool side_work = do_disp || do_rep;
-    if (side_work) {
+    if (overlap) {
       CK(cudaEventRecord(pl->ev_elect, st));
       CK(cudaStreamWaitEvent(pl->side[0], pl->ev_elect, 0));
       CK(cudaStreamWaitEvent(pl->side[1], pl->ev_elect, 0));
     }
+    cudaStream_t s_disp = overlap ? pl->side[0] : st;
+    if (do_disp) {
+      ev_begin(pl, 1, s_disp);
+      k_disp<<<nf, DISP_THREADS, sm_di, s_disp>>>(p, (int)f0, pl->fl, d_out);
+      ev_end(pl, s_disp);
+      ++pl->last_launches;
+    }
     if (do_pol) {
-      const int cap = side_work ? pl->pol_ctas_shared : pl->pol_ctas;
+      const int cap = overlap ? pl->pol_ctas_shared : pl->pol_ctas;
       const int g = nf < cap ? nf : cap;
       ev_begin(pl, 2, st);
       CK(cudaMemsetAsync(pl->d_queue, 0, sizeof(int), st));
@@ -385,23 +396,15 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
       ev_end(pl, st);
       ++pl->last_launches;
     }
-    if (do_disp) {
-      ev_begin(pl, 1, pl->side[0]);
-      k_disp<<<nf, DISP_THREADS, sm_di, pl->side[0]>>>(p, (int)f0, pl->fl, d_out);
-      ev_end(pl, pl->side[0]);
-      ++pl->last_launches;
-    }
     if (do_rep) {
       // Exchange repulsion runs in batches of frames sized by the integral pool.  The batch boundaries need the
-      // per-frame fragment counts on the host: one small copy and a synchronisation of side stream 1 per chunk (k_pol
-      // and k_disp are already queued and keep the GPU busy meanwhile).  Batches alternate between the two side
-      // streams (two pools): the integral kernels of one batch overlap the transform kernel of the other.
-      cudaStream_t s1 = pl->side[1];
-      ev_begin(pl, 3, s1);
-      k_rep_scan<<<1, 1024, 0, s1>>>(d_out, (int)f0, nf, pl->rp[0].pair0);
+      // per-frame fragment counts on the host: one small copy and a stream synchronisation per chunk.
+      cudaStream_t s0 = overlap ? pl->side[1] : st, s1 = overlap ? pl->side[0] : pl->side[1];
+      ev_begin(pl, 3, s0);
+      k_rep_scan<<<1, 1024, 0, s0>>>(d_out, (int)f0, nf, pl->rp[0].pair0);
       ++pl->last_launches;
-      CK(cudaMemcpyAsync(pl->h_pair0.data(), pl->rp[0].pair0, ((size_t)nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, s1));
-      CK(cudaStreamSynchronize(s1));
+      CK(cudaMemcpyAsync(pl->h_pair0.data(), pl->rp[0].pair0, ((size_t)nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, s0));
+      CK(cudaStreamSynchronize(s0));                            // serial schedule: everything the batches read is complete from here on
       const int *pair0 = pl->h_pair0.data();
       {
         // pools sized for two concurrent batches covering the chunk, and for the largest single frame
@@ -410,20 +413,20 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
         size_t need = ((size_t)pair0[nf] + 1) / 2;
         if (need < (size_t)fmax) need = (size_t)fmax;
         if (need > (size_t)pl->rp[0].pair_cap && (size_t)pl->rp[0].pair_cap < pl->rep_lim.max_pairs) {
-          CK(cudaStreamSynchronize(pl->side[0]));                 // nothing of an earlier chunk may still use the pools
+          CK(cudaStreamSynchronize(s1));                          // nothing of an earlier chunk may still use the pools
           const int rc = rep_reserve(pl->rp, pl->rep_lim, need, g_err);
-          if (rc) { ev_end(pl, s1); return rc; }
+          if (rc) { ev_end(pl, s0); return rc; }
         }
       }
       int batch = 0;
       for (int fs = 0; fs < nf; ++batch) {
         const RepPool &rp = pl->rp[batch & 1];
-        cudaStream_t sb = pl->side[(batch & 1) ^ 1];              // batch 0 on side stream 1 (side stream 0 starts with k_disp)
+        cudaStream_t sb = (batch & 1) ? s1 : s0;
         int fe = fs;
         while (fe < nf && pair0[fe + 1] - pair0[fs] <= rp.pair_cap) ++fe;
         if (fe == fs) {
-          cudaStreamSynchronize(pl->side[0]); cudaStreamSynchronize(s1);
-          ev_end(pl, s1);
+          cudaStreamSynchronize(s1); cudaStreamSynchronize(s0);
+          ev_end(pl, s0);
           return fail(SLVGPU_ENOMEM, "exchange repulsion: one frame has more fragments inside ecut than the integral pool holds");
         }
         const int nb = fe - fs, npairs = pair0[fe] - pair0[fs];
@@ -457,11 +460,13 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
         ++pl->last_launches;
         fs = fe;
       }
-      CK(cudaEventRecord(pl->ev_side[0], pl->side[0]));          // side stream 1 closes the timing bracket after both finished
-      CK(cudaStreamWaitEvent(s1, pl->ev_side[0], 0));
-      ev_end(pl, s1);
+      if (batch > 1) {                                          // the first stream closes the timing bracket after both finished
+        CK(cudaEventRecord(pl->ev_side[0], s1));
+        CK(cudaStreamWaitEvent(s0, pl->ev_side[0], 0));
+      }
+      ev_end(pl, s0);
     }
-    if (side_work) {                                            // join
+    if (overlap) {                                              // join the side streams
       CK(cudaEventRecord(pl->ev_side[0], pl->side[0]));
       CK(cudaEventRecord(pl->ev_side[1], pl->side[1]));
       CK(cudaStreamWaitEvent(st, pl->ev_side[0], 0));

@@ -141,13 +141,13 @@ def test_subshell_pair_integrals_match_oracle(L, frags, na, nb):
     Lc = np.ascontiguousarray(rng.normal(size=(len(posA), 3)))
     S, T, S1, T1 = IO.one_electron(bA, posA, bB, posB)
     ref = np.stack([S, T, np.einsum('ka,kla->kl', Lc[bA.center], S1), np.einsum('ka,kla->kl', Lc[bA.center], T1)], -1)
-    LP = len(bB) + 7                                   # row length of the record layout V[k][q][l] (any LP >= nbsB)
-    Vp = np.full((len(bA), 4, LP), np.nan)
+    LP = len(bB) + 7                                   # records per row of the layout V[k][l][q] (any LP >= nbsB)
+    Vp = np.full((len(bA), LP, 4), np.nan)
     eA, cA, eB, cB = [np.ascontiguousarray(v, np.float64) for v in (bA.exps, bA.coefs, bB.exps, bB.coefs)]
     sA, sB = np.ascontiguousarray(bA.subshells, np.int32), np.ascontiguousarray(bB.subshells, np.int32)
     L.hm_subshell_V(len(sA), P(sA), P(posA), P(eA), P(cA), P(Lc), len(sB), P(sB), P(posB), P(eB), P(cB), LP, P(Vp))
-    V = np.ascontiguousarray(Vp[:, :, :len(bB)].transpose(0, 2, 1))
+    V = np.ascontiguousarray(Vp[:, :len(bB)])
     assert np.isfinite(V).all()                       # every AO pair is written by exactly the classes walked
-    assert np.isnan(Vp[:, :, len(bB):]).all()         # and nothing beyond the fragment's last basis function
+    assert np.isnan(Vp[:, len(bB):]).all()            # and nothing beyond the fragment's last basis function
     scale = np.abs(ref).max((0, 1))
     assert (np.abs(V - ref).max((0, 1)) < 1e-12 * np.maximum(scale, 1.0)).all(), np.abs(V - ref).max((0, 1))
