@@ -143,6 +143,14 @@ int slvgpu_eval_frames(slvgpu_plan *plan, const double *d_coords, int64_t nframe
 int slvgpu_eval_frames_host(slvgpu_plan *plan, const double *h_coords, int64_t nframes,
                             double *h_out, int32_t *h_status);
 
+/* Same for float32 trajectory records as the MD engines write them (DCD, XTC, NetCDF hold float32): h_coords
+ * [nframes][natoms_src][3] in the file's units; the gather frame[idx] (h_idx [natoms_total] record atom of every plan atom,
+ * NULL = identity) and the conversion to Bohr (x scale; util/slv_md-run_nopp:205 `coords * AngstromToBohr`, md.py idx slice)
+ * happen on the device, so half the bytes cross the host link and no host pass touches the coordinates.  The rows are
+ * bit-identical to slvgpu_eval_frames_host on (double)h_coords[..] * scale. */
+int slvgpu_eval_frames_host_f32(slvgpu_plan *plan, const float *h_coords, int64_t nframes, int32_t natoms_src,
+                                const int32_t *h_idx, double scale, double *h_out, int32_t *h_status);
+
 /* Number of kernel launches issued by the last slvgpu_eval_frames* call on this plan. */
 int64_t slvgpu_last_launches(const slvgpu_plan *plan);
 
@@ -190,6 +198,15 @@ int slvgpu_trig_transform(const double *h_f, int64_t n, double y0, double dy, co
 /* counts of h_x in `bins` (<= 8192) equal-width bins over [lo, hi], last bin closed, as numpy / pylab.hist do for
  * util/slv_hist:60-61. */
 int slvgpu_hist(const double *h_x, int64_t n, double lo, double hi, int32_t bins, int64_t *h_counts);
+
+/* GROMACS XTC trajectories (the `gromacs` branch of util/slv_md-run:117-152, which goes through MDAnalysis): host-side
+ * decoder of the xdr3dcoord compression.  slvgpu_xtc_scan counts the frames and returns the atom count; slvgpu_xtc_read
+ * decodes `count` frames starting at frame `first` into h_xyz [count][natoms][3] float32 nm records (the precision the file
+ * holds -- feed them to slvgpu_eval_frames_host_f32 with scale = 10 * AngstromToBohr); h_step / h_time [count] and h_box
+ * [count][9] may be NULL. */
+int slvgpu_xtc_scan(const char *path, int64_t *nframes, int32_t *natoms);
+int slvgpu_xtc_read(const char *path, int64_t first, int64_t count, float *h_xyz, int32_t *h_step, float *h_time,
+                    float *h_box);
 
 const char *slvgpu_last_error(void);
 const char *slvgpu_version(void);

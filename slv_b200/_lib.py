@@ -44,6 +44,7 @@ def _load():
     lib.slvgpu_plan_destroy.argtypes = [vp]; lib.slvgpu_plan_destroy.restype = None
     lib.slvgpu_eval_frames.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.slvgpu_eval_frames_host.argtypes = [vp, vp, i64, vp, vp]
+    lib.slvgpu_eval_frames_host_f32.argtypes = [vp, vp, i64, i32, vp, dbl, vp, vp]
     lib.slvgpu_last_launches.argtypes = [vp]; lib.slvgpu_last_launches.restype = i64
     lib.slvgpu_set_timing.argtypes = [vp, i32]
     lib.slvgpu_get_timing.argtypes = [vp, vp, vp]
@@ -57,6 +58,8 @@ def _load():
     lib.slvgpu_expres.argtypes = [vp, i64, dbl, i64, vp, vp]
     lib.slvgpu_trig_transform.argtypes = [vp, i64, dbl, dbl, vp, i64, i32, vp]
     lib.slvgpu_hist.argtypes = [vp, i64, dbl, dbl, i32, vp]
+    lib.slvgpu_xtc_scan.argtypes = [ctypes.c_char_p, vp, vp]
+    lib.slvgpu_xtc_read.argtypes = [ctypes.c_char_p, i64, i64, vp, vp, vp, vp]
     lib.slvgpu_last_error.restype = ctypes.c_char_p
     lib.slvgpu_version.restype = ctypes.c_char_p
     return lib

@@ -15,6 +15,7 @@
 #include "k_rep.cuh"
 #include "k_spectra.cuh"
 #include "k_util.cuh"
+#include "xtc_reader.h"
 
 using namespace slv;
 
@@ -50,6 +51,7 @@ struct slvgpu_plan {
   int detail_frames = 0;
   int want_detail = 0;
   double *d_stage_coords2[2] = {nullptr, nullptr}, *d_stage_out = nullptr; int *d_stage_status = nullptr;
+  void *d_stage_src[2] = {nullptr, nullptr}; size_t stage_src_bytes = 0; int32_t *d_idx = nullptr;   // float32 ingest
   int64_t stage_frames = 0, stage_slice = 0;
   int64_t last_launches = 0;
   cudaStream_t own_stream = nullptr, copy_stream = nullptr;
@@ -125,6 +127,8 @@ extern "C" void slvgpu_plan_destroy(slvgpu_plan *pl) {
   for (void *q : pl->allocs) cudaFree(q);
   for (int b = 0; b < 2; ++b) rep_pool_free(pl->rp[b]);
   for (int b = 0; b < 2; ++b) if (pl->d_stage_coords2[b]) cudaFree(pl->d_stage_coords2[b]);
+  for (int b = 0; b < 2; ++b) if (pl->d_stage_src[b]) cudaFree(pl->d_stage_src[b]);
+  if (pl->d_idx) cudaFree(pl->d_idx);
   if (pl->d_stage_out) cudaFree(pl->d_stage_out);
   if (pl->d_stage_status) cudaFree(pl->d_stage_status);
   if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
@@ -479,10 +483,23 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
   return 0;
 }
 
-extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, int64_t nframes, double *h_out,
-                                       int32_t *h_status) {
-  if (!pl || !h_coords || !h_out || !h_status) return fail(SLVGPU_EINVAL, "null argument");
-  if (nframes <= 0) return nframes == 0 ? 0 : fail(SLVGPU_EINVAL, "negative frame count");
+// float32 trajectory records -> the plan's FP64 frame layout: dst[f][a][d] = (double)src[f][idx ? idx[a] : a][d] * scale
+// (the gather of frame[idx] and the unit conversion of util/slv_md-run_nopp:205, done at HBM speed instead of on the host)
+__global__ void k_ingest_f32(const float *__restrict__ src, const int *__restrict__ idx, int natoms_src, int natoms, int64_t nframes,
+                             double scale, double *__restrict__ dst) {
+  const int64_t n = nframes * natoms * 3;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n; w += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = w / ((int64_t)natoms * 3);
+    const int r = (int)(w - f * natoms * 3), a = r / 3, d = r - a * 3;
+    const int sa = idx ? idx[a] : a;
+    dst[w] = (double)src[(f * natoms_src + sa) * 3 + d] * scale;
+  }
+}
+
+// Common host entry: h_src holds nframes records of natoms_src atoms, FP64 (elem 8: natoms_src == natoms_total, no gather, no
+// scaling) or float32 (elem 4: gathered through d_idx and scaled on the device).
+static int eval_frames_host_any(slvgpu_plan *pl, const void *h_src, int elem, int natoms_src, const int32_t *h_idx, double scale,
+                                int64_t nframes, double *h_out, int32_t *h_status) {
   const DevPlan &p = pl->dp;
   if (!pl->own_stream) CK(cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking));
   // Device staging is bounded: two coordinate buffers of one slice each (double buffering), so trajectories far larger
@@ -490,7 +507,8 @@ extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, 
   // slice schedule: a first slice of ~16 MB of coordinates (its copy is the only one not hidden behind compute), then
   // 8x that, then full-size slices so the persistent kernels keep a long queue
   const int64_t slice = pl->max_chunk;
-  int64_t first = (int64_t)(16.0e6 / ((double)p.natoms_total * 24.0));
+  const size_t src_frame_bytes = (size_t)natoms_src * 3 * elem;
+  int64_t first = (int64_t)(16.0e6 / (double)src_frame_bytes);
   first = first < 32 ? 32 : (first > 1024 ? 1024 : first);
   if (first > slice) first = slice;
   const size_t fstride = (size_t)p.natoms_total * 3;
@@ -499,6 +517,12 @@ extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, 
     pl->stage_slice = 0;
     for (int b = 0; b < 2; ++b) CK(cudaMalloc(&pl->d_stage_coords2[b], (size_t)slice * fstride * sizeof(double)));
     pl->stage_slice = slice;
+  }
+  if (elem == 4 && pl->stage_src_bytes < (size_t)slice * src_frame_bytes) {
+    for (int b = 0; b < 2; ++b) { if (pl->d_stage_src[b]) cudaFree(pl->d_stage_src[b]); pl->d_stage_src[b] = nullptr; }
+    pl->stage_src_bytes = 0;
+    for (int b = 0; b < 2; ++b) CK(cudaMalloc(&pl->d_stage_src[b], (size_t)slice * src_frame_bytes));
+    pl->stage_src_bytes = (size_t)slice * src_frame_bytes;
   }
   if (pl->stage_frames < nframes) {
     if (pl->d_stage_out) { cudaFree(pl->d_stage_out); cudaFree(pl->d_stage_status); }
@@ -510,6 +534,10 @@ extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, 
   cudaStream_t st = pl->own_stream;
   if (!pl->copy_stream) CK(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
   while (pl->copy_ev.size() < 4) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); pl->copy_ev.push_back(e); }
+  if (elem == 4 && h_idx) {
+    if (!pl->d_idx) CK(cudaMalloc(&pl->d_idx, (size_t)p.natoms_total * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(pl->d_idx, h_idx, (size_t)p.natoms_total * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
   int64_t launches = 0, f0 = 0;
   for (int64_t c = 0; f0 < nframes; ++c) {
     const int b = (int)(c & 1);
@@ -517,10 +545,18 @@ extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, 
     if (want > slice) want = slice;
     const int64_t n = (nframes - f0) < want ? (nframes - f0) : want;
     if (c >= 2) CK(cudaStreamWaitEvent(pl->copy_stream, pl->copy_ev[2 + b], 0));      // buffer b has been consumed
-    CK(cudaMemcpyAsync(pl->d_stage_coords2[b], h_coords + f0 * fstride, (size_t)n * fstride * sizeof(double),
+    void *dst = elem == 4 ? pl->d_stage_src[b] : (void *)pl->d_stage_coords2[b];
+    CK(cudaMemcpyAsync(dst, (const char *)h_src + (size_t)f0 * src_frame_bytes, (size_t)n * src_frame_bytes,
                        cudaMemcpyHostToDevice, pl->copy_stream));
     CK(cudaEventRecord(pl->copy_ev[b], pl->copy_stream));
     CK(cudaStreamWaitEvent(st, pl->copy_ev[b], 0));
+    if (elem == 4) {
+      const int64_t work = n * (int64_t)fstride;
+      const unsigned grid = (unsigned)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
+      k_ingest_f32<<<grid, 256, 0, st>>>((const float *)pl->d_stage_src[b], h_idx ? pl->d_idx : nullptr, natoms_src, p.natoms_total, n,
+                                          scale, pl->d_stage_coords2[b]);
+      ++launches;
+    }
     int rc = slvgpu_eval_frames(pl, pl->d_stage_coords2[b], n, pl->d_stage_out + f0 * SLVGPU_NOUT, pl->d_stage_status + f0, st);
     if (rc) return rc;
     CK(cudaEventRecord(pl->copy_ev[2 + b], st));
@@ -532,6 +568,25 @@ extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, 
   CK(cudaMemcpyAsync(h_status, pl->d_stage_status, (size_t)nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return 0;
+}
+
+extern "C" int slvgpu_eval_frames_host(slvgpu_plan *pl, const double *h_coords, int64_t nframes, double *h_out,
+                                       int32_t *h_status) {
+  if (!pl || !h_coords || !h_out || !h_status) return fail(SLVGPU_EINVAL, "null argument");
+  if (nframes <= 0) return nframes == 0 ? 0 : fail(SLVGPU_EINVAL, "negative frame count");
+  return eval_frames_host_any(pl, h_coords, 8, pl->dp.natoms_total, nullptr, 1.0, nframes, h_out, h_status);
+}
+
+extern "C" int slvgpu_eval_frames_host_f32(slvgpu_plan *pl, const float *h_coords, int64_t nframes, int32_t natoms_src,
+                                           const int32_t *h_idx, double scale, double *h_out, int32_t *h_status) {
+  if (!pl || !h_coords || !h_out || !h_status) return fail(SLVGPU_EINVAL, "null argument");
+  if (nframes <= 0) return nframes == 0 ? 0 : fail(SLVGPU_EINVAL, "negative frame count");
+  if (natoms_src < 1 || (!h_idx && natoms_src != pl->dp.natoms_total)) return fail(SLVGPU_EINVAL, "natoms_src does not match the plan (no index list given)");
+  if (h_idx)
+    for (int a = 0; a < pl->dp.natoms_total; ++a)
+      if (h_idx[a] < 0 || h_idx[a] >= natoms_src) return fail(SLVGPU_EINVAL, "atom index outside the trajectory record");
+  if (!(scale > 0.0)) return fail(SLVGPU_EINVAL, "scale must be positive");
+  return eval_frames_host_any(pl, h_coords, 4, natoms_src, h_idx, scale, nframes, h_out, h_status);
 }
 
 extern "C" int64_t slvgpu_last_launches(const slvgpu_plan *pl) { return pl ? pl->last_launches : 0; }
@@ -735,5 +790,46 @@ extern "C" int slvgpu_hist(const double *h_x, int64_t n, double lo, double hi, i
   if (e == cudaSuccess) e = cudaMemcpy(h_counts, dc, (size_t)bins * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   cudaFree(dx); if (dc) cudaFree(dc);
   if (e != cudaSuccess) return fail(SLVGPU_ECUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ XTC trajectories (row N1)
+extern "C" int slvgpu_xtc_scan(const char *path, int64_t *nframes, int32_t *natoms) {
+  if (!path || !nframes || !natoms) return fail(SLVGPU_EINVAL, "null argument");
+  slvxtc::File f; f.fh = fopen(path, "rb");
+  if (!f.fh) return fail(SLVGPU_EINVAL, std::string("cannot open ") + path);
+  std::vector<unsigned char> buf; std::string err;
+  int64_t n = 0; int32_t na = 0, na0 = -1, step; float time, box[9];
+  for (;;) {
+    const int rc = slvxtc::read_frame(f, na, step, time, box, nullptr, buf, err);
+    if (rc == 0) break;
+    if (rc < 0) return fail(SLVGPU_EINVAL, std::string(path) + ": " + err);
+    if (na0 < 0) na0 = na;
+    if (na != na0) return fail(SLVGPU_EINVAL, std::string(path) + ": atom count changes between frames");
+    ++n;
+  }
+  *nframes = n; *natoms = na0 < 0 ? 0 : na0;
+  return 0;
+}
+
+extern "C" int slvgpu_xtc_read(const char *path, int64_t first, int64_t count, float *h_xyz, int32_t *h_step, float *h_time,
+                               float *h_box) {
+  if (!path || !h_xyz || first < 0 || count < 0) return fail(SLVGPU_EINVAL, "bad argument");
+  slvxtc::File f; f.fh = fopen(path, "rb");
+  if (!f.fh) return fail(SLVGPU_EINVAL, std::string("cannot open ") + path);
+  std::vector<unsigned char> buf; std::string err;
+  int32_t na = 0, step; float time, box[9];
+  for (int64_t k = 0; k < first + count; ++k) {
+    // (k - first) * na: na is the atom count of the previous frame, and slvgpu_xtc_scan guarantees it does not change
+    float *dst = k < first ? nullptr : (k == first ? h_xyz : h_xyz + (size_t)(k - first) * na * 3);
+    const int rc = slvxtc::read_frame(f, na, step, time, box, dst, buf, err);
+    if (rc == 0) return fail(SLVGPU_EINVAL, std::string(path) + ": fewer frames than requested");
+    if (rc < 0) return fail(SLVGPU_EINVAL, std::string(path) + ": " + err);
+    if (k >= first) {
+      if (h_step) h_step[k - first] = step;
+      if (h_time) h_time[k - first] = time;
+      if (h_box) memcpy(h_box + (size_t)(k - first) * 9, box, sizeof(box));
+    }
+  }
   return 0;
 }

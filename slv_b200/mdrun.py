@@ -5,8 +5,8 @@ the reference's column format: ``# Frame EL-CAMM EL-MEA EL-EA CORR-MEA CORR-EA P
 DISP-EA DISP-ISO TOTAL RMS-C RMS-S RMS-AVE`` (13 shifts %10.2f, 3 rms %10.5f).  Trajectories: a NumPy array
 [nframes, natoms, 3], a ``.npy`` file, or a multi-frame ``.xyz`` file; coordinates in Angstrom are converted to Bohr
 like the reference does (slv_md-run_nopp:205).  DCD (NAMD/CHARMM) and AMBER mdcrd
-files are read natively (the reference goes through MDAnalysis / its own readers, util/slv_md-run:117-152); GROMACS XTC
-(xdr-compressed) is not -- convert it or pass the coordinates as an array.  Frames may be sharded over ranks
+files and GROMACS XTC (xdr3dcoord-compressed, nm) are read natively (the reference goes through MDAnalysis / its own
+readers, util/slv_md-run:117-152); float32 records go to the device as they are (gather + unit conversion there).  Frames may be sharded over ranks
 (``rank``/``world``): each rank evaluates its contiguous block and writes its own rows; frame numbers stay global.
 """
 import sys
@@ -41,8 +41,8 @@ def read_xyz_frames(path):
 
 
 def read_dcd_frames(path, first=0, last=None):
-    """CHARMM/NAMD DCD trajectory (the `namd-charmm` branch of util/slv_md-run:117-152) -> float64 [nframes, natoms, 3]
-    in the file's units (Angstrom).  Little- or big-endian, with or without unit-cell records, fixed atoms unsupported."""
+    """CHARMM/NAMD DCD trajectory (the `namd-charmm` branch of util/slv_md-run:117-152) -> float32 [nframes, natoms, 3]
+    in the file's units (Angstrom), the precision the file holds.  Little- or big-endian, with or without unit-cell records, fixed atoms unsupported."""
     import struct
     with open(path, 'rb') as fh:
         raw = fh.read()
@@ -59,7 +59,7 @@ def read_dcd_frames(path, first=0, last=None):
     frame_bytes = (56 if has_cell else 0) + 3 * (8 + 4 * natoms)
     nset = min(nset, (len(raw) - pos) // frame_bytes) if nset > 0 else (len(raw) - pos) // frame_bytes
     last = nset if last is None else min(last, nset)
-    out = numpy.empty((max(0, last - first), natoms, 3), numpy.float64)
+    out = numpy.empty((max(0, last - first), natoms, 3), numpy.float32)      # as stored: float32 records
     for f in range(first, last):
         q = pos + f * frame_bytes + (56 if has_cell else 0)
         for d in range(3):
@@ -79,15 +79,32 @@ def read_mdcrd_frames(path, natoms, box=False):
     return vals[:nfr * per].reshape(nfr, per)[:, :3 * natoms].reshape(nfr, natoms, 3).copy()
 
 
+def read_xtc_frames(path, first=0, last=None):
+    """GROMACS XTC trajectory (the `gromacs` branch of util/slv_md-run:117-152) -> float32 [nframes, natoms, 3] in nm, the
+    records the file holds; decoded by the library (slv_b200/csrc/xtc_reader.h)."""
+    import ctypes
+    n = ctypes.c_int64(0); na = ctypes.c_int32(0)
+    _lib.check(_lib.lib.slvgpu_xtc_scan(path.encode(), ctypes.byref(n), ctypes.byref(na)))
+    last = n.value if last is None else min(last, n.value)
+    cnt = max(0, last - first)
+    out = numpy.empty((cnt, na.value, 3), numpy.float32)
+    if cnt:
+        _lib.check(_lib.lib.slvgpu_xtc_read(path.encode(), first, cnt, out.ctypes.data, None, None, None))
+    return out
+
+
 def load_trajectory(traj, natoms=None):
-    """numpy array, .npy, multi-frame .xyz, .dcd or AMBER .mdcrd/.crd (needs natoms)."""
+    """numpy array, .npy, multi-frame .xyz, .dcd, GROMACS .xtc (nm) or AMBER .mdcrd/.crd (needs natoms)."""
     if not isinstance(traj, str):
-        return numpy.asarray(traj, numpy.float64)
+        traj = numpy.asarray(traj)
+        return traj if traj.dtype == numpy.float32 else numpy.asarray(traj, numpy.float64)
     low = traj.lower()
     if low.endswith('.npy'):
         return numpy.load(traj)
     if low.endswith('.dcd'):
         return read_dcd_frames(traj)
+    if low.endswith('.xtc'):
+        return read_xtc_frames(traj)
     if low.endswith('.mdcrd') or low.endswith('.crd'):
         assert natoms is not None, 'AMBER trajectories need the number of atoms'
         return read_mdcrd_frames(traj, natoms)
@@ -123,12 +140,18 @@ def run(solinp, traj, out, mode, nframes=None, cuts=(40.0, 17.0, 12.0), no_elect
     args, idx = MDInput(solinp).get()
     efp = EFP(elect=not no_elect, pol=not no_polar, rep=not no_repul, disp=not no_disp, corr=not no_correc,
               ccut=cuts[0], pcut=cuts[1], ecut=cuts[2], freq=True, cunit=True, mode=mode, ea=not no_ea)
-    traj = numpy.asarray(load_trajectory(traj, natoms), numpy.float64)
+    traj_name = traj
+    traj = load_trajectory(traj, natoms)
+    f32 = traj.dtype == numpy.float32          # trajectory records as the MD engine wrote them: gather + units on the device
+    if not f32:
+        traj = numpy.asarray(traj, numpy.float64)
     if nframes is not None:
         traj = traj[:nframes]
     lo, hi = frame_range(len(traj) - first_frame, rank, world)
     lo += first_frame; hi += first_frame
-    scale = AngstromToBohr if units.lower().startswith('ang') else 1.0
+    if isinstance(traj_name, str) and traj_name.lower().endswith('.xtc') and units.lower().startswith('ang'):
+        units = 'nm'                           # XTC records are in nm whatever the caller assumed for the other formats
+    scale = {'ang': AngstromToBohr, 'nm': 10.0 * AngstromToBohr}.get(units.lower()[:3] if units.lower().startswith('ang') else units.lower(), 1.0)
     all_rows, all_status = [], []
     if world > 1 and isinstance(out, str):
         # every rank writes its own block of frames: one file per rank (the ranks would clobber a shared path)
@@ -139,8 +162,13 @@ def run(solinp, traj, out, mode, nframes=None, cuts=(40.0, 17.0, 12.0), no_elect
     first = True
     for b0 in range(lo, hi, batch):
         b1 = min(hi, b0 + batch)
-        coords = numpy.ascontiguousarray(traj[b0:b1][:, idx, :] * scale)
-        rows, status = efp.eval_frames(coords, *args) if first else efp.eval_frames(coords)
+        if f32:
+            kw = dict(scale=scale, idx=numpy.asarray(idx, numpy.int32))
+            coords = numpy.ascontiguousarray(traj[b0:b1])
+        else:
+            kw = {}
+            coords = numpy.ascontiguousarray(traj[b0:b1][:, idx, :] * scale)
+        rows, status = efp.eval_frames(coords, *args, **kw) if first else efp.eval_frames(coords, **kw)
         first = False
         bad = numpy.nonzero(numpy.asarray(status) != 0)[0]
         if len(bad):
@@ -166,7 +194,7 @@ def main(argv=None):
     import argparse
     ap = argparse.ArgumentParser(description='SolEFP frequency shifts over an MD trajectory (slv_md-run on the B200)')
     ap.add_argument('-i', '--inp', required=True, help='$Frag input file')
-    ap.add_argument('-t', '--traj', required=True, help='.npy [nframes,natoms,3], multi-frame .xyz, .dcd or AMBER .mdcrd')
+    ap.add_argument('-t', '--traj', required=True, help='.npy [nframes,natoms,3], multi-frame .xyz, .dcd, .xtc or AMBER .mdcrd')
     ap.add_argument('--natoms', type=int, default=None, help='atoms per frame (AMBER trajectories)')
     ap.add_argument('--first-frame', type=int, default=0, help='0-based frame to start from (resume)')
     ap.add_argument('--append', action='store_true', help='append to an existing report (resume)')
@@ -199,7 +227,7 @@ def _main_distributed(a):
     if cuda:
         torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
     dist.init_process_group('nccl' if cuda else 'gloo')
-    traj = numpy.asarray(load_trajectory(a.traj, a.natoms), numpy.float64)
+    traj = load_trajectory(a.traj, a.natoms)
     if a.nframes is not None:
         traj = traj[:a.nframes]
     rows, status = run(a.inp, traj, None, a.mode, None, (a.ccut, a.pcut, a.ecut), a.no_elect, a.no_polar, a.no_repul, a.no_disp,

@@ -235,10 +235,36 @@ class Plan(object):
         _lib.check(_lib.lib.slvgpu_eval_frames(self._h, coords.data_ptr(), nf, out.data_ptr(), status.data_ptr(), st))
         return out, status
 
-    def eval_host(self, coords, out=None, status=None):
-        """coords: numpy or pinned CPU torch tensor [nframes, natoms_total, 3] float64 (host buffers;
-        the H2D / D2H copies happen inside the call)."""
-        if hasattr(coords, 'data_ptr'):
+    def eval_host(self, coords, out=None, status=None, scale=None, idx=None):
+        """coords: numpy or pinned CPU torch tensor (host buffers; the H2D / D2H copies happen inside the call).
+        float64 [nframes, natoms_total, 3] in Bohr, or float32 [nframes, natoms_src, 3] in the trajectory file's units:
+        then `scale` converts to Bohr and `idx` (natoms_total record atoms, MDInput's idx) gathers the plan's atoms,
+        both on the device."""
+        is_t = hasattr(coords, 'data_ptr')
+        f32 = (str(coords.dtype).endswith('float32'))
+        if f32:
+            if not is_t:
+                coords = numpy.ascontiguousarray(coords, numpy.float32)
+            else:
+                assert coords.is_contiguous()
+            nf, nsrc = int(coords.shape[0]), int(coords.shape[1])
+            cptr = coords.data_ptr() if is_t else coords.ctypes.data
+            if idx is not None:
+                idx = numpy.ascontiguousarray(idx, numpy.int32)
+                assert idx.shape == (self.natoms_total,), 'idx must name one trajectory atom per plan atom'
+            else:
+                assert nsrc == self.natoms_total
+            if out is None:
+                out = numpy.empty((nf, _lib.NOUT), numpy.float64)
+            if status is None:
+                status = numpy.empty((nf,), numpy.int32)
+            optr = out.data_ptr() if hasattr(out, 'data_ptr') else out.ctypes.data
+            sptr = status.data_ptr() if hasattr(status, 'data_ptr') else status.ctypes.data
+            _lib.check(_lib.lib.slvgpu_eval_frames_host_f32(self._h, cptr, nf, nsrc, None if idx is None else idx.ctypes.data,
+                                                           1.0 if scale is None else float(scale), optr, sptr))
+            return out, status
+        assert scale is None and idx is None, 'scale / idx belong to the float32 (trajectory-record) entry'
+        if is_t:
             nf = coords.shape[0]; cptr = coords.data_ptr()
             assert coords.is_contiguous()
         else:

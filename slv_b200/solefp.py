@@ -238,10 +238,13 @@ class EFP(UNITS):
             print(self)
         return
 
-    def eval_frames(self, coords, ind=None, nmol=None, bsm=None, supl=None, reord=None, out=None, status=None):
+    def eval_frames(self, coords, ind=None, nmol=None, bsm=None, supl=None, reord=None, out=None, status=None,
+                    scale=None, idx=None):
         """Batched evaluation: coords [nframes, natoms, 3] (Bohr).  A CUDA torch tensor is evaluated in
         place on the device and CUDA tensors are returned; a host array (numpy / pinned torch) goes
-        through the host entry point.  Returns (rows [nframes,16] in a.u., status [nframes])."""
+        through the host entry point.  A float32 host array is taken as raw trajectory records [nframes, natoms_src, 3]
+        in the file's units: `scale` converts to Bohr and `idx` (MDInput's atom slice) picks the atoms, both on the
+        device.  Returns (rows [nframes,20] in a.u., status [nframes])."""
         if ind is not None:
             self._ind = numpy.array(ind, int); self._nmol = numpy.array(nmol, int)
             if bsm is not None:
@@ -253,7 +256,7 @@ class EFP(UNITS):
         plan = self._get_plan()
         if hasattr(coords, 'is_cuda') and coords.is_cuda:
             return plan.eval_device(coords, out, status)
-        return plan.eval_host(coords, out, status)
+        return plan.eval_host(coords, out, status, scale=scale, idx=idx)
 
     def shifts_of(self, rows):
         """Dictionary of per-frame arrays with the reference's shift keys."""

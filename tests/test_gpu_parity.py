@@ -487,3 +487,48 @@ def test_ill_conditioned_polarisation_still_converges(frags):
         ref = O.eval_frame(X[f], ind, nmol, [sol.get(), wat.get(), dmso.get()], [None] * 3, [None] * 3, 4, 40.0, 17.0, 12.0,
                            elect=True, pol=True)
         assert abs(rows[f, 4] * c - ref['pol_mea'] * c) < max(TOL, 1e-8 * abs(ref['pol_mea'] * c)), (f, rows[f, 4] * c, ref['pol_mea'] * c)
+
+
+def test_float32_ingest_is_bit_identical_to_float64_ingest(frags):
+    """Trajectory files hold float32 (DCD, XTC).  The float32 host entry (gather frame[idx] and x AngstromToBohr on the
+    device) must give the rows of the float64 entry fed with the same float32 values converted on the host, bit for
+    bit -- including a trajectory record that carries atoms the $Frag input does not use, in another order."""
+    from slv_b200 import synth
+    from slv_b200.units import AngstromToBohr
+    sol, wat = frags('nma'), frags('water')
+    nw = 40
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos()], np.zeros(nw, int), 37, seed=71)
+    nat = X.shape[1]
+    rng = np.random.default_rng(5)
+    nsrc = nat + 9                                                   # nine atoms of the record are not part of the system
+    idx = rng.permutation(nsrc)[:nat].astype(np.int32)
+    rec = rng.normal(0, 5, (len(X), nsrc, 3))
+    rec[:, idx, :] = X / AngstromToBohr                              # Angstrom records
+    rec32 = np.ascontiguousarray(rec, np.float32)
+    ind = [0] + [1] * nw; nmol = [12] + [3] * nw
+    efp = _efp(rep=True, ccut=30.0, pcut=14.0, ecut=11.0)
+    r32, s32 = efp.eval_frames(rec32, ind, nmol, [sol, wat], [None, None], [None, None], scale=AngstromToBohr, idx=idx)
+    x64 = np.ascontiguousarray(rec32[:, idx, :].astype(np.float64) * AngstromToBohr)
+    r64, s64 = efp.eval_frames(x64)
+    assert np.array_equal(r32, r64) and np.array_equal(s32, s64) and int(s32.max()) == 0
+    assert np.abs(r32[:, :8]).max() > 0
+    efp.max_chunk = 8                                                # several slices through the double-buffered staging
+    r32b, _ = efp.eval_frames(rec32, scale=AngstromToBohr, idx=idx)
+    assert np.array_equal(r32b, r64)
+
+
+def test_mdrun_reads_xtc_like_the_same_coordinates_as_an_array(frags, golden, tmp_path):
+    """N1: the frame loop on a GROMACS XTC file (nm, float32, decoded by the library, gathered and converted on the
+    device) writes the report it writes for the same float32 coordinates handed over as an array in Angstrom."""
+    from slv_b200 import mdrun
+    from util import BohrToAngstrom
+    from xtc_writer import write_xtc
+    X = np.array(scan_geometries(golden, 6)) * BohrToAngstrom * 0.1          # nm
+    fn = str(tmp_path / 'scan.xtc'); write_xtc(fn, X)
+    inp = '$Frag\n  NMA  nma\n  supl 2,8,3,5\n  atoms 1-12  1\n$endFrag\n$Frag\n  water water\n  supl 1-3\n  atoms 13-15 1\n$endFrag\n'
+    o1, o2 = tmp_path / 'a.dat', tmp_path / 'b.dat'
+    r1, s1 = mdrun.run(inp, fn, str(o1), 8, cuts=(1e10, 1e10, 1e10))
+    Y = mdrun.read_xtc_frames(fn)
+    r2, s2 = mdrun.run(inp, np.ascontiguousarray(Y.astype(np.float64) * 10.0), str(o2), 8, cuts=(1e10, 1e10, 1e10))
+    assert np.abs(r1[:, :8] - r2[:, :8]).max() < 1e-12 and o1.read_text().split('\n')[1:] == o2.read_text().split('\n')[1:]
+    assert abs(float(o1.read_text().split('\n')[1].split()[1]) - round(golden['f']['solcamm'], 2)) < 0.02

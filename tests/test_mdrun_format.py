@@ -64,3 +64,44 @@ def test_dcd_and_mdcrd_readers(tmp_path):
                 fh.write(''.join('%8.3f' % v for v in row[i:i + 10]) + '\n')
     Y = mdrun.read_mdcrd_frames(str(fn), 7, box=True)
     assert Y.shape == X.shape and np.abs(Y - X).max() < 1e-9
+
+
+def test_xtc_reader_roundtrip(tmp_path):
+    """The library's XTC decoder (slv_b200/csrc/xtc_reader.h, host code: no GPU needed) against files written by the
+    test-side transcription of the published xdr3dcoord compressor (tests/xtc_writer.py): water-like molecules (runs of
+    small triples with the swapped first pair), a dilute gas (large triples only), coordinate ranges beyond 2^24 grid
+    steps (the per-axis bit-size branch), nine atoms or fewer (uncompressed floats), frame sub-ranges."""
+    from slv_b200 import mdrun, _lib
+    from xtc_writer import write_xtc
+    rng = np.random.default_rng(8)
+    # 1. liquid-like: 300 three-atom molecules, atoms within 0.1 nm of each other
+    cent = rng.uniform(0, 4, (7, 300, 1, 3))
+    liquid = (cent + rng.normal(0, 0.04, (7, 300, 3, 3))).reshape(7, 900, 3)
+    # 2. gas: no two consecutive atoms close
+    gas = rng.uniform(-20, 20, (3, 50, 3))
+    # 3. huge box: per-axis bit sizes (range > 0xffffff grid steps at precision 1000)
+    huge = rng.uniform(-9000, 9000, (2, 40, 3)); huge[:, 1::2] = huge[:, ::2] + rng.normal(0, 0.02, (2, 20, 3))
+    # 4. tiny system
+    tiny = rng.uniform(0, 1, (4, 9, 3))
+    for name, X, prec in (('liquid', liquid, 1000.0), ('liquid100', liquid, 100.0), ('gas', gas, 1000.0), ('huge', huge, 1000.0),
+                          ('tiny', tiny, 1000.0)):
+        fn = str(tmp_path / (name + '.xtc'))
+        write_xtc(fn, X, precision=prec)
+        Y = mdrun.read_xtc_frames(fn)
+        assert Y.dtype == np.float32 and Y.shape == X.shape, name
+        if name == 'tiny':
+            assert np.array_equal(Y, X.astype(np.float32))
+        else:
+            q = np.where(X >= 0, np.floor(X * prec + 0.5), np.ceil(X * prec - 0.5))
+            assert np.array_equal(Y, (q.astype(np.int64).astype(np.float32) * np.float32(1.0 / np.float32(prec)))), name
+        assert np.array_equal(mdrun.read_xtc_frames(fn, 1, 2), Y[1:2])
+        assert np.array_equal(mdrun.load_trajectory(fn), Y)
+    import pytest
+    bad = tmp_path / 'bad.xtc'
+    bad.write_bytes(b'\x00\x00\x00\x01' * 20)
+    with pytest.raises(_lib.SlvGpuError):
+        mdrun.read_xtc_frames(str(bad))
+    trunc = tmp_path / 'trunc.xtc'
+    trunc.write_bytes(open(str(tmp_path / 'liquid.xtc'), 'rb').read()[:3000])
+    with pytest.raises(_lib.SlvGpuError):
+        mdrun.read_xtc_frames(str(trunc))
