@@ -35,6 +35,7 @@ constexpr int REP_THREADS = 128;
 constexpr int REP_INT_THREADS = 128;
 constexpr int REP_CS = 12;        // row stride (doubles) of a solute coefficient octet tile: 8 k's + 4 pad, == 4 (mod 8)
 constexpr int REP_MAX_NIT = 3;    // solute LMO tiles of 8 (nmos <= 24)
+constexpr int REP_IP = 8 * REP_MAX_NIT;   // rows of a solute coefficient tile (fixed: strides become compile-time constants)
 constexpr int REP_MAX_NNT = 5;    // fragment LMO tiles of 8 (nmos <= 40)
 
 // Records per row of the integral block of a fragment with nbs basis functions: V[k][l][q], l padded to the k-step of the
@@ -64,7 +65,8 @@ struct RepLimits { size_t max_pairs = 0; };
 inline int rep_alloc(RepPool rp[2], RepLimits &lim, std::vector<void *> &allocs, std::string &err, int nmosc, int nbasc,
                      int natc, int max_nbas, int max_nat, int max_chunk, int list_cap) {
   // integral pools: together up to 8 GiB and at most a quarter of the free memory, never more than the worst case
-  const int nbsA16 = (nbasc + 15) & ~15, IP = (nmosc + 7) & ~7;
+  const int nbsA16 = (nbasc + 15) & ~15, IP = REP_IP;
+  (void)nmosc;
   const size_t sV = (size_t)nbsA16 * 4 * rep_lp(max_nbas);
   const size_t sCA = (size_t)(nbsA16 / 8) * 2 * IP * REP_CS;
   size_t free_b = 0, total_b = 0;
@@ -148,7 +150,7 @@ inline RepSmem rep_smem_plan(int nmosA, int nbsA, int natA, int nmosB, int nbsB,
   (void)nbsA;
   s.LP = rep_lp(nbsB); s.LK = (nbsB + 3) & ~3;
   s.NNT = (nmosB + 7) / 8; s.JS = 8 * s.NNT + 4;
-  s.IP = (nmosA + 7) & ~7; s.nit = s.IP / 8;
+  s.IP = REP_IP; s.nit = (nmosA + 7) / 8;
   s.KT = (size_t)16 * 4 * s.LP * 8 <= 24 * 1024 ? 16 : 8;                     // tiles of 16 solute functions while they stay small
   const size_t tileV = (size_t)s.KT * 4 * s.LP, tileCA = (size_t)(s.KT / 8) * 2 * s.IP * REP_CS, tileX = (size_t)4 * s.KT * s.JS;
   const int nij = nmosA * nmosB;
@@ -331,7 +333,8 @@ k_rep_pair(const DevPlan p, int type, FrameLists fl, RepPool rp, RepSmem L) {
   const int natA = tm0[SLVGPU_M_NATOMS], nmosA = tm0[SLVGPU_M_NMOS], nbsA = tm0[SLVGPU_M_NBASIS];
   const int natB = tm[SLVGPU_M_NATOMS], nmosB = tm[SLVGPU_M_NMOS], nbsB = tm[SLVGPU_M_NBASIS];
   const int nij = nmosA * nmosB;
-  const int LP = L.LP, JS = L.JS, IP = L.IP, nit = L.nit;
+  constexpr int JS = 8 * NNT + 4;                        // row stride of the CB / X tiles (== 4 mod 8: conflict-free B fragments)
+  const int LP = L.LP, nit = L.nit;
   double *Vt = sm + L.oV, *CAs = sm + L.oCA, *Xs = sm + L.oX, *CBs = sm + L.oCB, *IJ = sm + L.oIJ;
   double *RI = sm + L.oTab, *RM = RI + nij, *col1 = RM + nij, *col2 = col1 + nmosB, *u3 = col2 + nmosB, *w3 = u3 + nmosB;
   double *row1 = w3 + nmosB, *row2 = row1 + nmosA, *u4 = row2 + nmosA, *w4 = u4 + nmosA;
@@ -342,7 +345,7 @@ k_rep_pair(const DevPlan p, int type, FrameLists fl, RepPool rp, RepSmem L) {
   const double *CAg = rp.CA + (size_t)fi * rp.sCA;
   const int ntile = (nbsA + KT - 1) / KT;
   const unsigned tileV_bytes = (unsigned)((size_t)KT * 4 * LP * sizeof(double));
-  const unsigned tileCA_doubles = (unsigned)((KT / 8) * 2 * IP * REP_CS);
+  constexpr unsigned tileCA_doubles = (unsigned)((KT / 8) * 2 * REP_IP * REP_CS);
   const size_t tileV_doubles = (size_t)KT * 4 * LP, tileX = (size_t)4 * KT * JS;
 
   if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
@@ -375,7 +378,7 @@ k_rep_pair(const DevPlan p, int type, FrameLists fl, RepPool rp, RepSmem L) {
   }
   for (int w = tid; w < L.LK * JS; w += NT) CBs[w] = 0.0;
   __syncthreads();
-  rotate_vecl_rows(p, tm, p.dtab + tm[SLVGPU_M_O_VECL], nmosB, R, CBs, [JS](int j, int l) { return (size_t)l * JS + j; });   // CBs[l][j]
+  rotate_vecl_rows(p, tm, p.dtab + tm[SLVGPU_M_O_VECL], nmosB, R, CBs, [](int j, int l) { return l * JS + j; });   // CBs[l][j]
   for (int w = tid; w < nij; w += NT) {
     const int i = w / nmosB, j = w - i * nmosB;
     const double dx = riA[i * 3] - riB[j * 3], dy = riA[i * 3 + 1] - riB[j * 3 + 1], dz = riA[i * 3 + 2] - riB[j * 3 + 2];
@@ -415,18 +418,38 @@ k_rep_pair(const DevPlan p, int type, FrameLists fl, RepPool rp, RepSmem L) {
   }
   __syncthreads();
 
-  // ---- tile loop.  Phase B units u = kind * nit + itile (kind: S, T, Sm, Tm), unit u belongs to warp u % 4
+  // ---- tile loop.  Phase B units u = kind * nit + itile (kind: S, T, Sm, Tm), unit u belongs to warp u % 4.  Every
+  //      offset below is a 32-bit count of doubles inside one shared-memory buffer, fixed before the loop.
   double accB[REP_MAX_NIT][NNT][2];
+  int ukind[REP_MAX_NIT], uoffA[REP_MAX_NIT], uoffX0[REP_MAX_NIT], uoffX1[REP_MAX_NIT], urow[REP_MAX_NIT];
 #pragma unroll
-  for (int s = 0; s < REP_MAX_NIT; ++s)
+  for (int s = 0; s < REP_MAX_NIT; ++s) {
 #pragma unroll
     for (int n = 0; n < NNT; ++n) accB[s][n][0] = accB[s][n][1] = 0.0;
-  const int nunit = 4 * nit, nks = L.LK >> 2;
+    const int u = warp + 4 * s;
+    const int kind = u < 4 * nit ? u / nit : -1, itile = u - kind * nit;
+    ukind[s] = kind;
+    urow[s] = itile * 8 + g;
+    uoffA[s] = (itile * 8 + g) * REP_CS + c4;
+    uoffX0[s] = (max(kind, 0) * KT + c4) * JS + g;
+    uoffX1[s] = ((kind & 1) * KT + c4) * JS + g;           // Sm, Tm: the C1 product uses X_S, X_T
+  }
+  const int nks = L.LK >> 2;
   constexpr int MW = KT / 8;                              // M-tiles (8 integral rows = 2 basis functions x 4 kinds) per warp and tile
+  constexpr int CA_P = REP_IP * REP_CS, CA_OCT = 2 * CA_P;
+  const int offVa = ((warp * 2 + (g >> 2)) * LP + c4) * 4 + (g & 3), strideVm = 32 * LP;
+  const int offCb = c4 * JS + g;
+  int offXw[MW];                                          // where this lane's two X values of M-tile m go
+#pragma unroll
+  for (int m = 0; m < MW; ++m) {
+    const int row = (m * 4 + warp) * 8 + g;               // tile row -> (basis function row >> 2, integral kind row & 3)
+    offXw[m] = ((row & 3) * KT + (row >> 2)) * JS + 2 * c4;
+  }
+  int vbuf = 0, cabuf = 0;
   for (int t = 0; t < ntile; ++t) {
     mbar_wait(bar + (t & 1), (unsigned)((t >> 1) & 1));
-    const double *Vb = Vt + (size_t)(t % L.nbuf) * tileV_doubles;
-    double *Xb = Xs + (size_t)(t & 1) * tileX;
+    const double *Vb = Vt + (size_t)vbuf * tileV_doubles;
+    double *Xb = Xs + (t & 1) * (int)tileX;
     // phase A: X[(k,q)][j] = sum_l V[(k,q)][l] CB[j][l]; warp w owns M-tiles w, w + 4
     {
       double acc[MW][NNT][2];
@@ -435,62 +458,57 @@ k_rep_pair(const DevPlan p, int type, FrameLists fl, RepPool rp, RepSmem L) {
 #pragma unroll
         for (int n = 0; n < NNT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
       // A fragment: row g of M-tile mt is (basis function 2 mt + g / 4, kind g % 4), column c4 is l = 4 ks + c4
-      const double *va = Vb + ((size_t)(warp * 2 + (g >> 2)) * LP + c4) * 4 + (g & 3);
-      const double *cb = CBs + (size_t)c4 * JS + g;
+      const double *va = Vb + offVa;
+      const double *cb = CBs + offCb;
 #pragma unroll 2
       for (int ks = 0; ks < nks; ++ks) {
         double a[MW], b[NNT];
 #pragma unroll
-        for (int m = 0; m < MW; ++m) a[m] = va[(size_t)m * 32 * LP + ks * 16];
+        for (int m = 0; m < MW; ++m) a[m] = va[m * strideVm];
 #pragma unroll
-        for (int n = 0; n < NNT; ++n) b[n] = cb[(size_t)ks * 4 * JS + n * 8];
+        for (int n = 0; n < NNT; ++n) b[n] = cb[n * 8];
 #pragma unroll
         for (int m = 0; m < MW; ++m)
 #pragma unroll
           for (int n = 0; n < NNT; ++n) dmma884(acc[m][n][0], acc[m][n][1], a[m], b[n]);
+        va += 16; cb += 4 * JS;
       }
 #pragma unroll
-      for (int m = 0; m < MW; ++m) {
-        const int row = (m * 4 + warp) * 8 + g, kk = row >> 2, q = row & 3;      // tile row -> (basis function, integral kind)
-        double *x = Xb + ((size_t)q * KT + kk) * JS + 2 * c4;
+      for (int m = 0; m < MW; ++m)
 #pragma unroll
-        for (int n = 0; n < NNT; ++n) *reinterpret_cast<double2 *>(x + n * 8) = make_double2(acc[m][n][0], acc[m][n][1]);
-      }
+        for (int n = 0; n < NNT; ++n) *reinterpret_cast<double2 *>(Xb + offXw[m] + n * 8) = make_double2(acc[m][n][0], acc[m][n][1]);
     }
     __syncthreads();                                       // X complete; every warp is done with this V buffer
     if (tid == 0 && t + L.nbuf < ntile) issue(t + L.nbuf);
     // phase B: IJ[kind][i][j] += sum_k C[i][k] X[k][q][j]
     {
-      const double *cat = CAs + (size_t)(t % ncab) * tileCA_doubles;
+      const double *cat = CAs + cabuf * (int)tileCA_doubles;
 #pragma unroll
       for (int s = 0; s < REP_MAX_NIT; ++s) {
-        const int u = warp + 4 * s;
-        if (u < nunit) {
-          const int kind = u / nit, itile = u - kind * nit;
-          const double *ca = cat + (size_t)(itile * 8 + g) * REP_CS + c4;
-          const double *x0 = Xb + ((size_t)kind * KT + c4) * JS + g;               // X_kind rows
-          const double *x1 = Xb + ((size_t)(kind & 1) * KT + c4) * JS + g;         // Sm, Tm: the C1 product uses X_S, X_T
+        if (ukind[s] >= 0) {
+          const double *ca = cat + uoffA[s], *x0 = Xb + uoffX0[s], *x1 = Xb + uoffX1[s];
+          const bool two = ukind[s] >= 2;
 #pragma unroll
           for (int k4 = 0; k4 < KT / 4; ++k4) {
-            const int o = k4 >> 1, kk0 = (k4 & 1) * 4;
-            const double a0 = ca[(size_t)o * 2 * IP * REP_CS + kk0];
+            const double a0 = ca[(k4 >> 1) * CA_OCT + (k4 & 1) * 4];
 #pragma unroll
-            for (int n = 0; n < NNT; ++n) dmma884(accB[s][n][0], accB[s][n][1], a0, x0[(size_t)k4 * 4 * JS + n * 8]);
-            if (kind >= 2) {
-              const double a1 = ca[(size_t)(o * 2 + 1) * IP * REP_CS + kk0];
+            for (int n = 0; n < NNT; ++n) dmma884(accB[s][n][0], accB[s][n][1], a0, x0[k4 * 4 * JS + n * 8]);
+            if (two) {
+              const double a1 = ca[(k4 >> 1) * CA_OCT + CA_P + (k4 & 1) * 4];
 #pragma unroll
-              for (int n = 0; n < NNT; ++n) dmma884(accB[s][n][0], accB[s][n][1], a1, x1[(size_t)k4 * 4 * JS + n * 8]);
+              for (int n = 0; n < NNT; ++n) dmma884(accB[s][n][0], accB[s][n][1], a1, x1[k4 * 4 * JS + n * 8]);
             }
           }
         }
       }
     }
+    if (++vbuf == L.nbuf) vbuf = 0;
+    if (++cabuf == ncab) cabuf = 0;
   }
 #pragma unroll
   for (int s = 0; s < REP_MAX_NIT; ++s) {
-    const int u = warp + 4 * s;
-    if (u < nunit) {
-      const int kind = u / nit, itile = u - kind * nit, i = itile * 8 + g;
+    if (ukind[s] >= 0) {
+      const int kind = ukind[s], i = urow[s];
 #pragma unroll
       for (int n = 0; n < NNT; ++n) {
         const int j = n * 8 + 2 * c4;
