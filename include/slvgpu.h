@@ -43,7 +43,10 @@ enum {
   SLVGPU_POL_NCENT = 17, /* polarisable centres of the many-body solve                                  */
   SLVGPU_POL_NSITE = 18, /* DMTP sites contributing fields                                              */
   SLVGPU_POL_PAIRS = 19, /* ordered centre pairs of different molecules = dipole-tensor applies per sweep */
-  SLVGPU_NOUT = 20
+  /* SolCAMM + corrections against the non-EFP environment (instances of types flagged SLVGPU_M_ENV): EFP.eval_dma,
+   * solvshift/solefp.py:151-178, 798-903 -- no cut-off, never part of the polarisation / dispersion / repulsion layers */
+  SLVGPU_ENV_ELE_MEA = 20, SLVGPU_ENV_ELE_EA = 21, SLVGPU_ENV_COR_MEA = 22, SLVGPU_ENV_COR_EA = 23,
+  SLVGPU_NOUT = 24
 };
 
 /* per-frame status bits */
@@ -73,7 +76,8 @@ enum {
   SLVGPU_M_IO_BFNP,   /* itab: [nbasis] number of primitives                                     */
   SLVGPU_M_O_BFEXP,   /* dtab: [nbasis][6] exponents                                             */
   SLVGPU_M_O_BFCOEF,  /* dtab: [nbasis][6] normalised contraction coefficients                   */
-  SLVGPU_M_REMOVABLE, /* 1: polarisation of this type is treated pair-wise (remove_clashes)          */
+  SLVGPU_M_REMOVABLE, /* 1: polarisation of this type is treated pair-wise (remove_clashes); 2: the type is part of the
+                       * non-EFP electrostatic environment of EFP.eval_dma (point multipoles riding on frame atoms)   */
   SLVGPU_M_NSUBSH,   /* number of basis sub-shells (an SP shell counts as an S and a P sub-shell)  */
   SLVGPU_M_IO_SUBSH, /* itab: [nsubsh][4] atom, first function, angular momentum, primitives      */
   SLVGPU_M_IO_SHPAIR, /* itab: exchange-repulsion integral work list against the solute: [24] class offsets, then the

@@ -11,12 +11,13 @@ import numpy
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('SLVGPU_LIB') or os.path.join(_HERE, 'csrc', 'libslvgpu.so')   # SLVGPU_LIB: developer override (kernel variants)
 
-NOUT = 20
+NOUT = 24
 NMETA = 32
 NSOL = 16
 FLAG = dict(elect=1, ea=2, corr=4, pol=8, disp=16, rep=32)
 OUT = dict(ele_mea=0, ele_ea=1, cor_mea=2, cor_ea=3, pol_mea=4, rep_mea=5, dis_mea=6, dis_mea_iso=7,
-           rms_c=8, rms_smax=9, rms_ave=10, n_elect=11, n_pol=12, n_rep=13, pol_iters=14, pol_resid=15, pol_add=16, pol_ncent=17, pol_nsite=18, pol_pairs=19)
+           rms_c=8, rms_smax=9, rms_ave=10, n_elect=11, n_pol=12, n_rep=13, pol_iters=14, pol_resid=15, pol_add=16, pol_ncent=17, pol_nsite=18, pol_pairs=19,
+           env_ele_mea=20, env_ele_ea=21, env_cor_mea=22, env_cor_ea=23)
 M = dict(NATOMS=0, NDMA=1, NPOL=2, NMOS=3, NBASIS=4, NSUPL=5, IO_SUPL=6, IO_REORD=7, O_POS=8, O_RDMA=9, O_MOM=10,
          O_RPOL=11, O_POL=12, O_POLINV=13, O_DPOLI=14, O_LMOC=15, O_FOCK=16, O_VECL=17, O_ZNUC=18, IO_BFC=19,
          IO_BFL=20, IO_BFNP=21, O_BFEXP=22, O_BFCOEF=23, REMOVABLE=24, NSUBSH=25, IO_SUBSH=26, IO_SHPAIR=27)

@@ -77,6 +77,7 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, Fr
 
   const double cx = s_xf[13], cy = s_xf[14], cz = s_xf[15];
   double e_mea = 0.0, e_ea = 0.0, c_mea = 0.0, c_ea = 0.0, rms_sum = 0.0, rms_max = 0.0;
+  double v_mea = 0.0, v_ea = 0.0, w_mea = 0.0, w_ea = 0.0;          // the same four sums over the non-EFP environment
   int n_c = 0, n_p = 0, n_e = 0;
   const int nsolv = p.ninst - 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -95,11 +96,13 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, Fr
       const double dx = cx - mx, dy = cy - my, dz = cz - mz;
       const double rr = sqrt(dx * dx + dy * dy + dz * dz);
       flag = (rr < p.ccut ? 4 : 0) | (rr < p.pcut ? 1 : 0) | (rr < p.ecut ? 2 : 0);
+      const int *tm = tmeta(p, p.inst_type[i]);
+      const bool env = tm[SLVGPU_M_REMOVABLE] == 2;       // environment of eval_dma: no cut-off, electrostatics only
+      if (env) flag = 4;
       if (flag) {
-        const int *tm = tmeta(p, p.inst_type[i]);
         fit_instance(p, tm, xi, rot, tr, rms);
         if (flag & 4) {
-          ++n_c; rms_sum += rms; rms_max = fmax(rms_max, rms);
+          if (!env) { ++n_c; rms_sum += rms; rms_max = fmax(rms_max, rms); }
           if (p.flags & SLVGPU_ELECT) {
             const int nd = tm[SLVGPU_M_NDMA];
             const double *rd = p.dtab + tm[SLVGPU_M_O_RDMA], *mom = p.dtab + tm[SLVGPU_M_O_MOM];
@@ -115,9 +118,10 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, Fr
                 double e1 = 0.0, e2 = 0.0;
 #pragma unroll
                 for (int k = 0; k < 20; ++k) { e1 += row[3 + k] * P[k]; e2 += row[23 + k] * P[k]; }
-                e_mea += e1; e_ea += e2;
-                c_mea += row[43] * P[20] + row[44] * P[21] + row[45] * P[22];
-                c_ea += row[46] * P[20] + row[47] * P[21] + row[48] * P[22];
+                const double c1 = row[43] * P[20] + row[44] * P[21] + row[45] * P[22];
+                const double c2 = row[46] * P[20] + row[47] * P[21] + row[48] * P[22];
+                if (env) { v_mea += e1; v_ea += e2; w_mea += c1; w_ea += c2; }
+                else { e_mea += e1; e_ea += e2; c_mea += c1; c_ea += c2; }
               }
             }
           }
@@ -156,6 +160,7 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, Fr
   c_mea = block_sum(c_mea, s_red); c_ea = block_sum(c_ea, s_red);
   rms_sum = block_sum(rms_sum, s_red); rms_max = block_max(rms_max, s_red);
   const double dn_c = block_sum((double)n_c, s_red), dn_p = block_sum((double)n_p, s_red), dn_e = block_sum((double)n_e, s_red);
+  v_mea = block_sum(v_mea, s_red); v_ea = block_sum(v_ea, s_red); w_mea = block_sum(w_mea, s_red); w_ea = block_sum(w_ea, s_red);
   if (threadIdx.x == 0) {
     double *o = out + (size_t)(frame0 + fi) * SLVGPU_NOUT;
     const bool el = (p.flags & SLVGPU_ELECT) != 0;
@@ -170,6 +175,10 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, Fr
     o[SLVGPU_N_ELECT] = dn_c; o[SLVGPU_N_POL] = dn_p; o[SLVGPU_N_REP] = dn_e;
     o[SLVGPU_POL_ITERS] = 0.0; o[SLVGPU_POL_RESID] = 0.0;
     for (int k = SLVGPU_POL_ADD; k < SLVGPU_NOUT; ++k) o[k] = 0.0;
+    o[SLVGPU_ENV_ELE_MEA] = el ? v_mea : 0.0;
+    o[SLVGPU_ENV_ELE_EA] = (el && (p.flags & SLVGPU_EA)) ? v_ea : 0.0;
+    o[SLVGPU_ENV_COR_MEA] = (el && (p.flags & SLVGPU_CORR)) ? w_mea : 0.0;
+    o[SLVGPU_ENV_COR_EA] = (el && (p.flags & SLVGPU_CORR)) ? w_ea : 0.0;
     fl.nlist[fi] = s_base < p.list_cap ? s_base : p.list_cap;
   }
 }

@@ -100,7 +100,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     for (int pass = -1;;) {
     auto included = [&](int e) -> bool {
       if (!(fl.list_flag[lbase + e] & 1)) return false;
-      const bool rem = tmeta(p, p.inst_type[fl.list_inst[lbase + e]])[SLVGPU_M_REMOVABLE] > 0;
+      const bool rem = tmeta(p, p.inst_type[fl.list_inst[lbase + e]])[SLVGPU_M_REMOVABLE] == 1;
       return pass < 0 ? !rem : e == pass;
     };
     do {
@@ -577,7 +577,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     if (tid == 0) {
       int nx = -1;
       for (int e = pass + 1; e < nl; ++e)
-        if ((fl.list_flag[lbase + e] & 1) && tmeta(p, p.inst_type[fl.list_inst[lbase + e]])[SLVGPU_M_REMOVABLE] > 0) { nx = e; break; }
+        if ((fl.list_flag[lbase + e] & 1) && tmeta(p, p.inst_type[fl.list_inst[lbase + e]])[SLVGPU_M_REMOVABLE] == 1) { nx = e; break; }
       s_n[2] = nx;
     }
     __syncthreads();

@@ -180,6 +180,10 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
       const int32_t *tm = d->type_meta + (size_t)ty * SLVGPU_NMETA;
       if ((d->flags & (SLVGPU_ELECT | SLVGPU_POL)) && tm[SLVGPU_M_NDMA] > 0 && (tm[SLVGPU_M_O_RDMA] < 0 || tm[SLVGPU_M_O_MOM] < 0))
         return miss("elect/pol", "distributed multipoles", ty);
+      if (tm[SLVGPU_M_REMOVABLE] == 2) {                  // non-EFP environment: electrostatics only, nothing else is read
+        if (tm[SLVGPU_M_NPOL] > 0) return fail(SLVGPU_EINVAL, "environment fragment types must not carry polarisabilities");
+        continue;
+      }
       if ((d->flags & (SLVGPU_POL | SLVGPU_DISP)) && tm[SLVGPU_M_NPOL] > 0 && (tm[SLVGPU_M_O_RPOL] < 0 || tm[SLVGPU_M_O_POL] < 0))
         return miss("pol/disp", "dpol", ty);
       if ((d->flags & SLVGPU_DISP) && tm[SLVGPU_M_NPOL] > 0 && tm[SLVGPU_M_O_DPOLI] < 0) return miss("disp", "dpoli", ty);
@@ -228,7 +232,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   for (int i = 0; i < d->ninst; ++i) {
     const int32_t *tm = d->type_meta + (size_t)d->inst_type[i] * SLVGPU_NMETA;
     tot_npol += tm[SLVGPU_M_NPOL]; tot_ndma += tm[SLVGPU_M_NDMA];
-    if (i > 0) {                                               // exchange-repulsion partner dimensions
+    if (i > 0 && tm[SLVGPU_M_REMOVABLE] != 2) {                 // exchange-repulsion partner dimensions
       solvent_type[d->inst_type[i]] = 1;
       if (tm[SLVGPU_M_NMOS] > pl->max_nmos) pl->max_nmos = tm[SLVGPU_M_NMOS];
       if (tm[SLVGPU_M_NBASIS] > pl->max_nbas) pl->max_nbas = tm[SLVGPU_M_NBASIS];

@@ -26,6 +26,7 @@ class MDInput(object):
         self._ind = []; self._nmol = []; self._bsm = []; self._supl = []; self._reord = []
         self._frame_slice = []
         self._frag_idx = 0
+        self._type_of = {}
         self._input_text = None
         self(file_name)
 
@@ -61,8 +62,8 @@ class MDInput(object):
         lines = [ln for ln in lines if ln]
         if not lines or lines[0].startswith('!'):
             return
-        frag = Frag(lines[0].split()[1])
-        reord = None; supl = None; n_atoms_per_mol = None
+        frag_name = lines[0].split()[1]
+        reord = None; supl = None; n_atoms_per_mol = None; spans = []
         for line in lines[1:]:
             if line.startswith('!'):
                 continue
@@ -79,12 +80,21 @@ class MDInput(object):
                 assert n_atoms % n_frags == 0, \
                     'MDInputError: Invalid atomic indices or fragment numbers in fragment %i\n -----> %s' % (self._frag_idx + 1, line)
                 n_atoms_per_mol = n_atoms // n_frags
-                for i in range(n_frags):
-                    self._ind.append(self._frag_idx); self._nmol.append(n_atoms_per_mol)
+                spans.append((n_frags, n_atoms_per_mol))
                 self._frame_slice += list(numpy.array(atoms) - 1)
         if reord is None:
             reord = numpy.arange(n_atoms_per_mol, dtype=int)
-        self._bsm.append(frag); self._supl.append(supl); self._reord.append(reord)
+        # A protein input (biomol.py:249-328) repeats the same (fragment, reorder, supl) block for every residue of a kind:
+        # such blocks share ONE fragment type (the reference appends a freshly parsed Frag per block; `ind` then simply
+        # points at the shared entry, which changes nothing for EFP.set)
+        key = (frag_name, tuple(int(x) for x in reord), None if supl is None else tuple(int(x) for x in supl))
+        t = self._type_of.get(key)
+        if t is None:
+            t = len(self._bsm); self._type_of[key] = t
+            self._bsm.append(Frag(frag_name)); self._supl.append(supl); self._reord.append(reord)
+        for n_frags, per in spans:
+            for i in range(n_frags):
+                self._ind.append(t); self._nmol.append(per)
         self._frag_idx += 1
 
     def __repr__(self):

@@ -102,7 +102,8 @@ class Plan(object):
             m[M['NATOMS']] = nat; m[M['NDMA']] = par.get('ndma', 0) or 0; m[M['NPOL']] = par.get('npol', 0) or 0
             m[M['NMOS']] = par.get('nmos', 0) or 0; m[M['NBASIS']] = par.get('nbasis', 0) or 0
             m[M['NSUPL']] = len(sl)
-            m[M['REMOVABLE']] = 1 if (removable is not None and t in removable) else 0
+            # 2: part of the non-EFP electrostatic environment (EFP.eval_dma): point multipoles riding on frame atoms
+            m[M['REMOVABLE']] = 2 if par.get('env') else (1 if (removable is not None and t in removable) else 0)
             m[M['IO_SUPL']] = it.add(sl); m[M['IO_REORD']] = it.add(ro)
             m[M['O_POS']] = dt.add(par['pos'])
             if 'rdma' in par:
@@ -131,6 +132,8 @@ class Plan(object):
         fl = self.flags
         for i in sorted(set(int(t) for t in ind[1:])):
             par, nm = pars[i], pars[i].get('name')
+            if par.get('env'):
+                continue
             if fl & _lib.FLAG['disp'] and meta[i][M['NPOL']] > 0 and 'dpoli' not in par:
                 raise KeyError("'dpoli': dispersion needs the polarisabilities at imaginary frequencies of fragment %r" % nm)
             if fl & _lib.FLAG['rep'] and not ('vecl' in par and 'fock' in par and 'lmoc' in par):

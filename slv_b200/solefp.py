@@ -55,9 +55,10 @@ REPORT_KEYS = ['solcamm', 'ele_mea', 'ele_ea', 'cor_mea', 'cor_ea', 'pol_mea', '
                'dis_mea', 'dis_ea', 'dis_mea_iso', 'total']
 
 
-def shifts_from_rows(rows, cunit):
-    """Assemble the reference's shift terms (solefp.py:1565-1614) from device output rows [n,16].
-    Returns a dict of arrays of length n."""
+def shifts_from_rows(rows, cunit, with_env=False):
+    """Assemble the reference's shift terms (solefp.py:1565-1614) from device output rows [n, NOUT].
+    Returns a dict of arrays of length n; with_env adds the non-EFP environment terms of eval_dma
+    (solefp.py:887-903) from the rows' environment columns."""
     O = _lib.OUT
     c = UNITS.HartreePerHbarToCmRec if cunit else 1.0
     r = numpy.asarray(rows, numpy.float64)
@@ -80,7 +81,21 @@ def shifts_from_rows(rows, cunit):
     s['solcamm'] = s['ele_mea'] + s['ele_ea']
     s['total_cor'] = s['cor_mea'] + s['cor_ea']
     s['pol_add_mea'] = r[:, O['pol_add']] * c; s['pol_add_ea'] = z.copy(); s['pol_add_tot'] = s['pol_add_mea'].copy()
+    if with_env:
+        s['ele_env_mea'] = r[:, O['env_ele_mea']] * c; s['ele_env_ea'] = r[:, O['env_ele_ea']] * c
+        s['cor_env_mea'] = r[:, O['env_cor_mea']] * c; s['cor_env_ea'] = r[:, O['env_cor_ea']] * c
+        s['tot_env'] = s['ele_env_mea'] + s['ele_env_ea'] + s['cor_env_mea'] + s['cor_env_ea']
+        s['total+env'] = s['total'] + s['tot_env']
     return s
+
+
+def point_charge_fragment(q, name='environment'):
+    """One point charge riding on one frame atom, as a fragment type of the non-EFP electrostatic environment
+    (EFP.eval_dma with an [n,4] charge array, solefp.py:151-178): append it to `bsm`, its type index to `ind`, 1 to `nmol`,
+    and the atom to the frame slice; the batched path then returns ele_env_* / cor_env_* for every frame."""
+    z1, z3 = numpy.zeros((1, 1)), numpy.zeros((1, 3))
+    return _ParHolder(dict(name=name, env=True, natoms=1, pos=z3.copy(), atno=numpy.zeros(1, int), ndma=1, rdma=z3.copy(),
+                           dmac=numpy.array([float(q)]), dmad=z3.copy(), dmaq=numpy.zeros((1, 6)), dmao=numpy.zeros((1, 10))))
 
 
 _REP_WARNED = [False]
@@ -239,12 +254,14 @@ class EFP(UNITS):
         return
 
     def eval_frames(self, coords, ind=None, nmol=None, bsm=None, supl=None, reord=None, out=None, status=None,
-                    scale=None, idx=None):
+                    scale=None, idx=None, remove_clashes=None, rcl_algorithm='remove_by_name', include_ions=False,
+                    include_polar=False):
         """Batched evaluation: coords [nframes, natoms, 3] (Bohr).  A CUDA torch tensor is evaluated in
         place on the device and CUDA tensors are returned; a host array (numpy / pinned torch) goes
         through the host entry point.  A float32 host array is taken as raw trajectory records [nframes, natoms_src, 3]
         in the file's units: `scale` converts to Bohr and `idx` (MDInput's atom slice) picks the atoms, both on the
-        device.  Returns (rows [nframes,20] in a.u., status [nframes])."""
+        device.  remove_clashes / rcl_algorithm / include_ions / include_polar act as in eval().
+        Returns (rows [nframes, NOUT] in a.u., status [nframes])."""
         if ind is not None:
             self._ind = numpy.array(ind, int); self._nmol = numpy.array(nmol, int)
             if bsm is not None:
@@ -253,20 +270,25 @@ class EFP(UNITS):
                 self._supl = supl
             if reord is not None:
                 self._reord = reord
+        if remove_clashes is not None:       # as in eval(): fragments of the listed names leave the many-body induction
+            self._removable = self._removable_types(rcl_algorithm, include_ions, include_polar) if remove_clashes else None
         plan = self._get_plan()
         if hasattr(coords, 'is_cuda') and coords.is_cuda:
             return plan.eval_device(coords, out, status)
         return plan.eval_host(coords, out, status, scale=scale, idx=idx)
 
+    def _has_env(self):
+        return self._bsm is not None and any(b.get().get('env') for b in self._bsm)
+
     def shifts_of(self, rows):
         """Dictionary of per-frame arrays with the reference's shift keys."""
         if hasattr(rows, 'cpu'):
             rows = rows.cpu().numpy()
-        return shifts_from_rows(rows, self._cunit)
+        return shifts_from_rows(rows, self._cunit, with_env=self._has_env())
 
     def _store(self, rows, status):
         self._rows = rows; self._status = status
-        s = shifts_from_rows(rows[:1], self._cunit)
+        s = shifts_from_rows(rows[:1], self._cunit, with_env=self._has_env())
         for k, v in s.items():
             self._shift[k] = float(v[0])
         self._shift['total+env'] = self._shift['total'] + self._shift['tot_env']

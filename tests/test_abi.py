@@ -28,7 +28,7 @@ def test_header_symbols_exported():
 def test_struct_layout_matches_header():
     from slv_b200 import _lib
     assert ctypes.sizeof(_lib.PlanDesc) == 4 * 4 + 3 * 8 + 2 * 8 + 2 * 8 + 2 * 8 + 2 * 8 + 2 * 4 + 8 + 2 * 4
-    assert _lib.NOUT == 20 and _lib.NMETA == 32 and _lib.NSOL == 16
+    assert _lib.NOUT == 24 and _lib.NMETA == 32 and _lib.NSOL == 16
 
 
 def test_no_gpu_means_error_not_fallback(frags):

@@ -86,7 +86,7 @@ def test_solcamm_property_matches_plan_tables(frags):
 def test_shift_dictionary_assembly():
     from slv_b200.solefp import shifts_from_rows
     from slv_b200.units import HartreePerHbarToCmRec as c
-    row = np.zeros((1, 20)); row[0, :8] = [1e-5, 2e-5, -3e-6, 4e-6, 5e-6, 6e-5, 7e-5, 8e-5]
+    row = np.zeros((1, 24)); row[0, :8] = [1e-5, 2e-5, -3e-6, 4e-6, 5e-6, 6e-5, 7e-5, 8e-5]
     s = shifts_from_rows(row, True)
     assert abs(s['ele_tot'][0] - (1e-5 + 2e-5 - 3e-6 + 4e-6) * c) < 1e-9
     assert abs(s['total'][0] - (s['ele_tot'][0] + s['pol_mea'][0] + s['rep_mea'][0] + s['dis_mea'][0])) < 1e-9
