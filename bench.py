@@ -43,10 +43,10 @@ WORKLOADS = {
     3: dict(name='MeSCN in 50/50 water/DMSO (%(n)d fragments), full SolEFP elect+pol+rep+disp', solute='mescn',
             solvents=['water', 'dmso'], nsolv=400, mode=4, flags=dict(elect=True, corr=True, pol=True, rep=True, disp=True),
             frames=10000, spacing=9.5, seed=3, jit_lattice=0.3),
-    4: dict(name='protein-like: MeSCN probe among %(n)d mixed EFP fragments incl. charged ones, full SolEFP, remove_clashes',
-            solute='mescn', solvents=['water', 'mecoo-', 'menh3+', 'meoh', 'methane', 'phenol', 'benzene', 'chonh2', 'nma'],
-            nsolv=2000, mode=4, flags=dict(elect=True, corr=True, pol=True, rep=True, disp=True), frames=1000, spacing=8.5,
-            seed=4, jit_lattice=0.3, cuts=(45.0, 16.0, 13.0), remove_clashes=True, unique=50, rmin=3.5),
+    4: dict(name='protein-like through the biomol front-end: SCN probe residue in a 160-residue chain + waters (%(n)d EFP fragments '
+                 'incl. charged side chains, 8 near-zone CONH point charges), full SolEFP, remove_clashes',
+            biomol=True, nres=160, nsolv=2000, mode=4, flags=dict(elect=True, corr=True, pol=True, rep=True, disp=True), frames=1000,
+            seed=4, cuts=(45.0, 16.0, 13.0), remove_clashes=True, unique=50),
     5: dict(name='NMA + %(n)d waters, full SolEFP elect+pol+rep+disp', solute='nma', solvents=['water'], nsolv=4000, mode=8,
             flags=dict(elect=True, corr=True, pol=True, rep=True, disp=True), frames=2000, spacing=5.87, seed=5),
 }
@@ -81,6 +81,83 @@ def workload_string(cfg, nw, nframes):
     wl = WORKLOADS[cfg]; cuts = wl.get('cuts', CUTS)
     return (wl['name'] % dict(n=nw)) + ', mode %d, ccut/pcut/ecut %g/%g/%g Bohr, %d frames per GPU per step' % (
         wl['mode'], cuts[0], cuts[1], cuts[2], nframes)
+
+
+BIOMOL_SEQ = ['ASP', 'SER', 'GLY', 'LYS', 'ASN', 'ALA', 'GLU', 'TYR', 'PHE', 'THR', 'LEU', 'VAL', 'ILE', 'GLN', 'ARG', 'MET', 'HIE', 'CYS']
+
+
+def make_biomol(wl, nfrag, nunique, nframes, rank):
+    """Config 4: a synthetic protein-like system pushed through the real front-end (slv_b200/biomol.py: .tc tables, amide
+    zones, $Frag input, near-zone charges).  Returns the workload dictionary of make_workload."""
+    import numpy as np
+    from slv_b200 import biomol, synth_biomol
+    from slv_b200.units import AngstromToBohr
+    tcdir = os.path.join(ROOT, 'slv_b200', 'data', 'tc')
+    tc = biomol.parse_tc(os.path.join(tcdir, 'gmx.tc')); ptc = biomol.parse_tc(os.path.join(tcdir, 'probe.tc'))
+    rng = np.random.default_rng(wl['seed'])
+    seq = [BIOMOL_SEQ[k] for k in rng.integers(0, len(BIOMOL_SEQ), wl['nres'])]
+    nprot = wl['nres'] + sum(len(tc[r]) for r in seq)                 # links + side-chain fragments (about)
+    top, xyz = synth_biomol.make_system(tc, ptc, seq, rng, nwater=max(0, nfrag - nprot))
+    cuts = wl['cuts']
+    bf = biomol.BiomoleculeFragmentation(tc, ptc, wl['mode'], ccut=cuts[0], pcut=cuts[1], ecut=cuts[2], report=os.devnull,
+                                         include_ions=False, include_polar=False)
+    (ind, nmol, bsm, supl, reord), idx = bf.build(top, xyz)
+    nu = min(nunique, nframes)
+    rec = synth_biomol.jiggle(xyz, top, nu, np.random.default_rng(wl['seed'] + 1000 * rank), amp=0.02).astype(np.float32)
+    rec = np.ascontiguousarray(np.concatenate([rec] * ((nframes + nu - 1) // nu))[:nframes])
+    return dict(bsm=bsm, ind=ind, nmol=nmol, supl=supl, reord=reord, rec32=rec, idx=np.asarray(idx, np.int32), scale=AngstromToBohr,
+                nfrag=len(ind) - 1, efp=bf._efp)
+
+
+def make_workload(cfg, nw, nunique, nframes, rank):
+    """Synthetic trajectory of a workload as float32 RECORDS in Angstrom (what DCD / XTC files hold) plus the frame slice:
+    dict(bsm, ind, nmol, supl, reord, rec32 [nframes, natoms_src, 3], idx or None, scale)."""
+    import numpy as np
+    from slv_b200.units import AngstromToBohr
+    wl = WORKLOADS[cfg]
+    if wl.get('biomol'):
+        return make_biomol(wl, nw, nunique, nframes, rank)
+    bsm, ind, nmol, X = make_frames(wl, nw, nunique, nframes, rank)
+    nt = len(bsm)
+    rec = np.ascontiguousarray((X / AngstromToBohr).astype(np.float32))
+    return dict(bsm=bsm, ind=ind, nmol=nmol, supl=[None] * nt, reord=[None] * nt, rec32=rec, idx=None, scale=AngstromToBohr,
+                nfrag=len(ind) - 1, efp=None)
+
+
+def bohr_frames(w):
+    """The float64 Bohr coordinates the device-resident leg sees: exactly what the float32 entry computes on the device."""
+    import numpy as np
+    r = w['rec32'] if w['idx'] is None else w['rec32'][:, w['idx'], :]
+    return np.ascontiguousarray(r.astype(np.float64) * w['scale'])
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and therefore the pinned staging buffers it allocates next) to the CPUs of the NUMA node the GPU
+    hangs off: eight ranks pushing coordinates through one socket's memory controllers was the 8-GPU e2e limit."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), 'pci_bus_id') else None
+        if bus is None:
+            out = subprocess.run(['nvidia-smi', '-i', str(local_rank), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            bus = out
+        bus = bus.lower()
+        if bus.startswith('00000000:'):
+            bus = bus[4:]
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus |= set(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
 
 
 def make_frames(wl, nw, nunique, nframes, rank):
@@ -141,22 +218,35 @@ def _cpu_worker_init(cfg, nw):
         _W['limit'] = threadpool_limits(1)
     except Exception:
         pass
+    import warnings
+    warnings.simplefilter('ignore')
     wl = WORKLOADS[cfg]
-    bsm, ind, nmol, X = make_frames(wl, nw, 1, 1, 0)
-    _W.update(wl=wl, pars=[b.get() for b in bsm], ind=ind, nmol=nmol, nt=len(bsm))
+    w = make_workload(cfg, nw, 1, 1, 0)
+    pars = [b.get() for b in w['bsm']]
+    nenv = sum(1 for t in w['ind'] if pars[t].get('env'))
+    _W.update(wl=wl, pars=pars, ind=w['ind'], nmol=w['nmol'], supl=w['supl'], reord=w['reord'], nenv=nenv)
     if wl.get('remove_clashes'):
         from slv_b200.solefp import EFP
         names = set(EFP._RCL_BASE + ['Acetamide'] + EFP._RCL_POLAR + EFP._RCL_IONS + ['Methyl Sulphate (VI) -1 anion'])
-        _W['removable'] = set(t for t, p in enumerate(_W['pars']) if t != 0 and p.get('name') in names)
+        _W['removable'] = set(t for t, p in enumerate(pars) if t != 0 and p.get('name') in names)
 
 
 def _cpu_worker_frame(xyz):
+    """One frame (gathered float64 Bohr coordinates) through the oracle: EFP.set + eval (+ eval_dma for the environment)."""
+    import numpy as np
     from oracle import solefp_oracle as O
-    wl = _W['wl']; fl = wl['flags']; nt = _W['nt']
+    wl = _W['wl']; fl = wl['flags']; ne = _W['nenv']
+    ind, nmol = _W['ind'], _W['nmol']
     t0 = time.time()
-    O.eval_frame(xyz, _W['ind'], _W['nmol'], _W['pars'], [None] * nt, [None] * nt, wl['mode'], *wl.get('cuts', CUTS),
-                 elect=True, ea=True, corr=True, pol=fl.get('pol', False), disp=fl.get('disp', False),
+    n_efp = sum(nmol[:len(nmol) - ne])
+    O.eval_frame(xyz[:n_efp], ind[:len(ind) - ne], nmol[:len(nmol) - ne], _W['pars'], _W['supl'], _W['reord'], wl['mode'],
+                 *wl.get('cuts', CUTS), elect=True, ea=True, corr=True, pol=fl.get('pol', False), disp=fl.get('disp', False),
                  rep=fl.get('rep', False), literal_gemm=True, removable=_W.get('removable'))
+    if ne:
+        q = np.array([_W['pars'][t]['dmac'][0] for t in ind[len(ind) - ne:]])
+        ro = _W['reord'][ind[0]]
+        pos_c = O.reorder_xyz(xyz[:nmol[0]], ro if ro is not None else np.arange(nmol[0]))
+        O.eval_dma_frame(pos_c, _W['pars'][ind[0]], _W['supl'][ind[0]], wl['mode'], np.concatenate([xyz[n_efp:], q[:, None]], axis=1))
     return time.time() - t0
 
 
@@ -219,7 +309,8 @@ def run_reference(a):
     farm = CpuFarm(cfg, nw)
     per_step = a.cpu_frames or farm.nproc
     nu = min(4 * per_step, 64)
-    bsm, ind, nmol, X = make_frames(wl, nw, nu, nu, 0)
+    w = make_workload(cfg, nw, nu, nu, 0)
+    X = bohr_frames(w); nfrag = w['nfrag']
     k = 0
     for _ in range(a.warmup):
         farm.run([X[(k + f) % nu] for f in range(per_step)]); k += per_step
@@ -238,7 +329,7 @@ def run_reference(a):
     line = dict(metric='md_frames_per_sec', value=fps, unit='frames/s', n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                 ms_per_step=dt / a.steps * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
                 data='synthetic', impl='reference',
-                config=dict(workload=workload_string(cfg, nw, nframes), baseline_config=cfg),
+                config=dict(workload=workload_string(cfg, nfrag, nframes), baseline_config=cfg),
                 cpu_baseline=dict(value=fps, unit='frames/s', cores=farm.nproc, kind='port', sample=sample),
                 e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -281,15 +372,20 @@ def run_config(cfg, a, steps, warmup, world, rank, dev, with_cpu, sampler=None):
     main = cfg == a.config
     nw = (a.waters if main else 0) or wl['nsolv']; nframes = (a.frames if main else 0) or wl['frames']
     nunique = (a.unique if main else 0) or wl.get('unique', 250)
-    bsm, ind, nmol, X = make_frames(wl, nw, nunique, nframes, rank)
-    nt = len(bsm)
-    efp = EFP(freq=True, mode=wl['mode'], ccut=cuts[0], pcut=cuts[1], ecut=cuts[2], cunit=True, **wl['flags'])
+    w = make_workload(cfg, nw, nunique, nframes, rank)
+    bsm, ind, nmol = w['bsm'], w['ind'], w['nmol']
+    X = bohr_frames(w)                                  # float64 Bohr, gathered: the device-resident leg
+    nw = w['nfrag']
+    efp = w['efp'] or EFP(freq=True, mode=wl['mode'], ccut=cuts[0], pcut=cuts[1], ecut=cuts[2], cunit=True, **wl['flags'])
     efp.max_chunk = min(nframes, 10240)
-    efp.set(X[0], ind, nmol, bsm, [None] * nt, [None] * nt)
+    efp.set(X[0], ind, nmol, bsm, w['supl'], w['reord'])
     if wl.get('remove_clashes'):
         efp._removable = efp._removable_types('remove_by_name', False, False)
     d_coords = torch.from_numpy(X).to(dev)
-    h_coords = torch.from_numpy(X).pin_memory()
+    # the e2e leg starts from float32 trajectory records in pinned host memory (what DCD / XTC files hold); the frame
+    # slice and the conversion to Bohr happen on the device inside the public call
+    h_coords = torch.from_numpy(w['rec32']).pin_memory()
+    e2e_kw = dict(scale=w['scale'], idx=w['idx'])
     nf = d_coords.shape[0]
     rows = torch.empty((nf, _lib.NOUT), dtype=torch.float64, device=dev)
     status = torch.empty((nf,), dtype=torch.int32, device=dev)
@@ -326,11 +422,11 @@ def run_config(cfg, a, steps, warmup, world, rank, dev, with_cpu, sampler=None):
     h_rows = torch.empty((nf, _lib.NOUT), dtype=torch.float64).pin_memory()
     h_status = torch.empty((nf,), dtype=torch.int32).pin_memory()
     for _ in range(2):
-        efp.eval_frames(h_coords, out=h_rows, status=h_status)
+        efp.eval_frames(h_coords, out=h_rows, status=h_status, **e2e_kw)
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        efp.eval_frames(h_coords, out=h_rows, status=h_status)     # the public call: pinned host in, host rows out
+        efp.eval_frames(h_coords, out=h_rows, status=h_status, **e2e_kw)     # the public call: pinned host records in, host rows out
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -358,7 +454,8 @@ def run_config(cfg, a, steps, warmup, world, rank, dev, with_cpu, sampler=None):
     step_ms = ms / steps
     rec = dict(
         value=fps, unit='frames/s', ms_per_step=step_ms,
-        e2e=dict(value=total_frames * steps / e2e_s, unit='frames/s', h2d_bytes_per_step=int(X.nbytes),
+        e2e=dict(value=total_frames * steps / e2e_s, unit='frames/s', h2d_bytes_per_step=int(w['rec32'].nbytes),
+                 input='float32 trajectory records in Angstrom (pinned host memory); frame slice and conversion to Bohr on the device',
                  d2h_bytes_per_step=int(nf * (_lib.NOUT * 8 + 4)), rows_identical_to_device_path=same),
         config=dict(workload=workload_string(cfg, nw, nf), baseline_config=cfg),
         detail=dict(frames_per_gpu=nf, l2='inputs larger than L2 (%.0f MB of coordinates per step)' % (X.nbytes / 1e6),
@@ -381,7 +478,7 @@ def run_config(cfg, a, steps, warmup, world, rank, dev, with_cpu, sampler=None):
                                             alg_tflops=SWEEP_BODY_TFLOPS, frac_of_ceiling=ach / SWEEP_BODY_TFLOPS),
                                flops_per_step=pol_flops, ms_per_step=kms['k_pol'], share_of_step=kms['k_pol'] / step_ms)
     ndma_c = int(bsm[0].get()['ndma'])
-    ndma_s = float(np.mean([bsm[i].get()['ndma'] for i in ind[1:]]))
+    ndma_s = float(np.mean([bsm[i].get()['ndma'] for i in ind[1:] if not bsm[i].get().get('env')]))
     elect_pairs = float((ndma_c * ndma_s * nel).sum())
     ea = elect_pairs * FLOPS_PER_ELECT_PAIR / (kms['k_frame_elect'] * 1e-3) / 1e12
     rec['roofline_elect'] = dict(bound='fp64', kernel='k_frame_elect', achieved=ea, peak=peak, unit='TFLOP/s', frac=ea / peak,
@@ -393,11 +490,11 @@ def run_config(cfg, a, steps, warmup, world, rank, dev, with_cpu, sampler=None):
     rec['pol_tensor_pairs_per_sec'] = float((its * tpairs).sum()) * world * steps / (ms * 1e-3)
     if kms['k_rep'] > 0:
         # half transform X = V C_B^T (4 integral kinds) and LMO integrals C_A X (6 products) per (solute, fragment) pair
-        pa = bsm[0].get(); nbA, nmA = int(pa['nbasis']), int(pa['nmos'])
-        per_type = [8.0 * nbA * b.get()['nbasis'] * b.get()['nmos'] + 12.0 * nmA * b.get()['nmos'] * nbA for b in bsm[1:]]
+        pa = bsm[ind[0]].get(); nbA, nmA = int(pa['nbasis']), int(pa['nmos'])
         import collections
-        cnt = collections.Counter(ind[1:])
-        mean_flop = sum(per_type[t - 1] * c for t, c in cnt.items()) / float(len(ind) - 1)
+        cnt = collections.Counter(t for t in ind[1:] if not bsm[t].get().get('env'))
+        flop = lambda b: 8.0 * nbA * b['nbasis'] * b['nmos'] + 12.0 * nmA * b['nmos'] * nbA
+        mean_flop = sum(flop(bsm[t].get()) * c for t, c in cnt.items()) / float(sum(cnt.values()))
         rep_pairs = float(nrep.sum())
         ra = rep_pairs * mean_flop / (kms['k_rep'] * 1e-3) / 1e12
         rec['roofline_rep'] = dict(bound='fp64', kernel='k_rep_* (integrals + transform + CALCFI)', achieved=ra, peak=peak, unit='TFLOP/s',
@@ -420,6 +517,7 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     sampler = ClockSampler(local); sampler.start()
@@ -438,11 +536,14 @@ def main():
                     vs_baseline=None, dtype='f64', data='synthetic')
         line.update(rec)
         line['clocks'] = sampler.summary()
+        line['host'] = dict(numa_node_of_gpu=numa, cpus=os.cpu_count())
         if sub:
             line['configs'] = sub
         if not a.no_cpu and world == 1:          # rank 0 at N=1 only
             nw = a.waters or wl['nsolv']
-            _, _, _, X = make_frames(wl, nw, 64, 64, 0)
+            if numa is not None:
+                os.sched_setaffinity(0, range(os.cpu_count()))     # the CPU farm uses every core again
+            X = bohr_frames(make_workload(a.config, nw, 64, 64, 0))
             line['cpu_baseline'] = cpu_sample_record(a.config, nw, X, a.cpu_frames)
         print(json.dumps(line))
     if world > 1:

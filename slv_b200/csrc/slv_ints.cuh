@@ -110,19 +110,28 @@ SLV_HD void subshell_pair_t(const double A[3], int npa, const double *ea, const 
       if (a * b * AB2 <= 46.0 * (a + b)) live |= 1ull << (p * 8 + q);
     }
   }
-  while (live) {
-    {
+  // the exponents and coefficients of the NEXT surviving pair are fetched before the arithmetic of the current one
+  // (the loads are L1 / L2 hits, but their latency sat on the critical path of every iteration)
+  auto pop = [&live]() {
 #ifdef __CUDA_ARCH__
-      const int bit = __ffsll((long long)live) - 1;
+    const int bit = __ffsll((long long)live) - 1;
 #else
-      const int bit = __builtin_ctzll(live);
+    const int bit = __builtin_ctzll(live);
 #endif
-      live &= live - 1ull;
-      const int p = bit >> 3, q = bit & 7;
-      const double a = ea[p], b = eb[q];
+    live &= live - 1ull;
+    return bit;
+  };
+  double a_n = 0.0, b_n = 0.0, cc_n = 0.0;
+  bool more = live != 0ull;
+  if (more) { const int bit = pop(); a_n = ea[bit >> 3]; b_n = eb[bit & 7]; cc_n = ca[bit >> 3] * cb[bit & 7]; }
+  while (more) {
+    {
+      const double a = a_n, b = b_n, cc = cc_n;
+      more = live != 0ull;
+      if (more) { const int bit = pop(); a_n = ea[bit >> 3]; b_n = eb[bit & 7]; cc_n = ca[bit >> 3] * cb[bit & 7]; }
       const double pp = a + b, ip = 1.0 / pp, h = 0.5 * ip;
       const double mu = a * b * ip;
-      const double pref = ca[p] * cb[q] * exp(-mu * AB2) * (3.14159265358979323846 * ip) * sqrt(3.14159265358979323846 * ip);
+      const double pref = cc * exp(-mu * AB2) * (3.14159265358979323846 * ip) * sqrt(3.14159265358979323846 * ip);
       const double fa = -b * ip, fb = a * ip;
       AxisVals<MX, LB, ALL> X; AxisVals<MY, LB, ALL> Y; AxisVals<MZ, LB, ALL> Z;
       X.build(fa * ABx, fb * ABx, h, a, b); X.scale(pref);       // every term below carries exactly one x factor

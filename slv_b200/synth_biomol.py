@@ -1,4 +1,5 @@
-"""Synthetic protein-like system for the biomolecular front-end (TEST / BENCH INFRASTRUCTURE).
+"""Synthetic protein-like system for the biomolecular front-end (used by bench.py --config 4 and the tests; like
+slv_b200/synth.py there is no network for real trajectories).
 
 A chain of residues whose EFP fragments (side chains from a .tc table, peptide links as N-methylacetamide bodies, the
 probe residue) are rigid parameter geometries in random orientations on a jittered lattice; the residue atom lists are
@@ -6,10 +7,10 @@ composed by inverting the .tc `reorder` maps, so every fragment superimposes ont
 are named N, H, CA, HA ... C, O in GROMACS order, which is what the amide detection of biomol.py:331-438 keys on."""
 import numpy as np
 
-from slv_b200 import synth
-from slv_b200.biomol import Topology
-from slv_b200.slvpar import Frag
-from slv_b200.units import AngstromToBohr
+from . import synth
+from .biomol import Topology
+from .slvpar import Frag
+from .units import AngstromToBohr
 
 B2A = 1.0 / AngstromToBohr
 _NMA_LINK = dict(C=2, O=4, N=1, H=7)          # 0-based parameter atoms of nma.frg taken by C, O (residue i) and N, H (residue i+1)

@@ -10,7 +10,7 @@ TC = os.path.join(ROOT, 'slv_b200', 'data', 'tc')
 
 
 def _system(seed=4, nwater=20, seq=('ASP', 'SER', 'GLY', 'LYS', 'ASN', 'ALA', 'GLU', 'TYR', 'PHE', 'THR')):
-    from biomol_synth import make_system
+    from slv_b200.synth_biomol import make_system
     from slv_b200 import biomol
     tc = biomol.parse_tc(os.path.join(TC, 'gmx.tc')); ptc = biomol.parse_tc(os.path.join(TC, 'probe.tc'))
     top, xyz = make_system(tc, ptc, list(seq), np.random.default_rng(seed), nwater=nwater)
@@ -52,7 +52,7 @@ def test_tc_parser_and_frag_input(tmp_path):
 def test_biomol_run_matches_oracle(tmp_path):
     """BASELINE config 4, small: the whole front-end -> one batched call (SolEFP with clash removal + near-zone CONH
     charges as environment fragments) against the oracle's eval_frame + eval_dma_frame on the same frames."""
-    from biomol_synth import jiggle
+    from slv_b200.synth_biomol import jiggle
     from slv_b200 import biomol
     from slv_b200.units import AngstromToBohr
     from oracle import solefp_oracle as O
