@@ -527,6 +527,8 @@ k_rep_pair(const DevPlan p, int type, FrameLists fl, RepPool rp, RepSmem L) {
     for (int w = tid; w < nij; w += NT) {
       const int i = w / nmosB, j = w - i * nmosB;
       const double S = Sij[w], T = Tij[w], Sm = Smij[w], Tm = Tmij[w];
+      if (S == 0.0) continue;       // every primitive pair screened out (fragments far apart although their centres are inside
+                                    // ecut): the term vanishes like S ln S; log(0) must not turn it into a NaN
       const double sl = log(fabs(S)), S2 = S * S;
       const double sdr = S * RI[w];
       const double aux = 2.0 * sqrt(-2.0 * sl / PI);

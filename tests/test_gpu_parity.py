@@ -533,3 +533,39 @@ def test_mdrun_reads_xtc_like_the_same_coordinates_as_an_array(frags, golden, tm
     assert np.abs(r1[:, :8] - r2[:, :8]).max() < 1e-11, np.abs(r1[:, :8] - r2[:, :8]).max()
     assert o1.read_text().split('\n')[1:] == o2.read_text().split('\n')[1:]
     assert abs(float(o1.read_text().split('\n')[1].split()[1]) - round(golden['f']['solcamm'], 2)) < 0.05
+
+
+def test_exchange_repulsion_of_a_far_fragment_is_zero_not_nan(frags):
+    """A fragment inside ecut whose atoms are so far away that every primitive pair is screened out (protein residues
+    with a distant side-chain fragment, or simply a huge ecut): S_ij is exactly 0 and the S ln S terms must vanish
+    instead of turning rep_mea into NaN; the oracle (no screening) gives a number below 1e-30."""
+    from oracle import solefp_oracle as O
+    sol, wat = frags('nma'), frags('water')
+    X = np.concatenate([sol.get_pos() - sol.get_pos().mean(0), wat.get_pos() - wat.get_pos().mean(0) + np.array([48.0, 3.0, -2.0]),
+                        wat.get_pos() - wat.get_pos().mean(0) + np.array([0.5, 6.5, 1.0])])[None]
+    efp = _efp(rep=True, ccut=1e10, pcut=20.0, ecut=80.0)
+    rows, status = efp.eval_frames(X, [0, 1, 1], [12, 3, 3], [sol, wat], [None, None], [None, None])
+    assert int(status[0]) == 0 and rows[0, 13] == 2 and np.isfinite(rows[0, 5])
+    ref = O.eval_frame(X[0], [0, 1, 1], [12, 3, 3], [sol.get(), wat.get()], [None, None], [None, None], 8, 1e10, 20.0, 80.0, elect=True, rep=True)
+    far = O.eval_frame(X[0][:15], [0, 1], [12, 3], [sol.get(), wat.get()], [None, None], [None, None], 8, 1e10, 20.0, 80.0, elect=True, rep=True)
+    assert abs(far['rep_mea']) < 1e-30
+    c = O.HartreePerHbarToCmRec
+    assert abs(rows[0, 5] * c - ref['rep_mea'] * c) < 1e-6 * max(1.0, abs(ref['rep_mea'] * c) * 1e-3)
+
+
+@pytest.mark.parametrize('partner', ['4-me-phenol', 'ccl4', 'me-guanidinium+', 'li+', 'so3--', 'cyclohexane'])
+def test_exchange_repulsion_partner_types(frags, partner):
+    """k_rep_pair instantiations beyond water / DMSO: fragment types with 1 to 37 LMOs (one to five LMO tiles of the tensor-core
+    transform), up to 240 basis functions, one-atom ions -- against the oracle (all 43 bundled types were checked once with
+    tools/scratch/dbg_rep_types.py; this is the subset that exercises every tile shape)."""
+    from slv_b200 import synth
+    from oracle import solefp_oracle as O
+    sol, fr = frags('mescn'), frags(partner)
+    X = synth.make_trajectory(sol.get_pos(), [fr.get_pos()], np.zeros(4, int), 1, seed=5, spacing=11.0, rmin=3.5)
+    ind = [0] + [1] * 4; nmol = [7] + [fr.get_natoms()] * 4
+    efp = _efp(mode=4, rep=True, ccut=1e10, pcut=1e10, ecut=16.0, pol=False, disp=False)
+    rows, status = efp.eval_frames(X, ind, nmol, [sol, fr], [None, None], [None, None])
+    ref = O.eval_frame(X[0], ind, nmol, [sol.get(), fr.get()], [None, None], [None, None], 4, 1e10, 1e10, 16.0, elect=True, rep=True)
+    c = O.HartreePerHbarToCmRec
+    assert int(status[0]) == 0 and rows[0, 13] == ref['n_rep'] >= 1
+    assert abs(rows[0, 5] * c - ref['rep_mea'] * c) < 1e-6 * max(1.0, abs(ref['rep_mea'] * c) * 1e-3), (rows[0, 5] * c, ref['rep_mea'] * c)
