@@ -31,6 +31,9 @@ extern "C" {
 #define SLVGPU_POL     8   /* pol    */
 #define SLVGPU_DISP   16   /* disp   */
 #define SLVGPU_REP    32   /* rep    */
+#define SLVGPU_GLOBAL 64   /* freq=False: EFP2 interaction ENERGIES of the whole cluster, every fragment pair, no cut-offs
+                            * (EFP._eval_mode_global, solvshift/solefp.py:905-1009): the electrostatic energy comes back in
+                            * the ELE_MEA column, the polarisation energy (SOLPOL) in POL_MEA, both in Hartree             */
 
 /* columns of the per-frame output row (a.u.) */
 enum {

@@ -150,3 +150,17 @@ def exrep(ria, rib, rna, rnb, faij, fbij, cika, cikb, skm, tkm, za, zb):
                  _i(cika.shape[1]), _i(cikb.shape[1]), _i(ria.shape[0]), _i(rib.shape[0]), _i(rna.shape[0]), _i(rnb.shape[0]),
                  ctypes.byref(e))
     return e.value
+
+
+def solpol(rdma, chg, dip, qad, octu, rpol, polinv, ndma, npol):
+    """solpol2.solpol as called at solefp.py:969 -> epol (Hartree), the EFP2 polarisation energy -1/2 F . D^-1 F
+    (solvshift/src/solpol2.f:1153-1267); scratch arrays allocated here."""
+    a = [_d(x).ravel() for x in (rdma, chg, dip, qad, octu, rpol, polinv)]
+    ndma = np.ascontiguousarray(ndma, np.int32); npol = np.ascontiguousarray(npol, np.int32)
+    nmols = ndma.size; ndim = 3 * int(npol.sum()); ndmas = int(ndma.sum())
+    dmat = np.zeros((ndim, ndim), order='F'); flds = np.zeros(ndim); dipind = np.zeros(ndim)
+    epol = ctypes.c_double(0.0)
+    lib().solpol_(*[_p(x) for x in a], ctypes.byref(epol), _p(dmat), _p(flds), _p(dipind),
+                  _i(nmols), _p(ndma), _p(npol), _i(ndim), _i(ndmas),
+                  _i(a[2].size), _i(a[3].size), _i(a[4].size), _i(a[5].size), _i(a[6].size), _i(0))
+    return epol.value, flds, dipind

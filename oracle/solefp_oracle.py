@@ -551,3 +551,34 @@ def eval_dma_frame(pos_c, parc0, supl_c, mode, env, ea=True, corr=True):
     pe = dict(rdma=env[:, :3], dmac=env[:, 3], dmad=np.zeros((n, 3)), dmaq=np.zeros((n, 6)), dmao=np.zeros((n, 10)))
     m, e, cm, ce, fi = elect_shifts(parc, [pe], mode, ea=ea, corr=corr)
     return dict(ele_env_mea=m, ele_env_ea=e, cor_env_mea=cm, cor_env_ea=ce)
+
+
+# --------------------------------------------------------------------------- energy ("global") mode
+def global_energies(pos, ind, nmol, pars, supl, reord, elect=True, pol=True):
+    """EFP._eval_mode_global (solefp.py:905-1009): every molecule superimposed, no cut-offs; e_coul over all molecule pairs,
+    e_pol = SOLPOL (solpol2.f:1153-1267) = -1/2 F . D^-1 F.  e_coul comes from libbbg.qm.clemtp.edmtpa, which is
+    un-vendored and has no known-answer data in the tree: restated with the multipole series through R^-4 of the shift
+    path (PARITY UNPINNED for this term).  Returns dict(ele, pol) in Hartree."""
+    ind = np.asarray(ind, int); nmol = np.asarray(nmol, int)
+    off = np.concatenate([[0], np.cumsum(nmol)])
+    PAR = []
+    for i in range(len(ind)):
+        t = ind[i]; p = pars[t]
+        ro = reord[t] if reord is not None and reord[t] is not None else np.arange(p['natoms'])
+        r, tr, _ = kabsch(p['pos'], reorder_xyz(pos[off[i]:off[i + 1]], ro), supl[t] if supl is not None else None)
+        PAR.append(sup_params(p, r, tr))
+    out = dict(ele=0.0, pol=0.0)
+    if elect:
+        mom = [_lab_moments(p) for p in PAR]
+        e = 0.0
+        for a in range(len(PAR)):
+            for b in range(a + 1, len(PAR)):
+                qa, ma, Ta, Oa = mom[a]; qb, mb, Tb, Ob = mom[b]
+                e += float(emtp_r4(PAR[a]['rdma'], qa, ma, Ta, Oa, PAR[b]['rdma'], qb, mb, Tb, Ob))
+        out['ele'] = e
+        if pol:
+            F, D = pol_system(PAR[0], PAR[1:])[:2]
+            Fv = F.ravel()
+            out['pol'] = -0.5 * Fv @ np.linalg.solve(D, Fv)
+    out['PAR'] = PAR
+    return out

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get('SLVGPU_LIB') or os.path.join(_HERE, 'csrc', 'libslvgp
 NOUT = 24
 NMETA = 32
 NSOL = 16
-FLAG = dict(elect=1, ea=2, corr=4, pol=8, disp=16, rep=32)
+FLAG = dict(elect=1, ea=2, corr=4, pol=8, disp=16, rep=32, glob=64)
 OUT = dict(ele_mea=0, ele_ea=1, cor_mea=2, cor_ea=3, pol_mea=4, rep_mea=5, dis_mea=6, dis_mea_iso=7,
            rms_c=8, rms_smax=9, rms_ave=10, n_elect=11, n_pol=12, n_rep=13, pol_iters=14, pol_resid=15, pol_add=16, pol_ncent=17, pol_nsite=18, pol_pairs=19,
            env_ele_mea=20, env_ele_ea=21, env_cor_mea=22, env_cor_ea=23)

@@ -51,8 +51,9 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, Fr
   }
   __syncthreads();
 
+  const bool global = (p.flags & SLVGPU_GLOBAL) != 0;     // energy mode: this kernel only superimposes and hands every instance over
   // solute site rows in the lab frame
-  if ((p.flags & SLVGPU_ELECT) && threadIdx.x < ndmac) {
+  if ((p.flags & SLVGPU_ELECT) && !global && threadIdx.x < ndmac) {
     const int s = threadIdx.x;
     double R[9];
 #pragma unroll
@@ -99,11 +100,12 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, Fr
       const int *tm = tmeta(p, p.inst_type[i]);
       const bool env = tm[SLVGPU_M_REMOVABLE] == 2;       // environment of eval_dma: no cut-off, electrostatics only
       if (env) flag = 4;
+      if (global) flag = 5;                               // no cut-offs: every fragment is in the electrostatic and polarisation layers
       if (flag) {
         fit_instance(p, tm, xi, rot, tr, rms);
         if (flag & 4) {
           if (!env) { ++n_c; rms_sum += rms; rms_max = fmax(rms_max, rms); }
-          if (p.flags & SLVGPU_ELECT) {
+          if ((p.flags & SLVGPU_ELECT) && !global) {
             const int nd = tm[SLVGPU_M_NDMA];
             const double *rd = p.dtab + tm[SLVGPU_M_O_RDMA], *mom = p.dtab + tm[SLVGPU_M_O_MOM];
             for (int s = 0; s < nd; ++s) {
@@ -180,6 +182,97 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, Fr
     o[SLVGPU_ENV_COR_MEA] = (el && (p.flags & SLVGPU_CORR)) ? w_mea : 0.0;
     o[SLVGPU_ENV_COR_EA] = (el && (p.flags & SLVGPU_CORR)) ? w_ea : 0.0;
     fl.nlist[fi] = s_base < p.list_cap ? s_base : p.list_cap;
+  }
+}
+
+
+// Energy mode (EFP(freq=False), solvshift/solefp.py:905-1009): electrostatic interaction energy of the whole cluster,
+//   E = sum over site pairs (a, b) of DIFFERENT fragments of the multipole series through R^-4
+// (libbbg.qm.clemtp.edmtpa is un-vendored: the same truncation as the shift path, slv::pair_potentials, is used -- DESIGN.md).
+// Persistent CTAs, one frame at a time; the lab-frame site table [nsite][24] (pos3, mom20, fragment) lives in a per-CTA
+// workspace; rows in registers, columns staged through shared memory, each unordered pair evaluated once.
+constexpr int GLOB_THREADS = 256;
+__global__ void __launch_bounds__(GLOB_THREADS, 2)
+k_global_elect(const DevPlan p, int frame0, int nframes, FrameLists fl, double *__restrict__ site_ws, double *__restrict__ out) {
+  __shared__ double s_tile[GLOB_THREADS * 24];
+  __shared__ double s_red[32];
+  __shared__ int s_n;
+  double *ws = site_ws + (size_t)blockIdx.x * p.site_cap * 24;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int *tm0 = tmeta(p, p.inst_type[0]);
+  for (int fi = blockIdx.x; fi < nframes; fi += gridDim.x) {
+    const int nl = fl.nlist[fi];
+    const size_t lbase = (size_t)fi * p.list_cap;
+    __syncthreads();
+    if (tid == 0) s_n = tm0[SLVGPU_M_NDMA];
+    __syncthreads();
+    // site table: fragment 0 first, then the list entries in order (offsets by a serial scan in chunks of NT entries)
+    for (int e0 = -1; e0 < nl; e0 += NT) {
+      const int e = e0 + tid;
+      const bool on = e < nl;
+      const int *tm = e < 0 ? tm0 : (on ? tmeta(p, p.inst_type[fl.list_inst[lbase + e]]) : tm0);
+      const int nd = on ? tm[SLVGPU_M_NDMA] : 0;
+      // exclusive scan of nd over the chunk
+      __shared__ int s_cnt[GLOB_THREADS];
+      s_cnt[tid] = (e < 0) ? 0 : nd;
+      __syncthreads();
+      int offs = (e < 0) ? 0 : s_n;
+      if (e >= 0) for (int k = 0; k < tid; ++k) offs += s_cnt[k];
+      if (on) {
+        double R[9], t[3];
+        const double *xf = e < 0 ? fl.sol_xf + (size_t)fi * 12 : fl.list_xf + (lbase + e) * 12;
+        for (int d = 0; d < 9; ++d) R[d] = xf[d];
+        for (int d = 0; d < 3; ++d) t[d] = xf[9 + d];
+        for (int sidx = 0; sidx < nd; ++sidx) {
+          if (offs + sidx >= p.site_cap) break;
+          double y[3], m[20];
+          rot_vec(R, p.dtab + tm[SLVGPU_M_O_RDMA] + sidx * 3, y);
+          rot_mom20(R, p.dtab + tm[SLVGPU_M_O_MOM] + sidx * 20, m);
+          double *row = ws + (size_t)(offs + sidx) * 24;
+          for (int d = 0; d < 3; ++d) row[d] = y[d] + t[d];
+          for (int d = 0; d < 20; ++d) row[3 + d] = m[d];
+          row[23] = (double)(e + 1);
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && e0 >= 0) { int tot = 0; for (int k = 0; k < NT; ++k) tot += s_cnt[k]; s_n += tot; }
+      if (e0 < 0) e0 = -NT;              // the first pass handled the solute alone (e = -1); entries start at 0
+      __syncthreads();
+    }
+    const int nsite = min(s_n, p.site_cap);
+    double acc = 0.0;
+    for (int i0 = 0; i0 < nsite; i0 += NT) {
+      const int i = i0 + tid;
+      const bool act = i < nsite;
+      double ri[3] = {0, 0, 0}, mi[20]; int moli = -1;
+      if (act) {
+        const double *row = ws + (size_t)i * 24;
+        for (int d = 0; d < 3; ++d) ri[d] = row[d];
+        for (int d = 0; d < 20; ++d) mi[d] = row[3 + d];
+        fold20(mi);
+        moli = (int)row[23];
+      }
+      for (int j0 = i0; j0 < nsite; j0 += NT) {           // columns j > i only
+        const int jn = min(NT, nsite - j0);
+        __syncthreads();
+        for (int w = tid; w < jn * 24; w += NT) s_tile[w] = ws[(size_t)j0 * 24 + w];
+        __syncthreads();
+        if (act) {
+          for (int jj = 0; jj < jn; ++jj) {
+            const double *rj = s_tile + jj * 24;
+            if (j0 + jj <= i || (int)rj[23] == moli) continue;
+            double P[23];
+            pair_potentials(ri, rj, rj + 3, P);
+            double e1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 20; ++k) e1 += mi[k] * P[k];
+            acc += e1;
+          }
+        }
+      }
+    }
+    acc = block_sum(acc, s_red);
+    if (tid == 0) out[(size_t)(frame0 + fi) * SLVGPU_NOUT + SLVGPU_ELE_MEA] = acc;
   }
 }
 

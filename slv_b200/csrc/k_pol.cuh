@@ -434,6 +434,13 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     // ---- (d) contractions with the solute rows: y^T dD x - (x+y).dF
     // solute tables in shared memory: centres [npolc][21]: pos3 r1(3) G(9) x3 y3 ; sites [ndmac][46]: pos3 mom20 dma1(20) L3
     double *s_c = sm + POL_TILE * 10, *s_s = s_c + (size_t)npolc * 21;
+    double acc = 0.0;
+    const bool global = (p.flags & SLVGPU_GLOBAL) != 0;
+    if (global) {
+      // EFP2 polarisation ENERGY of the whole cluster (SOLPOL, solvshift/src/solpol2.f:1153-1267): EPOL = -1/2 F . D^-1 F
+      for (int c = tid; c < ncent; c += NT)
+        acc += wk.fld[(size_t)c * 3] * vxy[(size_t)c * 6] + wk.fld[(size_t)c * 3 + 1] * vxy[(size_t)c * 6 + 1] + wk.fld[(size_t)c * 3 + 2] * vxy[(size_t)c * 6 + 2];
+    } else {
     {
       const double *sx = fl.sol_xf + (size_t)fi * 12;
       double R[9];
@@ -454,7 +461,6 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       }
     }
     __syncthreads();
-    double acc = 0.0;
     // term A: solute diagonal blocks  y_i^T G_i x_i,  G = -alpha^-1 (sum_m g_m alpha1_m) alpha^-1
     for (int i = tid; i < npolc; i += NT) {
       const double *row = s_c + (size_t)i * 21, *G = row + 6, *xi = row + 15, *yi = row + 18;
@@ -503,6 +509,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
         acc -= (row[15] + row[18]) * dF[0] + (row[16] + row[19]) * dF[1] + (row[17] + row[20]) * dF[2];
       }
     }
+    }   // frequency-shift contractions
     acc = block_sum(acc, s_red);
     if (pass < 0) { shift_main = -0.5 * acc; iters_out = iters; resid_out = resid; ncent_out = ncent; nsite_out = nsite; }
     else { shift_add += -0.5 * acc; resid_out = fmax(resid_out, resid); }
@@ -516,6 +523,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
           dd[(size_t)c * 12 + 6 + d] = wk.cent_pos[(size_t)c * 3 + d];
         }
       if (tid == 0) dd[(size_t)p.cent_cap * 12] = (double)ncent;
+      if (!global) {
       // ---- solvatochromic induced dipoles AVEC = sum_m g_m MIVEC_m = D^-T (dD^T y - dF) - D^-1 dF (solpol2.f:1122-1143):
       //      the vectors dF and w = dD^T y, then one more BiCG run with the right-hand sides (dF, w - dF)
       double *dFv = wk.aux, *btv = wk.aux + (size_t)p.cent_cap * 3;
@@ -570,6 +578,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
         for (int d = 0; d < 3; ++d) dd[(size_t)c * 12 + 9 + d] = vfin[(size_t)c * 6 + 3 + d] - vfin[(size_t)c * 6 + d];
       resid = fmax(res1, resid); iters = it1;
       iters_out = iters; resid_out = resid;
+      }   // AVEC (frequency-shift mode only)
     }
     } while (0);
     // next removable fragment inside pcut, if any

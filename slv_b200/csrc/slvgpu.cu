@@ -45,6 +45,7 @@ struct slvgpu_plan {
   std::vector<RepSmem> rep_sm;                // per such type: shared-memory plan of k_rep_pair
   std::vector<int> h_pair0;
   int pol_ctas_shared = 0;                    // k_pol grid when other kernels share the SMs with it
+  double *d_glob_sites = nullptr; int glob_ctas = 0;   // energy mode: per-CTA site tables of k_global_elect
   int overlap = 0;                            // SLVGPU_OVERLAP=1: dispersion / exchange repulsion beside k_pol (experimental)
   double *d_detail = nullptr;
   int *d_queue = nullptr;
@@ -158,7 +159,12 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
                                      ", which its parameter file does not provide");
     };
     const int ts = d->inst_type[0];
-    if (d->flags & SLVGPU_ELECT) {
+    const bool glob = (d->flags & SLVGPU_GLOBAL) != 0;       // energy mode: no mode-derivative tables are read
+    if (glob && (d->flags & (SLVGPU_DISP | SLVGPU_REP)))
+      return fail(SLVGPU_EINVAL, "the energy mode evaluates electrostatics and polarisation only (solvshift/solefp.py:906-908, 917-919)");
+    if ((d->flags & SLVGPU_ELECT) && glob) {
+      if (t0[SLVGPU_M_O_RDMA] < 0 || t0[SLVGPU_M_O_MOM] < 0) return miss("elect", "distributed multipoles", ts);
+    } else if (d->flags & SLVGPU_ELECT) {
       if (t0[SLVGPU_M_O_RDMA] < 0 || t0[SLVGPU_M_NDMA] < 1) return miss("elect", "distributed multipoles", ts);
       if (!need_sol(SLVGPU_S_SMEA) || !need_sol(SLVGPU_S_SEA) || !need_sol(SLVGPU_S_CMEA) || !need_sol(SLVGPU_S_CEA))
         return miss("elect", "multipole derivatives (dma1/dma2, lvec, gijk)", ts);
@@ -168,7 +174,10 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
       if (!need_sol(SLVGPU_S_DPOLI1)) return miss("disp", "dpoli1", ts);
       if (!need_sol(SLVGPU_S_LMOC1)) return miss("disp", "lmoc1", ts);
     }
-    if (d->flags & SLVGPU_POL) {
+    if ((d->flags & SLVGPU_POL) && glob) {
+      if (t0[SLVGPU_M_NPOL] < 1 || t0[SLVGPU_M_O_RPOL] < 0 || t0[SLVGPU_M_O_POL] < 0) return miss("pol", "dpol", ts);
+      if (t0[SLVGPU_M_O_RDMA] < 0 || t0[SLVGPU_M_O_MOM] < 0) return miss("pol", "distributed multipoles", ts);
+    } else if (d->flags & SLVGPU_POL) {
       if (t0[SLVGPU_M_NPOL] < 1 || t0[SLVGPU_M_O_RPOL] < 0 || t0[SLVGPU_M_O_POL] < 0) return miss("pol", "dpol", ts);
       if (t0[SLVGPU_M_O_RDMA] < 0 || t0[SLVGPU_M_O_MOM] < 0) return miss("pol", "distributed multipoles", ts);
       if (!need_sol(SLVGPU_S_DPOL1)) return miss("pol", "dpol1", ts);
@@ -245,7 +254,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   const int32_t *tm0 = d->type_meta + (size_t)d->inst_type[0] * SLVGPU_NMETA;
   pl->ndmac = tm0[SLVGPU_M_NDMA]; pl->npolc = tm0[SLVGPU_M_NPOL]; pl->nmosc = tm0[SLVGPU_M_NMOS];
   pl->nbasc = tm0[SLVGPU_M_NBASIS]; pl->natc = tm0[SLVGPU_M_NATOMS];
-  if ((d->flags & SLVGPU_POL) && pl->ndmac != pl->natc) {
+  if ((d->flags & SLVGPU_POL) && !(d->flags & SLVGPU_GLOBAL) && pl->ndmac != pl->natc) {
     slvgpu_plan_destroy(pl);
     return fail(SLVGPU_EINVAL, "polarisation shift needs ndma == natoms on the solute (solpol2.f:738-741, 873-876)");
   }
@@ -294,6 +303,10 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
       pl->detail_frames = pl->max_chunk;
       TRY(dalloc(pl, &pl->d_detail, (size_t)pl->detail_frames * (cc * 12 + 1)));
     }
+  }
+  if ((d->flags & SLVGPU_GLOBAL) && (d->flags & SLVGPU_ELECT)) {
+    pl->glob_ctas = pl->sm_count * 2;
+    TRY(dalloc(pl, &pl->d_glob_sites, (size_t)pl->glob_ctas * (size_t)p.site_cap * 24));
   }
   if (d->flags & SLVGPU_REP) {
     if (tm0[SLVGPU_M_O_VECL] < 0 || d->sol_meta[SLVGPU_S_VECL1] < 0) {
@@ -387,6 +400,13 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
       CK(cudaEventRecord(pl->ev_elect, st));
       CK(cudaStreamWaitEvent(pl->side[0], pl->ev_elect, 0));
       CK(cudaStreamWaitEvent(pl->side[1], pl->ev_elect, 0));
+    }
+    if ((p.flags & SLVGPU_GLOBAL) && (p.flags & SLVGPU_ELECT) && p.ninst > 1) {
+      const int g = nf < pl->glob_ctas ? nf : pl->glob_ctas;
+      ev_begin(pl, 1, st);
+      k_global_elect<<<g, GLOB_THREADS, 0, st>>>(p, (int)f0, nf, pl->fl, pl->d_glob_sites, d_out);
+      ev_end(pl, st);
+      ++pl->last_launches;
     }
     cudaStream_t s_disp = overlap ? pl->side[0] : st;
     if (do_disp) {

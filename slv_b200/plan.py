@@ -140,7 +140,7 @@ class Plan(object):
                 raise KeyError("'vecl'/'fock'/'lmoc': exchange repulsion needs the wave function of fragment %r" % nm)
             if fl & (_lib.FLAG['elect'] | _lib.FLAG['pol']) and 'rdma' not in par:
                 raise KeyError("'rdma': fragment %r has no distributed multipoles" % nm)
-        if len(ind) > 1:
+        if len(ind) > 1 and not (fl & _lib.FLAG['glob']):
             pc0 = pars[int(ind[0])]
             for flag, keys in (('disp', ('dpoli', 'dpoli1', 'lmoc1')), ('pol', ('dpol', 'dpol1', 'lmoc1', 'dmac1', 'lvec')),
                                ('rep', ('vecl', 'vecl1', 'fock', 'fock1', 'lmoc', 'lmoc1', 'lvec')), ('elect', ('rdma', 'dmac1', 'gijk'))):

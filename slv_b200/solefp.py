@@ -141,12 +141,18 @@ class EFP(UNITS):
         if ct:
             raise NotImplementedError('charge-transfer is not evaluated by the central (frequency shift) mode '
                                       '(no ct branch in solvshift/solefp.py:1011-1629)')
+        self._freq = bool(freq)
         if not freq:
-            raise NotImplementedError('only the frequency-shift (freq=True) mode is on the GPU path; the global '
-                                      'EFP2 interaction-energy mode (solefp.py:905-1009) is out of scope')
-        if mode is None:
+            # EFP2 interaction-energy ("global") mode, solefp.py:905-1009: electrostatics + polarisation over every fragment
+            # pair, no cut-offs, no central molecule; dispersion raises as in the reference (906-908) and the
+            # exchange-repulsion energy is 0.0 there (its loop is commented out, 917-919)
+            if self._disp:
+                raise NotImplementedError(' Global mode is not implemented yet for Dispersion Interaction Energies!')
+            self._rep = False
+        elif mode is None:
             raise ValueError('freq=True needs mode=<1-based normal mode index>')
         self._mode = mode
+        self._eint = dict((k, numpy.nan) for k in ('ele', 'rep', 'pol', 'dis', 'total_hf', 'total'))
         if self._rep:
             _warn_rep_unpinned()
         self._plan = None; self._plan_key = None
@@ -194,6 +200,8 @@ class EFP(UNITS):
     def _flags(self):
         # in the reference, pol/disp are only reached inside `if self.__eval_elect` (solefp.py:1122-1437)
         el = bool(self._elect)
+        if not self._freq:
+            return dict(elect=el, ea=False, corr=False, pol=bool(self._pol) and el, disp=False, rep=False, glob=True)
         return dict(elect=el, ea=bool(self._ea) and el, corr=bool(self._corr) and el,
                     pol=bool(self._pol) and el, disp=bool(self._disp) and el, rep=bool(self._rep))
 
@@ -246,12 +254,52 @@ class EFP(UNITS):
         if num:
             raise NotImplementedError('numerical (finite-difference) mode needs the num_0.006/*.frg sets, which are '
                                       'not part of the parameter library')
-        self._removable = self._removable_types(rcl_algorithm, include_ions, include_polar) if remove_clashes else None
+        self._removable = self._removable_types(rcl_algorithm, include_ions, include_polar) if (remove_clashes and self._freq) else None
         rows, status = self._get_plan().eval_host(self._pos[None])
+        if not self._freq:
+            self._rows, self._status = rows, status
+            for k, v in self.energies_of(rows).items():
+                self._eint[k] = float(v[0])
+            O = _lib.OUT
+            self._rms_central = float(rows[0, O['rms_c']]); self._rms_solvent_max = float(max(rows[0, O['rms_c']], rows[0, O['rms_smax']]))
+            self._rms_ave = float(rows[0, O['rms_ave']])
+            if lwrite:
+                print(self._energy_report())
+            return
         self._store(rows, status)
         if lwrite:
             print(self)
         return
+
+    def energies_of(self, rows):
+        """Energy mode: per-frame EFP2 interaction energies from device rows, in kcal/mol when cunit else Hartree
+        (the dictionary the reference fills at solefp.py:975-995)."""
+        if hasattr(rows, 'cpu'):
+            rows = rows.cpu().numpy()
+        r = numpy.asarray(rows, numpy.float64)
+        c = self.HartreeToKcalPerMole if self._cunit else 1.0
+        O = _lib.OUT
+        e = dict(ele=r[:, O['ele_mea']] * c, rep=numpy.zeros(len(r)), pol=r[:, O['pol_mea']] * c, dis=numpy.zeros(len(r)))
+        e['total_hf'] = e['ele'] + e['rep'] + e['pol']
+        e['total'] = e['total_hf'] + e['dis']
+        return e
+
+    def get_eint(self):
+        """Energy mode: the interaction-energy dictionary (ele, rep, pol, dis, total_hf, total) of the last eval()."""
+        return self._eint.copy()
+
+    def _energy_report(self):
+        e = self._eint
+        log = " EFP2 Interaction Energies %s\n" % ('[kcal/Mole]' if self._cunit else '[A.U.]')
+        log += " =============================================== \n"
+        log += " Electrostatic      Int. Energy    : %10.2f\n" % e['ele']
+        log += " Exchange-repulsion Int. Energy    : %10.2f\n" % e['rep']
+        log += " Polarization       Int. Energy    : %10.2f\n" % e['pol']
+        log += " Dispersion         Int. Energy    : %10.2f\n" % e['dis']
+        log += " ----------------------------------------------- \n"
+        log += " Total Int. Energy                 : %10.2f\n" % e['total']
+        log += " Total Int. Energy (HF)            : %10.2f" % e['total_hf']
+        return log
 
     def eval_frames(self, coords, ind=None, nmol=None, bsm=None, supl=None, reord=None, out=None, status=None,
                     scale=None, idx=None, remove_clashes=None, rcl_algorithm='remove_by_name', include_ions=False,

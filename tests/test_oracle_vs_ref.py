@@ -164,3 +164,21 @@ def test_rep_force_is_the_derivative_of_the_reference_exrep_energy(frags, solute
     for m in modes:
         fd = (8.0 * (energy(m, h) - energy(m, -h)) - (energy(m, 2 * h) - energy(m, -2 * h))) / (12.0 * h)
         assert abs(fd - fi[m]) < 1e-6 * max(np.abs(fi).max(), abs(fi[m])), (m, fd, fi[m])
+
+
+def test_solpol_energy(frags):
+    """Energy mode (row N3): the oracle's polarisation energy -1/2 F . D^-1 F against the reference's own SOLPOL
+    (solpol2.f:1153-1267, transpiled), called as at solefp.py:969."""
+    from oracle import solefp_oracle as O
+    sol, wat, parc, solv, rot = _cluster(frags, 7, 4)
+    PAR = [parc] + solv
+    QO = [RN.tracls(p['dmaq'], p['dmao']) for p in PAR]
+    cat = lambda k: np.concatenate([p[k] for p in PAR])
+    epol, flds, dipind = RN.solpol(cat('rdma'), cat('dmac'), cat('dmad'), np.concatenate([x[0] for x in QO]),
+                                   np.concatenate([x[1] for x in QO]), cat('rpol'), np.linalg.inv(cat('dpol')),
+                                   [p['ndma'] for p in PAR], [p['npol'] for p in PAR])
+    F, D = O.pol_system(parc, solv)[:2]
+    Fv = F.ravel()
+    e = -0.5 * Fv @ np.linalg.solve(D, Fv)
+    assert epol < 0 and abs(e - epol) < 1e-12 * abs(epol)
+    assert np.abs(Fv - flds).max() < 1e-13 * np.abs(flds).max()
