@@ -194,7 +194,8 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, Fr
 constexpr int GLOB_THREADS = 256;
 __global__ void __launch_bounds__(GLOB_THREADS, 2)
 k_global_elect(const DevPlan p, int frame0, int nframes, FrameLists fl, double *__restrict__ site_ws, double *__restrict__ out) {
-  __shared__ double s_tile[GLOB_THREADS * 24];
+  constexpr int TJ = 128;                          // column sites per shared-memory tile
+  __shared__ double s_tile[TJ * 24];
   __shared__ double s_red[32];
   __shared__ int s_n;
   double *ws = site_ws + (size_t)blockIdx.x * p.site_cap * 24;
@@ -252,8 +253,8 @@ k_global_elect(const DevPlan p, int frame0, int nframes, FrameLists fl, double *
         fold20(mi);
         moli = (int)row[23];
       }
-      for (int j0 = i0; j0 < nsite; j0 += NT) {           // columns j > i only
-        const int jn = min(NT, nsite - j0);
+      for (int j0 = i0; j0 < nsite; j0 += TJ) {           // columns j > i only
+        const int jn = min(TJ, nsite - j0);
         __syncthreads();
         for (int w = tid; w < jn * 24; w += NT) s_tile[w] = ws[(size_t)j0 * 24 + w];
         __syncthreads();

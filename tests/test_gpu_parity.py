@@ -569,3 +569,31 @@ def test_exchange_repulsion_partner_types(frags, partner):
     c = O.HartreePerHbarToCmRec
     assert int(status[0]) == 0 and rows[0, 13] == ref['n_rep'] >= 1
     assert abs(rows[0, 5] * c - ref['rep_mea'] * c) < 1e-6 * max(1.0, abs(ref['rep_mea'] * c) * 1e-3), (rows[0, 5] * c, ref['rep_mea'] * c)
+
+
+def test_energy_mode_matches_oracle(frags):
+    """Row N3, EFP(freq=False) (solefp.py:905-1009): electrostatic energy of all fragment pairs and the polarisation
+    energy of the cluster, no cut-offs and no central molecule, in kcal/mol with cunit -- against the oracle (whose
+    polarisation energy is pinned on the reference's SOLPOL; the electrostatic term restates the un-vendored edmtpa)."""
+    from slv_b200 import synth
+    from slv_b200.solefp import EFP
+    from oracle import solefp_oracle as O
+    wat, meoh, nma = frags('water'), frags('meoh'), frags('nma')
+    types = np.array([0, 1, 0, 0, 2, 1, 0, 0, 1, 0, 0, 0])
+    X = synth.make_trajectory(wat.get_pos(), [wat.get_pos(), meoh.get_pos(), nma.get_pos()], types, 3, seed=12, spacing=7.5, rmin=3.2)
+    bsm = [wat, wat, meoh, nma]                       # fragment 0 is an ordinary water: nothing is "central" here
+    ind = [0] + [1 + int(t) for t in types]; nmol = [3] + [bsm[1 + t].get_natoms() for t in types]
+    efp = EFP(elect=True, pol=True, freq=False, cunit=True, ccut=5.0, pcut=5.0, ecut=5.0)      # cut-offs are ignored in this mode
+    rows, status = efp.eval_frames(X, ind, nmol, bsm, [None] * 4, [None] * 4)
+    e = efp.energies_of(rows)
+    k = 627.509451
+    for f in range(3):
+        ref = O.global_energies(X[f], ind, nmol, [b.get() for b in bsm], [None] * 4, [None] * 4)
+        assert abs(e['ele'][f] - ref['ele'] * k) < 1e-9 * max(1.0, abs(ref['ele'] * k)), (f, e['ele'][f], ref['ele'] * k)
+        assert abs(e['pol'][f] - ref['pol'] * k) < 1e-9 * max(1.0, abs(ref['pol'] * k)), (f, e['pol'][f], ref['pol'] * k)
+        assert e['rep'][f] == 0.0 and abs(e['total'][f] - e['ele'][f] - e['pol'][f]) < 1e-12
+    assert int(status.max()) == 0 and rows[0, 12] == len(types)
+    efp.set(X[1], ind, nmol, bsm, [None] * 4, [None] * 4); efp.eval(0)
+    assert abs(efp.get_eint()['total'] - e['total'][1]) < 1e-12 and 'Polarization       Int. Energy' in efp._energy_report()
+    with pytest.raises(NotImplementedError):
+        EFP(elect=True, pol=True, disp=True, freq=False)
