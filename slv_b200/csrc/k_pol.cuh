@@ -27,7 +27,10 @@ namespace slv {
 constexpr int POL_THREADS = SLV_POL_THREADS;
 constexpr int POL_CTAS_PER_SM = SLV_POL_CTAS_PER_SM;
 constexpr int POL_CTAS_SHARED_PER_SM = 2;   // k_pol CTAs per SM while dispersion / exchange-repulsion kernels run beside it
-constexpr int POL_TILE = 1024;   // centres the resident sweep tile holds (80 KB of shared memory)
+#ifndef SLV_POL_TILE
+#define SLV_POL_TILE 1024
+#endif
+constexpr int POL_TILE = SLV_POL_TILE;   // centres the resident sweep tile holds (80 KB of shared memory)
 constexpr int SITE_ROW = 24;     // pos3, mom20, molecule id
 constexpr int PST = 30;          // BiCG state per centre: x xt r rt p pt u ut q qt (3 each)
 
