@@ -87,6 +87,10 @@ enum {
                        * work items a * nsubsh + b (a: solute sub-shell, b: this type's), grouped by the 23
                        * (L_bra, L_ket, bra component) specialisations of slv_ints.cuh SLV_SUBSHELL_CLASSES,
                        * heavy primitive-pair counts first inside a class                                    */
+  SLVGPU_M_IO_SHITEM, /* itab (16-byte aligned): [items][8] per work item of IO_SHPAIR, same order: 3 * solute atom, first
+                       * solute function, 3 * fragment atom, first fragment function, first record in O_PPTAB, records   */
+  SLVGPU_M_O_PPTAB,   /* dtab (16-byte aligned): [records][6] primitive pairs of every (solute sub-shell, sub-shell) pair,
+                       * thr = 46 (a+b)/(ab), mu, c_a c_b (pi/(a+b))^1.5, 1/(a+b), a, b; thr descending within a pair    */
   SLVGPU_NMETA = 32
 };
 

@@ -33,6 +33,9 @@ namespace slv {
 
 constexpr int REP_THREADS = 128;
 constexpr int REP_INT_THREADS = 128;
+#ifndef SLV_REP_INT_DBLOCKS
+#define SLV_REP_INT_DBLOCKS 3     // resident blocks per SM the d-shell classes of the integral kernel are compiled for
+#endif
 constexpr int REP_CS = 12;        // row stride (doubles) of a solute coefficient octet tile: 8 k's + 4 pad, == 4 (mod 8)
 constexpr int REP_MAX_NIT = 3;    // solute LMO tiles of 8 (nmos <= 24)
 constexpr int REP_IP = 8 * REP_MAX_NIT;   // rows of a solute coefficient tile (fixed: strides become compile-time constants)
@@ -52,8 +55,10 @@ struct RepPool {            // one batch of (frame, fragment) pairs (V .. pair_t
   double *res;     // [pair_cap]  sum_ij fi of the pair
   int *pair_frame, *pair_entry, *pair_type;   // [pair_cap]
   int *pair0;      // [max_chunk + 1] exclusive scan of the per-frame pair counts
+  int *tlist;      // [ntypes][pair_cap]  pair slots of every fragment type (filled by k_rep_prep, any order)
+  int *tcount;     // [ntypes]            their number (zeroed before k_rep_prep)
   size_t sV, sCA;
-  int pair_cap, max_nat, nbsA16, IP;
+  int pair_cap, max_nat, nbsA16, IP, ntypes;
 };
 
 // Two pools (the batches alternate between two streams, so the integral kernels of one batch overlap the
@@ -63,7 +68,7 @@ struct RepPool {            // one batch of (frame, fragment) pairs (V .. pair_t
 struct RepLimits { size_t max_pairs = 0; };
 
 inline int rep_alloc(RepPool rp[2], RepLimits &lim, std::vector<void *> &allocs, std::string &err, int nmosc, int nbasc,
-                     int natc, int max_nbas, int max_nat, int max_chunk, int list_cap) {
+                     int natc, int max_nbas, int max_nat, int max_chunk, int list_cap, int ntypes) {
   // integral pools: together up to 8 GiB and at most a quarter of the free memory, never more than the worst case
   const int nbsA16 = (nbasc + 15) & ~15, IP = REP_IP;
   (void)nmosc;
@@ -99,13 +104,16 @@ inline int rep_alloc(RepPool rp[2], RepLimits &lim, std::vector<void *> &allocs,
   for (int h = 0; h < 2; ++h) {
     rp[h].sV = sV; rp[h].sCA = sCA; rp[h].max_nat = max_nat; rp[h].pair_cap = 0; rp[h].V = nullptr; rp[h].nbsA16 = nbsA16; rp[h].IP = IP;
     rp[h].posB = nullptr; rp[h].res = nullptr; rp[h].pair_frame = rp[h].pair_entry = rp[h].pair_type = nullptr;
+    rp[h].tlist = rp[h].tcount = nullptr; rp[h].ntypes = ntypes;
   }
   return 0;
 }
 
 inline void rep_pool_free(RepPool &r) {
   cudaFree(r.V); cudaFree(r.posB); cudaFree(r.res); cudaFree(r.pair_frame); cudaFree(r.pair_entry); cudaFree(r.pair_type);   // cudaFree(nullptr) is a no-op
+  cudaFree(r.tlist); cudaFree(r.tcount);
   r.V = nullptr; r.posB = nullptr; r.res = nullptr; r.pair_frame = r.pair_entry = r.pair_type = nullptr;
+  r.tlist = r.tcount = nullptr;
   r.pair_cap = 0;
 }
 
@@ -125,6 +133,8 @@ inline int rep_reserve(RepPool rp[2], const RepLimits &lim, size_t pairs, std::s
     ok = ok && cudaMalloc(&rp[h].pair_frame, pairs * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&rp[h].pair_entry, pairs * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&rp[h].pair_type, pairs * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&rp[h].tlist, pairs * (size_t)rp[h].ntypes * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&rp[h].tcount, (size_t)rp[h].ntypes * sizeof(int)) == cudaSuccess;
     // the memsets ran on the legacy default stream, which the plan's non-blocking streams do not wait for
     ok = ok && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {                                     // leave no half-built pool behind (a retry starts from scratch)
@@ -260,6 +270,7 @@ __global__ void __launch_bounds__(128) k_rep_prep(const DevPlan p, int fs, Frame
       const int ty = p.inst_type[fl.list_inst[lbase + e]];
       const int *tm = tmeta(p, ty);
       rp.pair_frame[slot] = fi; rp.pair_entry[slot] = e; rp.pair_type[slot] = ty;
+      rp.tlist[(size_t)ty * rp.pair_cap + atomicAdd(rp.tcount + ty, 1)] = slot;   // order within a type is irrelevant: every pair is independent
       const double *xf = fl.list_xf + (lbase + e) * 12;
       double R[9], t[3];
       for (int d = 0; d < 9; ++d) R[d] = xf[d];
@@ -277,27 +288,6 @@ __global__ void __launch_bounds__(128) k_rep_prep(const DevPlan p, int fs, Frame
   }
 }
 
-// AO integrals of one (L_bra, L_ket, bra component) class for the pairs of fragment type `type`: thread t handles
-// pair t / n_items, item lo + t % n_items (items sorted by primitive-pair count, so neighbouring lanes run equal loops)
-template <int LA, int LB, int IA>
-__global__ void __launch_bounds__(REP_INT_THREADS)
-k_rep_ints(const DevPlan p, int type, int lo, int n_items, int npairs, RepPool rp) {
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int pr = (int)(t / n_items);
-  if (pr >= npairs || rp.pair_type[pr] != type) return;
-  const int it = (int)(t - (long)pr * n_items);
-  const int *tm0 = tmeta(p, p.inst_type[0]), *tm = tmeta(p, type);
-  const int nsubB = tm[SLVGPU_M_NSUBSH], nbsB = tm[SLVGPU_M_NBASIS], natA = tm0[SLVGPU_M_NATOMS];
-  const int w = p.itab[tm[SLVGPU_M_IO_SHPAIR] + SUBSHELL_NCLASS + 1 + lo + it];
-  const int a = w / nsubB, b = w - a * nsubB;
-  const size_t fa = (size_t)rp.pair_frame[pr] * natA * 3;
-  subshell_pair_store<LA, LB, IA>(p.itab + tm0[SLVGPU_M_IO_SUBSH] + a * 4, p.itab + tm[SLVGPU_M_IO_SUBSH] + b * 4,
-                                  rp.posA + fa, rp.posB + (size_t)pr * rp.max_nat * 3,
-                                  p.dtab + tm0[SLVGPU_M_O_BFEXP], p.dtab + tm0[SLVGPU_M_O_BFCOEF],
-                                  p.dtab + tm[SLVGPU_M_O_BFEXP], p.dtab + tm[SLVGPU_M_O_BFCOEF],
-                                  rp.LcA + fa, rep_lp(nbsB), rp.V + (size_t)pr * rp.sV);
-}
-
 // ---- small PTX wrappers: FP64 tensor-core MMA, mbarrier, 1-D bulk asynchronous copy (TMA)
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -313,9 +303,70 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {   // 8 bytes global -> shared, no register staging
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
   asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n"
                ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// AO integrals of one (L_bra, L_ket, bra component) class for the pairs of fragment type `type`.  A thread owns ONE item
+// of the class (a sub-shell pair; items sorted by primitive-pair count, so neighbouring lanes run equal loops) and walks
+// the block's share of the type's pairs (blockIdx.y, `ppb` <= 32 pairs): everything that does not depend on the geometry
+// -- the item record, its primitive-pair table, the V offsets -- is fetched once, and the geometry of
+// the next pair (solute atoms and displacement vectors of its frame, the fragment's atoms) streams into the warp's
+// shared-memory buffer with cp.async while the current pair is evaluated.  (One thread per (pair, item) paid the chain of
+// five dependent global loads for ~500 instructions of arithmetic.)
+template <int LA, int LB, int IA>
+__global__ void __launch_bounds__(REP_INT_THREADS, (LB == 2 || (LA == 2 && LB == 0)) ? SLV_REP_INT_DBLOCKS : (LA + LB == 0 ? 6 : 4))
+k_rep_ints(const DevPlan p, int type, int lo, int n_items, int ppb, RepPool rp) {
+  extern __shared__ double s_geo[];                        // [warps][2][gws]
+  constexpr int NA = IA < 0 ? cart_ncomp(LA) : 1, NB = cart_ncomp(LB);
+  const int cnt = rp.tcount[type];
+  const int q0 = blockIdx.y * ppb;
+  if (q0 >= cnt) return;
+  const int nq = min(cnt - q0, ppb);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int *tm0 = tmeta(p, p.inst_type[0]), *tm = tmeta(p, type);
+  const int natA = tm0[SLVGPU_M_NATOMS], natB = tm[SLVGPU_M_NATOMS];
+  const int LP = rep_lp(tm[SLVGPU_M_NBASIS]);
+  const int it = blockIdx.x * blockDim.x + tid;
+  const bool act = it < n_items;
+  // item record: 3 * atom_A, first function A, 3 * atom_B, first function B, first primitive-pair record, records
+  const int4 ir = *reinterpret_cast<const int4 *>(p.itab + tm[SLVGPU_M_IO_SHITEM] + (size_t)(lo + (act ? it : n_items - 1)) * 8);
+  const int2 ip = *reinterpret_cast<const int2 *>(p.itab + tm[SLVGPU_M_IO_SHITEM] + (size_t)(lo + (act ? it : n_items - 1)) * 8 + 4);
+  const int atA = ir.x, f0a = ir.y, atB = ir.z, f0b = ir.w, npp = ip.y;
+  const double *rec = p.dtab + tm[SLVGPU_M_O_PPTAB] + (size_t)ip.x * PP_REC;
+  const int nA3 = natA * 3, gw = 2 * nA3 + natB * 3, gws = (gw + 1) & ~1;
+  double *geo = s_geo + (size_t)warp * 2 * gws;
+  // lane l keeps the slot and the frame of pair q0 + l
+  const int my_slot = lane < nq ? rp.tlist[(size_t)type * rp.pair_cap + q0 + lane] : 0;
+  const int my_frame = rp.pair_frame[my_slot];
+  auto stage = [&](int i) {
+    const int slot = __shfl_sync(0xffffffffu, my_slot, i), fr = __shfl_sync(0xffffffffu, my_frame, i);
+    const double *gA = rp.posA + (size_t)fr * nA3, *gL = rp.LcA + (size_t)fr * nA3 - nA3, *gB = rp.posB + (size_t)slot * rp.max_nat * 3 - 2 * nA3;
+    double *dst = geo + (i & 1) * gws;
+    for (int x = lane; x < gw; x += 32) cp_async8(dst + x, (x < nA3 ? gA : (x < 2 * nA3 ? gL : gB)) + x);
+    cp_async_commit();
+  };
+  stage(0);
+  for (int i = 0; i < nq; ++i) {
+    cp_async_wait_all();
+    __syncwarp();
+    if (i + 1 < nq) stage(i + 1);                          // the other buffer: every lane finished pair i - 1 before the barrier above
+    const int slot = __shfl_sync(0xffffffffu, my_slot, i);
+    if (act) {
+      const double *g = geo + (i & 1) * gws;
+      const double A[3] = {g[atA], g[atA + 1], g[atA + 2]}, L[3] = {g[nA3 + atA], g[nA3 + atA + 1], g[nA3 + atA + 2]};
+      const double B[3] = {g[2 * nA3 + atB], g[2 * nA3 + atB + 1], g[2 * nA3 + atB + 2]};
+      double acc[NA * NB * 4];
+      subshell_pair_t<LA, LB, IA>(A, B, L, npp, rec, acc);
+      subshell_pair_write<LA, LB, IA>(acc, f0a, f0b, LP, rp.V + (size_t)slot * rp.sV);
+    }
+  }
 }
 
 // One CTA per (frame, fragment) pair of fragment type `type`: half transform and LMO integrals on the FP64 tensor cores,

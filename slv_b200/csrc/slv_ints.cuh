@@ -86,12 +86,18 @@ struct AxisVals {
   }
 };
 
+// Record of one primitive pair of a sub-shell pair, tabulated when the plan is built (slv_b200/plan.py
+// primitive_pair_records): thr = 46 (a + b) / (a b), mu = a b / (a + b), pref0 = c_a c_b (pi / (a + b))^(3/2) with the
+// coefficients of the first component of each sub-shell, ip = 1 / (a + b), a, b.  The records of a sub-shell pair are
+// sorted by thr, largest first: the pairs with exp(-mu AB^2) >= exp(-46) at a distance AB are a prefix of the list, so a
+// thread walks ITS survivors and stops at the first record whose threshold the distance exceeds -- no division, square
+// root or screening loop per evaluation.
+constexpr int PP_REC = 6;
+
 // acc[(ca * NB + cb) * 4 + q] += contributions of all primitive pairs; q = S, T, L.dS/dA, L.dT/dA.
 // ca = bra component slot (component index when IA < 0, else 0), cb = ket component.
 template <int LA, int LB, int IA>
-SLV_HD void subshell_pair_t(const double A[3], int npa, const double *ea, const double *ca,
-                            const double B[3], int npb, const double *eb, const double *cb,
-                            const double L[3], double *acc) {
+SLV_HD void subshell_pair_t(const double A[3], const double B[3], const double L[3], int npp, const double *__restrict__ rec, double *acc) {
   constexpr bool ALL = IA < 0;
   constexpr int NA = ALL ? cart_ncomp(LA) : 1, NB = cart_ncomp(LB);
   constexpr int MX = ALL ? LA : cart_pow(LA, IA, 0), MY = ALL ? LA : cart_pow(LA, IA, 1), MZ = ALL ? LA : cart_pow(LA, IA, 2);
@@ -99,39 +105,12 @@ SLV_HD void subshell_pair_t(const double A[3], int npa, const double *ea, const 
   const double AB2 = ABx * ABx + ABy * ABy + ABz * ABz;
 #pragma unroll
   for (int w = 0; w < NA * NB * 4; ++w) acc[w] = 0.0;
-  // Primitive pairs with exp(-mu AB^2) < exp(-46) are dropped.  The survivors are first collected in a bit mask and then
-  // walked bit by bit: every lane runs through ITS survivors only, so a warp iterates max(survivors per lane) times
-  // instead of over the union of all lanes' survivors (a third fewer iterations on the bench workloads).
-  unsigned long long live = 0ull;
-  for (int p = 0; p < npa; ++p) {
-    const double a = ea[p];
-    for (int q = 0; q < npb; ++q) {
-      const double b = eb[q];
-      if (a * b * AB2 <= 46.0 * (a + b)) live |= 1ull << (p * 8 + q);
-    }
-  }
-  // the exponents and coefficients of the NEXT surviving pair are fetched before the arithmetic of the current one
-  // (the loads are L1 / L2 hits, but their latency sat on the critical path of every iteration)
-  auto pop = [&live]() {
-#ifdef __CUDA_ARCH__
-    const int bit = __ffsll((long long)live) - 1;
-#else
-    const int bit = __builtin_ctzll(live);
-#endif
-    live &= live - 1ull;
-    return bit;
-  };
-  double a_n = 0.0, b_n = 0.0, cc_n = 0.0;
-  bool more = live != 0ull;
-  if (more) { const int bit = pop(); a_n = ea[bit >> 3]; b_n = eb[bit & 7]; cc_n = ca[bit >> 3] * cb[bit & 7]; }
-  while (more) {
+  for (int k = 0; k < npp; ++k, rec += PP_REC) {
+    if (!(AB2 <= rec[0])) break;
     {
-      const double a = a_n, b = b_n, cc = cc_n;
-      more = live != 0ull;
-      if (more) { const int bit = pop(); a_n = ea[bit >> 3]; b_n = eb[bit & 7]; cc_n = ca[bit >> 3] * cb[bit & 7]; }
-      const double pp = a + b, ip = 1.0 / pp, h = 0.5 * ip;
-      const double mu = a * b * ip;
-      const double pref = cc * exp(-mu * AB2) * (3.14159265358979323846 * ip) * sqrt(3.14159265358979323846 * ip);
+      const double mu = rec[1], pref0 = rec[2], ip = rec[3], a = rec[4], b = rec[5];
+      const double h = 0.5 * ip;
+      const double pref = pref0 * exp(-mu * AB2);
       const double fa = -b * ip, fb = a * ip;
       AxisVals<MX, LB, ALL> X; AxisVals<MY, LB, ALL> Y; AxisVals<MZ, LB, ALL> Z;
       X.build(fa * ABx, fb * ABx, h, a, b); X.scale(pref);       // every term below carries exactly one x factor
@@ -161,35 +140,63 @@ SLV_HD void subshell_pair_t(const double A[3], int npa, const double *ea, const 
   }
 }
 
-// One work item of k_rep phase 1: sub-shells sa = {atom, first function, L, nprim} of the solute and sb of the
-// solvent fragment; writes V[((f0a + ca) * LP + f0b + cb) * 4 + q] (LP records of four kinds per solute basis function).  eX/cX are the per-function [nbf][6] exponent and
-// coefficient tables (coefficient x primitive norm x contracted norm), LcA the per-atom displacement vectors.
+// Norm of component c of a sub-shell relative to its first component: only d components differ, d_xy, d_xz, d_yz carry
+// sqrt(3) relative to d_xx, d_yy, d_zz (primitive norms ~ 1/sqrt((2l-1)!!(2m-1)!!(2n-1)!!), equal contracted norms;
+// slv_b200/basis.py) -- a compile-time constant, so the contraction can use the coefficients of the first component.
+SLV_HD constexpr double cart_norm_ratio(int L, int c) { return (L == 2 && c >= 3) ? 1.7320508075688772 : 1.0; }
+
+// Scale the contracted sums of one sub-shell pair and write them to V[((f0a + ca) * LP + f0b + cb) * 4 + q]
+// (LP records of four kinds per solute basis function).
 template <int LA, int LB, int IA>
-SLV_HD void subshell_pair_store(const int *sa, const int *sb, const double *posA, const double *posB,
-                                const double *eA, const double *cA, const double *eB, const double *cB,
-                                const double *LcA, int LP, double *V) {
+SLV_HD void subshell_pair_write(const double *acc, int f0a, int f0b, int LP, double *V) {
   constexpr int NA = IA < 0 ? cart_ncomp(LA) : 1, NB = cart_ncomp(LB);
-  const int f0a = sa[1], f0b = sb[1];
-  double acc[NA * NB * 4];
-  subshell_pair_t<LA, LB, IA>(posA + sa[0] * 3, sa[3], eA + f0a * 6, cA + f0a * 6, posB + sb[0] * 3, sb[3], eB + f0b * 6, cB + f0b * 6,
-                              LcA + sa[0] * 3, acc);
-  const double ia0 = 1.0 / cA[f0a * 6], ib0 = 1.0 / cB[f0b * 6];
 #pragma unroll
   for (int c1 = 0; c1 < NA; ++c1) {
-    const int k = f0a + (IA < 0 ? c1 : IA);
-    const double ra = (LA == 2) ? cA[k * 6] * ia0 : 1.0;          // only d components differ in norm within a sub-shell
+    const int ka = IA < 0 ? c1 : IA, k = f0a + ka;
 #pragma unroll
     for (int c2 = 0; c2 < NB; ++c2) {
       const int l = f0b + c2;
-      const double f = (LB == 2) ? ra * (cB[l * 6] * ib0) : ra;
+      const double f = cart_norm_ratio(LA, ka) * cart_norm_ratio(LB, c2);
       double *v = V + ((size_t)k * LP + l) * 4;                   // V[k][l][q], LP records per row
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const double x = f * acc[(c1 * NB + c2) * 4 + q];
+        const double x = (f == 1.0) ? acc[(c1 * NB + c2) * 4 + q] : f * acc[(c1 * NB + c2) * 4 + q];
         v[q] = (x - x == 0.0) ? x : 0.0;                            // non-finite -> 0: the pool is recycled and its cells are
       }                                                             // read (times zero) by later batches
     }
   }
+}
+
+// Host-side restatement of the record builder (the plan builds the same table in NumPy): records of the primitive
+// pairs of two sub-shells, thresholds descending.  rec must hold npa * npb * PP_REC doubles.
+inline void primitive_pair_records(int npa, const double *ea, const double *ca, int npb, const double *eb, const double *cb, double *rec) {
+  int n = 0;
+  for (int p = 0; p < npa; ++p)
+    for (int q = 0; q < npb; ++q, ++n) {
+      const double a = ea[p], b = eb[q], ip = 1.0 / (a + b), pi = 3.14159265358979323846;
+      double *r = rec + n * PP_REC;
+      r[0] = 46.0 * (a + b) / (a * b); r[1] = a * b * ip; r[2] = ca[p] * cb[q] * (pi * ip) * sqrt(pi * ip); r[3] = ip; r[4] = a; r[5] = b;
+    }
+  for (int i = 1; i < n; ++i)                                       // insertion sort, thr descending (stable)
+    for (int j = i; j > 0 && rec[(j - 1) * PP_REC] < rec[j * PP_REC]; --j)
+      for (int d = 0; d < PP_REC; ++d) { const double t = rec[j * PP_REC + d]; rec[j * PP_REC + d] = rec[(j - 1) * PP_REC + d]; rec[(j - 1) * PP_REC + d] = t; }
+}
+
+// One work item of k_rep phase 1 in a single call (the integral kernel takes the records from the plan's table and
+// hoists everything that does not depend on the geometry out of its loop over pairs; this is the same sequence, used
+// by the host check): sub-shells sa = {atom, first function, L, nprim} of the solute and sb of the solvent fragment,
+// eX/cX the per-function [nbf][6] exponent and coefficient tables (coefficient x primitive norm x contracted norm),
+// LcA the per-atom displacement vectors.
+template <int LA, int LB, int IA>
+inline void subshell_pair_store(const int *sa, const int *sb, const double *posA, const double *posB,
+                                const double *eA, const double *cA, const double *eB, const double *cB,
+                                const double *LcA, int LP, double *V) {
+  constexpr int NA = IA < 0 ? cart_ncomp(LA) : 1, NB = cart_ncomp(LB);
+  const int f0a = sa[1], f0b = sb[1];
+  double acc[NA * NB * 4], rec[36 * PP_REC];
+  primitive_pair_records(sa[3], eA + f0a * 6, cA + f0a * 6, sb[3], eB + f0b * 6, cB + f0b * 6, rec);
+  subshell_pair_t<LA, LB, IA>(posA + sa[0] * 3, posB + sb[0] * 3, LcA + sa[0] * 3, sa[3] * sb[3], rec, acc);
+  subshell_pair_write<LA, LB, IA>(acc, f0a, f0b, LP, V);
 }
 
 // The 23 (LA, LB, IA) specialisations in the order of the plan's work list (slv_b200/plan.py, IO_SHPAIR):

@@ -46,6 +46,7 @@ struct slvgpu_plan {
   std::vector<int> h_pair0;
   int pol_ctas_shared = 0;                    // k_pol grid when other kernels share the SMs with it
   double *d_glob_sites = nullptr; int glob_ctas = 0;   // energy mode: per-CTA site tables of k_global_elect
+  int rep_ppb = 0, rep_bt = 128;              // integral kernels: pairs per block (0 = by batch size) and block size (testing knobs)
   int overlap = 0;                            // SLVGPU_OVERLAP=1: dispersion / exchange repulsion beside k_pol (experimental)
   double *d_detail = nullptr;
   int *d_queue = nullptr;
@@ -317,7 +318,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
       slvgpu_plan_destroy(pl);
       return fail(SLVGPU_EINVAL, "exchange repulsion: the solute has more than 24 LMOs (k_rep_pair keeps its LMO integrals in registers)");
     }
-    TRY(rep_alloc(pl->rp, pl->rep_lim, pl->allocs, g_err, pl->nmosc, pl->nbasc, pl->natc, pl->max_nbas, pl->max_nat, pl->max_chunk, p.list_cap));
+    TRY(rep_alloc(pl->rp, pl->rep_lim, pl->allocs, g_err, pl->nmosc, pl->nbasc, pl->natc, pl->max_nbas, pl->max_nat, pl->max_chunk, p.list_cap, p.ntypes));
     for (int t = 0; t < d->ntypes; ++t) {
       const int32_t *tm = d->type_meta + (size_t)t * SLVGPU_NMETA;
       if (tm[SLVGPU_M_IO_SHPAIR] < 0 || !solvent_type[t]) continue;
@@ -348,6 +349,8 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   if (const char *ev = getenv("SLVGPU_POL_CTAS")) { const int v = atoi(ev); if (v > 0) pl->pol_ctas_shared = v; }
   if (pl->pol_ctas_shared > pl->pol_ctas) pl->pol_ctas_shared = pl->pol_ctas;     // the workspace is sized for pol_ctas CTAs
   if (const char *ev = getenv("SLVGPU_OVERLAP")) pl->overlap = atoi(ev) != 0;
+  if (const char *ev = getenv("SLVGPU_REP_PPB")) { const int v = atoi(ev); if (v >= 1 && v <= 32) pl->rep_ppb = v; }
+  if (const char *ev = getenv("SLVGPU_REP_BT")) { const int v = atoi(ev); if (v == 32 || v == 64 || v == 128) pl->rep_bt = v; }
   *out = pl;
   return 0;
 }
@@ -459,17 +462,22 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
         }
         const int nb = fe - fs, npairs = pair0[fe] - pair0[fs];
         if (npairs > 0) {
+          CK(cudaMemsetAsync(rp.tcount, 0, (size_t)p.ntypes * sizeof(int), sb));
           k_rep_prep<<<nb, 128, 0, sb>>>(p, fs, pl->fl, rp);
           ++pl->last_launches;
+          // integral kernels: grid.x covers the items of a class, grid.y the pairs of the type in groups of ppb (the
+          // type's pair count lives on the device; groups past it leave at once)
+          const int ppb = pl->rep_ppb > 0 ? pl->rep_ppb : (npairs >= 8192 ? 32 : (npairs >= 2048 ? 16 : 8));
+          const unsigned gy = (unsigned)((npairs + ppb - 1) / ppb);
           for (size_t ti = 0; ti < pl->rep_types.size(); ++ti) {
             const int ty = pl->rep_types[ti];
             const std::vector<int> &co = pl->rep_cls[ti];
+            const size_t sm_geo = (size_t)(pl->rep_bt / 32) * 2 * ((2 * 3 * (size_t)pl->natc + 3 * (size_t)pl->max_nat + 1) & ~(size_t)1) * sizeof(double);
 #define X(ID, LA, LB, IA)                                                                                         \
             if (co[ID + 1] > co[ID]) {                                                                              \
               const int n_items = co[ID + 1] - co[ID];                                                              \
-              const long nthr = (long)npairs * n_items;                                                             \
-              k_rep_ints<LA, LB, IA><<<(unsigned)((nthr + REP_INT_THREADS - 1) / REP_INT_THREADS), REP_INT_THREADS, 0, sb>>>( \
-                  p, ty, co[ID], n_items, npairs, rp);                                                              \
+              k_rep_ints<LA, LB, IA><<<dim3((unsigned)((n_items + pl->rep_bt - 1) / pl->rep_bt), gy), pl->rep_bt, sm_geo, sb>>>( \
+                  p, ty, co[ID], n_items, ppb, rp);                                                                 \
               ++pl->last_launches;                                                                                  \
             }
             SLV_SUBSHELL_CLASSES(X)

@@ -33,6 +33,12 @@ class _Tab(object):
         self.chunks.append(a); self.n += a.size
         return off
 
+    def pad(self, k):
+        """Make the next offset a multiple of k elements."""
+        r = (-self.n) % k
+        if r:
+            self.add(numpy.zeros(r, self.dtype))
+
     def get(self):
         if not self.chunks:
             return numpy.zeros(1, self.dtype)
@@ -69,6 +75,38 @@ def subshell_work_list(sA, sB):
         items.append((a[o] * len(sB) + b[o]).astype(numpy.int32))
         offs.append(offs[-1] + len(o))
     return numpy.array(offs, numpy.int32), numpy.concatenate(items).astype(numpy.int32)
+
+
+PP_REC = 6      # doubles per primitive-pair record (slv_ints.cuh PP_REC)
+
+
+def primitive_pair_records(bA, bB, items):
+    """Tables behind the integral kernels' work items (``items`` from subshell_work_list).
+
+    Returns ``irec`` int32 [nitems, 8] = (3 * atom_A, first function A, 3 * atom_B, first function B, first record,
+    records, 0, 0) and ``ptab`` float64 [nrec, PP_REC]: for every (solute sub-shell, fragment sub-shell) pair the
+    records (thr, mu, pref0, 1/(a+b), a, b) of its primitive pairs -- thr = 46 (a+b)/(a b) is the squared distance beyond
+    which exp(-mu AB^2) < exp(-46), mu = a b/(a+b), pref0 = c_a c_b (pi/(a+b))^1.5 with the coefficients of the first
+    component of each sub-shell -- sorted by thr, largest first, so the surviving pairs at any distance are a prefix."""
+    sA, sB = bA.subshells, bB.subshells
+    nB = len(sB)
+    first = numpy.zeros((len(sA), nB), numpy.int64)
+    recs, n = [], 0
+    for ia, (_, fa, _, npa) in enumerate(sA):
+        ea, ca = bA.exps[fa, :npa], bA.coefs[fa, :npa]
+        for ib, (_, fb, _, npb) in enumerate(sB):
+            eb, cb = bB.exps[fb, :npb], bB.coefs[fb, :npb]
+            a, b = numpy.repeat(ea, npb), numpy.tile(eb, npa)
+            ip = 1.0 / (a + b)
+            r = numpy.stack([46.0 * (a + b) / (a * b), a * b * ip, numpy.repeat(ca, npb) * numpy.tile(cb, npa) * (numpy.pi * ip) ** 1.5,
+                             ip, a, b], 1)
+            recs.append(r[numpy.argsort(-r[:, 0], kind='stable')])
+            first[ia, ib] = n; n += len(r)
+    ia, ib = items // nB, items % nB
+    irec = numpy.zeros((len(items), 8), numpy.int32)
+    irec[:, 0] = 3 * sA[ia, 0]; irec[:, 1] = sA[ia, 1]; irec[:, 2] = 3 * sB[ib, 0]; irec[:, 3] = sB[ib, 1]
+    irec[:, 4] = first[ia, ib]; irec[:, 5] = sA[ia, 3] * sB[ib, 3]
+    return irec, numpy.concatenate(recs).reshape(-1, PP_REC)
 
 
 class Plan(object):
@@ -157,6 +195,9 @@ class Plan(object):
             for t, bB in self._bfs.items():
                 offs, items = subshell_work_list(sA, bB.subshells)
                 meta[t][M['IO_SHPAIR']] = it.add(numpy.concatenate([offs, items]))
+                irec, ptab = primitive_pair_records(self._bfs[int(ind[0])], bB, items)
+                it.pad(4); dt.pad(2)                       # 16-byte aligned records
+                meta[t][M['IO_SHITEM']] = it.add(irec); meta[t][M['O_PPTAB']] = dt.add(ptab)
         # ---- solute: mode-contracted tables
         sol = numpy.full(_lib.NSOL, -1, numpy.int32)
         S = _lib.S
