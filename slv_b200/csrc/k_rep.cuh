@@ -33,6 +33,13 @@ namespace slv {
 
 constexpr int REP_THREADS = 128;
 constexpr int REP_INT_THREADS = 128;
+constexpr int REP_INT_SREC = PP_SREC;   // primitive-pair records per item the integral kernel keeps in shared memory
+// doubles of one geometry buffer of the integral kernel (solute atoms, displacement vectors, fragment atoms), even
+__host__ __device__ inline int gws_of(int natA, int natB) { return (natA * 6 + natB * 3 + 1) & ~1; }
+// dynamic shared memory of the integral kernel: two geometry buffers per warp, REP_INT_SREC records per thread
+__host__ __device__ inline size_t rep_ints_smem(int threads, int natA, int max_natB) {
+  return ((size_t)(threads / 32) * 2 * gws_of(natA, max_natB) + (size_t)threads * REP_INT_SREC * 6) * sizeof(double);
+}
 #ifndef SLV_REP_INT_DBLOCKS
 #define SLV_REP_INT_DBLOCKS 3     // resident blocks per SM the d-shell classes of the integral kernel are compiled for
 #endif
@@ -47,8 +54,8 @@ __host__ __device__ inline int rep_lp(int nbs) { return (nbs + 3) & ~3; }
 
 struct RepPool {            // one batch of (frame, fragment) pairs (V .. pair_type) + per-frame tables of the chunk
   double *V;       // [pair_cap][nbsA16][LP(type)][4]  AO integrals (S, T, L.dS, L.dT per record), block stride sV
-  double *posA;    // [max_chunk][natA][3]   solute atoms, lab frame
-  double *LcA;     // [max_chunk][natA][3]   mode-contracted displacement vectors, lab frame
+  double *posA;    // [max_chunk][2][natA][3]  per frame: solute atoms in the lab frame, then the mode-contracted displacement
+                   //                          vectors (one contiguous record: the integral kernels stage it in one piece)
   double *riA;     // [max_chunk][2][nmosA][3]  LMO centroids and their mode-contracted derivatives
   double *CA;      // [max_chunk][nbsA16/8][2][IP][REP_CS]  rotated vecl / g-contracted vecl1 of the solute in k-octet tiles
   double *posB;    // [pair_cap][max_nat][3]
@@ -92,8 +99,7 @@ inline int rep_alloc(RepPool rp[2], RepLimits &lim, std::vector<void *> &allocs,
 #define RA(ptr, n, T)                                                                                                   \
   if (cudaMalloc(&q, (size_t)(n) * sizeof(T)) != cudaSuccess) { err = "cudaMalloc(rep tables) failed"; return SLVGPU_ENOMEM; } \
   allocs.push_back(q); ptr = (T *)q;
-  RA(rp[0].posA, (size_t)max_chunk * natc * 3, double)
-  RA(rp[0].LcA, (size_t)max_chunk * natc * 3, double)
+  RA(rp[0].posA, (size_t)max_chunk * natc * 6, double)
   RA(rp[0].riA, (size_t)max_chunk * nmosc * 6, double)
   RA(rp[0].CA, (size_t)max_chunk * sCA, double)
   RA(rp[0].pair0, (size_t)max_chunk + 1, int)
@@ -233,9 +239,9 @@ __global__ void __launch_bounds__(128) k_rep_prep(const DevPlan p, int fs, Frame
     for (int a = tid; a < natA; a += NT) {
       double y[3];
       rot_vec(R0, p.dtab + tm0[SLVGPU_M_O_POS] + a * 3, y);
-      double *pa = rp.posA + ((size_t)fi * natA + a) * 3;
+      double *pa = rp.posA + ((size_t)fi * 2 * natA + a) * 3;
       pa[0] = y[0] + t0[0]; pa[1] = y[1] + t0[1]; pa[2] = y[2] + t0[2];
-      rot_vec(R0, p.dtab + p.sol_meta[SLVGPU_S_LVEC] + a * 3, rp.LcA + ((size_t)fi * natA + a) * 3);
+      rot_vec(R0, p.dtab + p.sol_meta[SLVGPU_S_LVEC] + a * 3, rp.posA + ((size_t)(fi * 2 + 1) * natA + a) * 3);
     }
     const int nmosA = tm0[SLVGPU_M_NMOS];
     double *ri = rp.riA + (size_t)fi * nmosA * 6;
@@ -340,16 +346,25 @@ k_rep_ints(const DevPlan p, int type, int lo, int n_items, int ppb, RepPool rp) 
   const int2 ip = *reinterpret_cast<const int2 *>(p.itab + tm[SLVGPU_M_IO_SHITEM] + (size_t)(lo + (act ? it : n_items - 1)) * 8 + 4);
   const int atA = ir.x, f0a = ir.y, atB = ir.z, f0b = ir.w, npp = ip.y;
   const double *rec = p.dtab + tm[SLVGPU_M_O_PPTAB] + (size_t)ip.x * PP_REC;
-  const int nA3 = natA * 3, gw = 2 * nA3 + natB * 3, gws = (gw + 1) & ~1;
+  // the first REP_INT_SREC records of the item stay in shared memory for all its pairs ([record][field][thread]: lanes
+  // read consecutive words); the deeper ones -- tight primitives, reached only at short distances -- come from the table
+  double *srec = s_geo + (size_t)(blockDim.x >> 5) * 2 * gws_of(natA, natB) + tid;
+  {
+    const int n = min(npp, REP_INT_SREC);
+    for (int k = 0; k < n; ++k)
+#pragma unroll
+      for (int d = 0; d < PP_REC; ++d) srec[(k * PP_REC + d) * blockDim.x] = rec[k * PP_REC + d];
+  }
+  const int nA6 = natA * 6, gw = nA6 + natB * 3, gws = gws_of(natA, natB);
   double *geo = s_geo + (size_t)warp * 2 * gws;
   // lane l keeps the slot and the frame of pair q0 + l
   const int my_slot = lane < nq ? rp.tlist[(size_t)type * rp.pair_cap + q0 + lane] : 0;
   const int my_frame = rp.pair_frame[my_slot];
   auto stage = [&](int i) {
     const int slot = __shfl_sync(0xffffffffu, my_slot, i), fr = __shfl_sync(0xffffffffu, my_frame, i);
-    const double *gA = rp.posA + (size_t)fr * nA3, *gL = rp.LcA + (size_t)fr * nA3 - nA3, *gB = rp.posB + (size_t)slot * rp.max_nat * 3 - 2 * nA3;
+    const double *gA = rp.posA + (size_t)fr * nA6, *gB = rp.posB + (size_t)slot * rp.max_nat * 3 - nA6;
     double *dst = geo + (i & 1) * gws;
-    for (int x = lane; x < gw; x += 32) cp_async8(dst + x, (x < nA3 ? gA : (x < 2 * nA3 ? gL : gB)) + x);
+    for (int x = lane; x < gw; x += 32) cp_async8(dst + x, (x < nA6 ? gA : gB) + x);
     cp_async_commit();
   };
   stage(0);
@@ -360,10 +375,10 @@ k_rep_ints(const DevPlan p, int type, int lo, int n_items, int ppb, RepPool rp) 
     const int slot = __shfl_sync(0xffffffffu, my_slot, i);
     if (act) {
       const double *g = geo + (i & 1) * gws;
-      const double A[3] = {g[atA], g[atA + 1], g[atA + 2]}, L[3] = {g[nA3 + atA], g[nA3 + atA + 1], g[nA3 + atA + 2]};
-      const double B[3] = {g[2 * nA3 + atB], g[2 * nA3 + atB + 1], g[2 * nA3 + atB + 2]};
+      const double A[3] = {g[atA], g[atA + 1], g[atA + 2]}, L[3] = {g[nA6 / 2 + atA], g[nA6 / 2 + atA + 1], g[nA6 / 2 + atA + 2]};
+      const double B[3] = {g[nA6 + atB], g[nA6 + atB + 1], g[nA6 + atB + 2]};
       double acc[NA * NB * 4];
-      subshell_pair_t<LA, LB, IA>(A, B, L, npp, rec, acc);
+      subshell_pair_t<LA, LB, IA>(A, B, L, npp, rec, srec, (int)blockDim.x, acc);
       subshell_pair_write<LA, LB, IA>(acc, f0a, f0b, LP, rp.V + (size_t)slot * rp.sV);
     }
   }
@@ -419,7 +434,7 @@ k_rep_pair(const DevPlan p, int type, FrameLists fl, RepPool rp, RepSmem L) {
     for (int d = 0; d < 9; ++d) R[d] = xf[d];
     for (int d = 0; d < 3; ++d) tr[d] = xf[9 + d];
   }
-  for (int w = tid; w < natA * 3; w += NT) { posA[w] = rp.posA[(size_t)fi * natA * 3 + w]; LcA[w] = rp.LcA[(size_t)fi * natA * 3 + w]; }
+  for (int w = tid; w < natA * 6; w += NT) posA[w] = rp.posA[(size_t)fi * natA * 6 + w];                 // posA then LcA, contiguous
   for (int w = tid; w < nmosA * 6; w += NT) riA[w] = rp.riA[(size_t)fi * nmosA * 6 + w];        // riA then ri1A, contiguous
   for (int w = tid; w < natB * 3; w += NT) posB[w] = rp.posB[(size_t)pr * rp.max_nat * 3 + w];
   for (int j = tid; j < nmosB; j += NT) {

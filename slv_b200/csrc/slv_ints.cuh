@@ -93,11 +93,13 @@ struct AxisVals {
 // thread walks ITS survivors and stops at the first record whose threshold the distance exceeds -- no division, square
 // root or screening loop per evaluation.
 constexpr int PP_REC = 6;
+constexpr int PP_SREC = 4;    // leading records of an item the integral kernel keeps in shared memory
 
 // acc[(ca * NB + cb) * 4 + q] += contributions of all primitive pairs; q = S, T, L.dS/dA, L.dT/dA.
 // ca = bra component slot (component index when IA < 0, else 0), cb = ket component.
 template <int LA, int LB, int IA>
-SLV_HD void subshell_pair_t(const double A[3], const double B[3], const double L[3], int npp, const double *__restrict__ rec, double *acc) {
+SLV_HD void subshell_pair_t(const double A[3], const double B[3], const double L[3], int npp, const double *__restrict__ rec,
+                            const double *srec, int sstride, double *acc) {
   constexpr bool ALL = IA < 0;
   constexpr int NA = ALL ? cart_ncomp(LA) : 1, NB = cart_ncomp(LB);
   constexpr int MX = ALL ? LA : cart_pow(LA, IA, 0), MY = ALL ? LA : cart_pow(LA, IA, 1), MZ = ALL ? LA : cart_pow(LA, IA, 2);
@@ -105,10 +107,14 @@ SLV_HD void subshell_pair_t(const double A[3], const double B[3], const double L
   const double AB2 = ABx * ABx + ABy * ABy + ABz * ABz;
 #pragma unroll
   for (int w = 0; w < NA * NB * 4; ++w) acc[w] = 0.0;
-  for (int k = 0; k < npp; ++k, rec += PP_REC) {
-    if (!(AB2 <= rec[0])) break;
+  // records k < PP_SREC come from srec[(k * PP_REC + field) * sstride] (the kernel's shared-memory copy), the rest from rec
+  for (int k = 0; k < npp; ++k) {
+    const bool sh = srec != nullptr && k < PP_SREC;
+    const double *r = sh ? srec + (size_t)k * PP_REC * sstride : rec + (size_t)k * PP_REC;
+    const int st = sh ? sstride : 1;
+    if (!(AB2 <= r[0])) break;
     {
-      const double mu = rec[1], pref0 = rec[2], ip = rec[3], a = rec[4], b = rec[5];
+      const double mu = r[st], pref0 = r[2 * st], ip = r[3 * st], a = r[4 * st], b = r[5 * st];
       const double h = 0.5 * ip;
       const double pref = pref0 * exp(-mu * AB2);
       const double fa = -b * ip, fb = a * ip;
@@ -195,7 +201,7 @@ inline void subshell_pair_store(const int *sa, const int *sb, const double *posA
   const int f0a = sa[1], f0b = sb[1];
   double acc[NA * NB * 4], rec[36 * PP_REC];
   primitive_pair_records(sa[3], eA + f0a * 6, cA + f0a * 6, sb[3], eB + f0b * 6, cB + f0b * 6, rec);
-  subshell_pair_t<LA, LB, IA>(posA + sa[0] * 3, posB + sb[0] * 3, LcA + sa[0] * 3, sa[3] * sb[3], rec, acc);
+  subshell_pair_t<LA, LB, IA>(posA + sa[0] * 3, posB + sb[0] * 3, LcA + sa[0] * 3, sa[3] * sb[3], rec, nullptr, 1, acc);
   subshell_pair_write<LA, LB, IA>(acc, f0a, f0b, LP, V);
 }
 

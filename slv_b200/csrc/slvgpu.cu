@@ -342,6 +342,9 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
 #define RPA(KT, NNT) cudaFuncSetAttribute(k_rep_pair<KT, NNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   RPA(8, 1) RPA(8, 2) RPA(8, 3) RPA(8, 4) RPA(8, 5) RPA(16, 1) RPA(16, 2) RPA(16, 3) RPA(16, 4) RPA(16, 5)
 #undef RPA
+#define X(ID, LA, LB, IA) cudaFuncSetAttribute(k_rep_ints<LA, LB, IA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  SLV_SUBSHELL_CLASSES(X)
+#undef X
   // With dispersion or exchange repulsion in the plan, k_pol leaves part of every SM to their kernels (they run on the
   // plan's side streams at the same time); SLVGPU_POL_CTAS overrides the grid for experiments.
   pl->pol_ctas_shared = pl->pol_ctas;
@@ -472,7 +475,7 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
           for (size_t ti = 0; ti < pl->rep_types.size(); ++ti) {
             const int ty = pl->rep_types[ti];
             const std::vector<int> &co = pl->rep_cls[ti];
-            const size_t sm_geo = (size_t)(pl->rep_bt / 32) * 2 * ((2 * 3 * (size_t)pl->natc + 3 * (size_t)pl->max_nat + 1) & ~(size_t)1) * sizeof(double);
+            const size_t sm_geo = rep_ints_smem(pl->rep_bt, pl->natc, pl->max_nat);
 #define X(ID, LA, LB, IA)                                                                                         \
             if (co[ID + 1] > co[ID]) {                                                                              \
               const int n_items = co[ID + 1] - co[ID];                                                              \

@@ -1,5 +1,4 @@
 #!/bin/bash
-# exchange-repulsion integral kernel variants on the headline workload (run through gpurun)
 python -m pytest tests -m gpu -x -q -k "rep or repulsion or full or batch" 2>&1 | tail -3
 run() {
   env "$@" python bench.py --config 3 --only --no-cpu --steps 3 --warmup 3 2>/dev/null | python -c "
@@ -9,4 +8,5 @@ d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$*', round(d['va
 run SLVGPU_REP_PPB=4
 run SLVGPU_REP_PPB=8
 run SLVGPU_REP_PPB=16
+run SLVGPU_REP_PPB=32
 run SLVGPU_REP_BT=64 SLVGPU_REP_PPB=8
