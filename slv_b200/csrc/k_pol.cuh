@@ -22,15 +22,21 @@ namespace slv {
 #define SLV_POL_THREADS 256
 #endif
 #ifndef SLV_POL_CTAS_PER_SM
-#define SLV_POL_CTAS_PER_SM 2
+#define SLV_POL_CTAS_PER_SM 3
 #endif
 constexpr int POL_THREADS = SLV_POL_THREADS;
 constexpr int POL_CTAS_PER_SM = SLV_POL_CTAS_PER_SM;
 constexpr int POL_CTAS_SHARED_PER_SM = 2;   // k_pol CTAs per SM while dispersion / exchange-repulsion kernels run beside it
 #ifndef SLV_POL_TILE
-#define SLV_POL_TILE 1024
+#define SLV_POL_TILE 768
 #endif
-constexpr int POL_TILE = SLV_POL_TILE;   // centres the resident sweep tile holds (80 KB of shared memory)
+constexpr int POL_TILE = SLV_POL_TILE;   // centres the resident sweep tile holds: {position, u, ut, molecule} = 80 bytes each;
+                                         // 768 centres = 60 KB: three CTAs share an SM and the shared-memory carve-out leaves L1 for the workspace traffic
+#ifndef SLV_POL_ROWS
+#define SLV_POL_ROWS 2
+#endif
+constexpr int POL_ROWS = SLV_POL_ROWS;   // rows per lane in the resident sweep (2: the tile entry of a column is read once for two rows)
+constexpr int POL_BSH = POL_ROWS == 2 ? 6 : 5;   // log2 of the rows of a sweep block
 constexpr int SITE_ROW = 24;     // pos3, mom20, molecule id
 constexpr int PST = 30;          // BiCG state per centre: x xt r rt p pt u ut q qt (3 each)
 
@@ -48,7 +54,7 @@ struct PolWork {                 // per-CTA workspace (device pointers already o
 };
 
 // One ordered centre pair of the BiCG sweep: dipole tensor of R = rc - r_j applied to the two search directions
-// held in the tile entry tt = {r_j(3), p_j(3), ut_j(3)}; same-molecule pairs (incl. self) are masked branch-free.
+// held in the tile entry tt = {r_j(3), p_j(3), ut_j(3), molecule_j}; same-molecule pairs (incl. self) are masked branch-free.
 __device__ __forceinline__ void sweep_pair(const double rc[3], const bool same, const double tt[9], double ax[3], double ay[3]) {
   const double Rx = rc[0] - tt[0], Ry = rc[1] - tt[1], Rz = rc[2] - tt[2];
   const double r2 = same ? 1.0 : (Rx * Rx + Ry * Ry + Rz * Rz);
@@ -65,11 +71,10 @@ __global__ void __launch_bounds__(POL_THREADS, POL_CTAS_PER_SM)
 k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, double *__restrict__ out, int *__restrict__ status,
       double *__restrict__ detail /* optional [nframes][cent_cap][9]: dipind, flds, rpol */, int *__restrict__ queue) {
   __shared__ double s_red[64];
-  __shared__ int s_tmol[POL_TILE];
   __shared__ int s_fi;
   __shared__ unsigned long long s_scan[POL_THREADS / 32];
   __shared__ int s_n[4];
-  extern __shared__ double sm[];    // [POL_TILE*10] sweep tile, then the solute tables of the contraction phase
+  extern __shared__ double sm[];    // [POL_TILE*10] sweep tile; the solute tables of the contraction phase reuse it
   double *s_tile = sm;
 
   PolWork wk = wk0;
@@ -254,7 +259,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       for (int j = tid; j < ncent; j += NT) {
         double *tt = s_tile + j * 10;
         tt[0] = wk.cent_pos[(size_t)j * 3]; tt[1] = wk.cent_pos[(size_t)j * 3 + 1]; tt[2] = wk.cent_pos[(size_t)j * 3 + 2];
-        s_tmol[j] = wk.cent_mol[j];
+        tt[9] = (double)wk.cent_mol[j];
       }
     }
     if (bnorm > 0.0) {
@@ -291,18 +296,18 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
           // A range that covers a block only partly leaves partial sums in the workspace (head = slot 0, tail =
           // slot 1); after one barrier they are added in ascending warp order -- deterministic.
           const int warp = tid >> 5, lane = tid & 31, nwarp = NT >> 5;
-          const int nb2 = (ncent + 63) >> 6;
+          const int nb2 = (ncent + (1 << POL_BSH) - 1) >> POL_BSH;
           const int W = nb2 * ncent, Q = (W + nwarp - 1) / nwarp;
           const bool split = (Q % ncent) != 0;
           const int u1 = min(W, (warp + 1) * Q);
           for (int u = warp * Q; u < u1;) {
             const int b = u / ncent, ja = u - b * ncent, jb = min(ncent, ja + (u1 - u));
-            const int ca = (b << 6) + lane, cb = ca + 32;
-            const bool acta = ca < ncent, actb = cb < ncent;
-            const bool anyb = __any_sync(0xffffffffu, actb);
-            double ra[3] = {0, 0, 0}, rb[3] = {0, 0, 0}; int ma = -1, mb = -1;
-            if (acta) { ra[0] = s_tile[ca * 10]; ra[1] = s_tile[ca * 10 + 1]; ra[2] = s_tile[ca * 10 + 2]; ma = s_tmol[ca]; }
-            if (actb) { rb[0] = s_tile[cb * 10]; rb[1] = s_tile[cb * 10 + 1]; rb[2] = s_tile[cb * 10 + 2]; mb = s_tmol[cb]; }
+            const int ca = (b << POL_BSH) + lane, cb = ca + 32;
+            const bool acta = ca < ncent, actb = POL_ROWS == 2 && cb < ncent;
+            const bool anyb = POL_ROWS == 2 && __any_sync(0xffffffffu, actb);
+            double ra[3] = {0, 0, 0}, rb[3] = {0, 0, 0}, ma = -1.0, mb = -1.0;      // molecule ids are small integers held as doubles
+            if (acta) { ra[0] = s_tile[ca * 10]; ra[1] = s_tile[ca * 10 + 1]; ra[2] = s_tile[ca * 10 + 2]; ma = s_tile[ca * 10 + 9]; }
+            if (actb) { rb[0] = s_tile[cb * 10]; rb[1] = s_tile[cb * 10 + 1]; rb[2] = s_tile[cb * 10 + 2]; mb = s_tile[cb * 10 + 9]; }
             double axa[3] = {0, 0, 0}, aya[3] = {0, 0, 0}, axb[3] = {0, 0, 0}, ayb[3] = {0, 0, 0};
             if (anyb) {
 #pragma unroll 2
@@ -310,9 +315,8 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
                 const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
                 const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
                 const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
-                const int mj = s_tmol[jj];
-                sweep_pair(ra, mj == ma, tt, axa, aya);
-                sweep_pair(rb, mj == mb, tt, axb, ayb);
+                sweep_pair(ra, q4.y == ma, tt, axa, aya);
+                sweep_pair(rb, q4.y == mb, tt, axb, ayb);
               }
             } else if (acta) {
 #pragma unroll 4
@@ -320,7 +324,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
                 const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
                 const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
                 const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
-                sweep_pair(ra, s_tmol[jj] == ma, tt, axa, aya);
+                sweep_pair(ra, q4.y == ma, tt, axa, aya);
               }
             }
             if (ja == 0 && jb == ncent) {                       // the whole block: finish its rows here
@@ -328,7 +332,8 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
               if (actb) finish(cb, axb, ayb);
             } else {
               double *pp = wk.part + ((size_t)(warp * 2 + (ja > 0 ? 0 : 1)) * 64 + lane) * 6;
-              for (int d = 0; d < 3; ++d) { pp[d] = axa[d]; pp[3 + d] = aya[d]; pp[192 + d] = axb[d]; pp[195 + d] = ayb[d]; }
+              for (int d = 0; d < 3; ++d) { pp[d] = axa[d]; pp[3 + d] = aya[d]; }
+              if (POL_ROWS == 2) for (int d = 0; d < 3; ++d) { pp[192 + d] = axb[d]; pp[195 + d] = ayb[d]; }
             }
             u += jb - ja;
           }
@@ -340,11 +345,12 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
               double axa[3] = {0, 0, 0}, aya[3] = {0, 0, 0}, axb[3] = {0, 0, 0}, ayb[3] = {0, 0, 0};
               for (int w2 = wf; w2 <= wl; ++w2) {
                 const double *pp = wk.part + ((size_t)(w2 * 2 + (b * ncent < w2 * Q ? 0 : 1)) * 64 + lane) * 6;
-                for (int d = 0; d < 3; ++d) { axa[d] += pp[d]; aya[d] += pp[3 + d]; axb[d] += pp[192 + d]; ayb[d] += pp[195 + d]; }
+                for (int d = 0; d < 3; ++d) { axa[d] += pp[d]; aya[d] += pp[3 + d]; }
+                if (POL_ROWS == 2) for (int d = 0; d < 3; ++d) { axb[d] += pp[192 + d]; ayb[d] += pp[195 + d]; }
               }
-              const int ca = (b << 6) + lane, cb = ca + 32;
+              const int ca = (b << POL_BSH) + lane, cb = ca + 32;
               if (ca < ncent) finish(ca, axa, aya);
-              if (cb < ncent) finish(cb, axb, ayb);
+              if (POL_ROWS == 2 && cb < ncent) finish(cb, axb, ayb);
             }
           }
         } else {
@@ -352,8 +358,8 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
           for (int c0 = 0; c0 < ncent; c0 += NT) {
             const int ca = c0 + tid;
             const bool acta = ca < ncent;
-            double ra[3] = {0, 0, 0}; int ma = -1;
-            if (acta) { ra[0] = wk.cent_pos[(size_t)ca * 3]; ra[1] = wk.cent_pos[(size_t)ca * 3 + 1]; ra[2] = wk.cent_pos[(size_t)ca * 3 + 2]; ma = wk.cent_mol[ca]; }
+            double ra[3] = {0, 0, 0}, ma = -1.0;
+            if (acta) { ra[0] = wk.cent_pos[(size_t)ca * 3]; ra[1] = wk.cent_pos[(size_t)ca * 3 + 1]; ra[2] = wk.cent_pos[(size_t)ca * 3 + 2]; ma = (double)wk.cent_mol[ca]; }
             double axa[3] = {0, 0, 0}, aya[3] = {0, 0, 0};
             for (int j0 = 0; j0 < ncent; j0 += POL_TILE) {
               __syncthreads();
@@ -364,8 +370,8 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
                   tt[0] = wk.cent_pos[(size_t)j * 3]; tt[1] = wk.cent_pos[(size_t)j * 3 + 1]; tt[2] = wk.cent_pos[(size_t)j * 3 + 2];
                   const double *vj = stt + (size_t)j * PST + 18;
                   for (int d = 0; d < 6; ++d) tt[3 + d] = vj[d];
-                  s_tmol[tl] = wk.cent_mol[j];
-                } else s_tmol[tl] = -2;
+                  tt[9] = (double)wk.cent_mol[j];
+                }
               }
               __syncthreads();
               const int jn = min(POL_TILE, ncent - j0);
@@ -375,7 +381,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
                   const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
                   const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
                   const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
-                  sweep_pair(ra, s_tmol[jj] == ma, tt, axa, aya);
+                  sweep_pair(ra, q4.y == ma, tt, axa, aya);
                 }
               }
             }
@@ -436,7 +442,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
 
     // ---- (d) contractions with the solute rows: y^T dD x - (x+y).dF
     // solute tables in shared memory: centres [npolc][21]: pos3 r1(3) G(9) x3 y3 ; sites [ndmac][46]: pos3 mom20 dma1(20) L3
-    double *s_c = sm + POL_TILE * 10, *s_s = s_c + (size_t)npolc * 21;
+    double *s_c = sm, *s_s = s_c + (size_t)npolc * 21;      // the sweep tile is dead here (every pass restages it)
     double acc = 0.0;
     const bool global = (p.flags & SLVGPU_GLOBAL) != 0;
     if (global) {

@@ -378,7 +378,8 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
   CK(cudaMemsetAsync(d_status, 0, (size_t)nframes * sizeof(int32_t), st));
   const size_t sm_el = (size_t)pl->ndmac * SOLROW * sizeof(double);
   const size_t sm_di = ((size_t)pl->npolc * DISP_SOLROW + (108 + 4) * DISP_TJ) * sizeof(double) + ((size_t)p.list_cap + 2) * sizeof(int);
-  const size_t sm_po = ((size_t)POL_TILE * 10 + (size_t)pl->npolc * 21 + (size_t)pl->ndmac * 46) * sizeof(double);
+  size_t sm_po = (size_t)POL_TILE * 10, sm_po_sol = (size_t)pl->npolc * 21 + (size_t)pl->ndmac * 46;   // tile; solute tables alias it
+  sm_po = (sm_po > sm_po_sol ? sm_po : sm_po_sol) * sizeof(double);
   const bool do_disp = (p.flags & SLVGPU_DISP) && p.ninst > 1, do_pol = (p.flags & SLVGPU_POL) && p.ninst > 1;
   const bool do_rep = (p.flags & SLVGPU_REP) && p.ninst > 1;
   if ((do_disp || do_rep) && !pl->side[0]) {
@@ -470,7 +471,7 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
           ++pl->last_launches;
           // integral kernels: grid.x covers the items of a class, grid.y the pairs of the type in groups of ppb (the
           // type's pair count lives on the device; groups past it leave at once)
-          const int ppb = pl->rep_ppb > 0 ? pl->rep_ppb : (npairs >= 8192 ? 32 : (npairs >= 2048 ? 16 : 8));
+          const int ppb = pl->rep_ppb > 0 ? pl->rep_ppb : (4);
           const unsigned gy = (unsigned)((npairs + ppb - 1) / ppb);
           for (size_t ti = 0; ti < pl->rep_types.size(); ++ti) {
             const int ty = pl->rep_types[ti];
