@@ -17,7 +17,8 @@ constexpr int ELECT_THREADS = 256;
 constexpr int SOLROW = 52;   // doubles per solute site in shared memory: pos3, smea20, sea20, cmea3, cea3 (+3 pad)
 
 __global__ void __launch_bounds__(ELECT_THREADS, 2)
-k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, FrameLists fl, double *__restrict__ out) {
+k_frame_elect(const DevPlan p, const double *__restrict__ coords /* first frame of this launch */, int frame0 /* its row in out */,
+              FrameLists fl, double *__restrict__ out) {
   extern __shared__ double sm[];
   double *s_sol = sm;                                   // [ndma_c][SOLROW]
   __shared__ double s_xf[16];                           // solute rot(9) transl(3) rms, centroid(3)
@@ -26,7 +27,7 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords, int frame0, Fr
   __shared__ int s_base;
 
   const int fi = blockIdx.x;                            // frame within chunk
-  const double *x = coords + (size_t)(frame0 + fi) * p.natoms_total * 3;
+  const double *x = coords + (size_t)fi * p.natoms_total * 3;
   const int *tm0 = tmeta(p, p.inst_type[0]);
   const int ndmac = tm0[SLVGPU_M_NDMA];
   const int a0c = p.inst_atom0[0], natc_md = p.inst_atom0[1] - a0c;

@@ -367,16 +367,28 @@ __global__ void k_status(const double *__restrict__ out, int *__restrict__ statu
   if (bad) status[f] |= SLVGPU_ST_NONFINITE;
 }
 
-extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64_t nframes, double *d_out,
-                                  int32_t *d_status, void *stream_) {
-  if (!pl || !d_coords || !d_out || !d_status) return fail(SLVGPU_EINVAL, "null argument");
-  if (nframes < 0) return fail(SLVGPU_EINVAL, "negative frame count");
-  cudaStream_t st = (cudaStream_t)stream_;
+// Stage 1 of a chunk: superimposition + electrostatics of `n` frames whose coordinates start at frame `cframe0` of
+// d_coords; results go to rows oframe0.. of d_out, the hand-over lists to slots lframe0.. of the chunk's lists.  The host
+// entry feeds a chunk slice by slice (each slice's copy hides behind the previous slice's kernel); coordinates are not
+// read again after this stage.
+static int launch_elect(slvgpu_plan *pl, const double *d_coords, int64_t cframe0, int64_t oframe0, int lframe0, int n, double *d_out,
+                        cudaStream_t st) {
   const DevPlan &p = pl->dp;
-  pl->last_launches = 0;
-  if (nframes == 0) return 0;
-  CK(cudaMemsetAsync(d_status, 0, (size_t)nframes * sizeof(int32_t), st));
   const size_t sm_el = (size_t)pl->ndmac * SOLROW * sizeof(double);
+  FrameLists fl = pl->fl;
+  fl.sol_xf += (size_t)lframe0 * 12; fl.nlist += lframe0;
+  fl.list_inst += (size_t)lframe0 * p.list_cap; fl.list_flag += (size_t)lframe0 * p.list_cap; fl.list_xf += (size_t)lframe0 * p.list_cap * 12;
+  ev_begin(pl, 0, st);
+  k_frame_elect<<<n, ELECT_THREADS, sm_el, st>>>(p, d_coords + (size_t)cframe0 * p.natoms_total * 3, (int)oframe0, fl, d_out);
+  ev_end(pl, st);
+  ++pl->last_launches;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Stage 2 of a chunk: everything that works from the hand-over lists of its nf frames (rows f0.. of d_out).
+static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32_t *d_status, cudaStream_t st) {
+  const DevPlan &p = pl->dp;
   const size_t sm_di = ((size_t)pl->npolc * DISP_SOLROW + (108 + 4) * DISP_TJ) * sizeof(double) + ((size_t)p.list_cap + 2) * sizeof(int);
   size_t sm_po = (size_t)POL_TILE * 10, sm_po_sol = (size_t)pl->npolc * 21 + (size_t)pl->ndmac * 46;   // tile; solute tables alias it
   sm_po = (sm_po > sm_po_sol ? sm_po : sm_po_sol) * sizeof(double);
@@ -397,12 +409,7 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
   // register file, at one CTA per SM it loses more than the side kernels gain, and the FP64 tensor-core instructions of
   // k_rep_pair share the FP64 pipe with k_pol's DFMAs (profiles/overlap_pol_ctas_r02.jsonl, profiles/dmma_mix_r02.json).
   const bool overlap = pl->overlap && do_pol && (do_disp || do_rep);
-  for (int64_t f0 = 0; f0 < nframes; f0 += pl->max_chunk) {
-    const int nf = (int)((nframes - f0) < pl->max_chunk ? (nframes - f0) : pl->max_chunk);
-    ev_begin(pl, 0, st);
-    k_frame_elect<<<nf, ELECT_THREADS, sm_el, st>>>(p, d_coords, (int)f0, pl->fl, d_out);
-    ev_end(pl, st);
-    ++pl->last_launches;
+  {
     if (overlap) {
       CK(cudaEventRecord(pl->ev_elect, st));
       CK(cudaStreamWaitEvent(pl->side[0], pl->ev_elect, 0));
@@ -513,6 +520,25 @@ extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64
       CK(cudaStreamWaitEvent(st, pl->ev_side[1], 0));
     }
   }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int slvgpu_eval_frames(slvgpu_plan *pl, const double *d_coords, int64_t nframes, double *d_out,
+                                  int32_t *d_status, void *stream_) {
+  if (!pl || !d_coords || !d_out || !d_status) return fail(SLVGPU_EINVAL, "null argument");
+  if (nframes < 0) return fail(SLVGPU_EINVAL, "negative frame count");
+  cudaStream_t st = (cudaStream_t)stream_;
+  pl->last_launches = 0;
+  if (nframes == 0) return 0;
+  CK(cudaMemsetAsync(d_status, 0, (size_t)nframes * sizeof(int32_t), st));
+  for (int64_t f0 = 0; f0 < nframes; f0 += pl->max_chunk) {
+    const int nf = (int)((nframes - f0) < pl->max_chunk ? (nframes - f0) : pl->max_chunk);
+    int rc = launch_elect(pl, d_coords, f0, f0, 0, nf, d_out, st);
+    if (rc) return rc;
+    rc = launch_rest(pl, f0, nf, d_out, d_status, st);
+    if (rc) return rc;
+  }
   k_status<<<(unsigned)((nframes + 255) / 256), 256, 0, st>>>(d_out, d_status, nframes);
   ++pl->last_launches;
   CK(cudaGetLastError());
@@ -538,16 +564,18 @@ static int eval_frames_host_any(slvgpu_plan *pl, const void *h_src, int elem, in
                                 int64_t nframes, double *h_out, int32_t *h_status) {
   const DevPlan &p = pl->dp;
   if (!pl->own_stream) CK(cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking));
-  // Device staging is bounded: two coordinate buffers of one slice each (double buffering), so trajectories far larger
-  // than device memory stream through; the result rows of the whole call stay on the device until the end.
-  // slice schedule: a first slice of ~16 MB of coordinates (its copy is the only one not hidden behind compute), then
-  // 8x that, then full-size slices so the persistent kernels keep a long queue
-  const int64_t slice = pl->max_chunk;
+  // Device staging is bounded: two coordinate buffers of one SLICE each (double buffering), so trajectories far larger
+  // than device memory stream through; the result rows of the whole call stay on the device until the end.  A chunk (up
+  // to max_chunk frames: the unit the persistent kernels and the exchange-repulsion batches work on) is fed slice by slice:
+  // copy -> (float32: gather + unit conversion) -> k_frame_elect, which is the only kernel that reads coordinates; the copy
+  // of a slice hides behind the previous slice's kernel.  Then the rest of the chunk's kernels run once over all its frames
+  // -- the step costs what the device-resident path costs plus the first slice's copy.
   const size_t src_frame_bytes = (size_t)natoms_src * 3 * elem;
-  int64_t first = (int64_t)(16.0e6 / (double)src_frame_bytes);
-  first = first < 32 ? 32 : (first > 1024 ? 1024 : first);
-  if (first > slice) first = slice;
   const size_t fstride = (size_t)p.natoms_total * 3;
+  int64_t slice = (int64_t)(48.0e6 / (double)src_frame_bytes);
+  slice = slice < 296 ? 296 : slice;
+  if (slice > pl->max_chunk) slice = pl->max_chunk;
+  int64_t first = slice / 4 < 64 ? (slice < 64 ? slice : 64) : slice / 4;     // a short first slice: its copy is the exposed one
   if (pl->stage_slice < slice) {
     for (int b = 0; b < 2; ++b) { if (pl->d_stage_coords2[b]) cudaFree(pl->d_stage_coords2[b]); pl->d_stage_coords2[b] = nullptr; }
     pl->stage_slice = 0;
@@ -574,31 +602,38 @@ static int eval_frames_host_any(slvgpu_plan *pl, const void *h_src, int elem, in
     if (!pl->d_idx) CK(cudaMalloc(&pl->d_idx, (size_t)p.natoms_total * sizeof(int32_t)));
     CK(cudaMemcpyAsync(pl->d_idx, h_idx, (size_t)p.natoms_total * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   }
-  int64_t launches = 0, f0 = 0;
-  for (int64_t c = 0; f0 < nframes; ++c) {
-    const int b = (int)(c & 1);
-    int64_t want = c == 0 ? first : (c == 1 ? 8 * first : slice);
-    if (want > slice) want = slice;
-    const int64_t n = (nframes - f0) < want ? (nframes - f0) : want;
-    if (c >= 2) CK(cudaStreamWaitEvent(pl->copy_stream, pl->copy_ev[2 + b], 0));      // buffer b has been consumed
-    void *dst = elem == 4 ? pl->d_stage_src[b] : (void *)pl->d_stage_coords2[b];
-    CK(cudaMemcpyAsync(dst, (const char *)h_src + (size_t)f0 * src_frame_bytes, (size_t)n * src_frame_bytes,
-                       cudaMemcpyHostToDevice, pl->copy_stream));
-    CK(cudaEventRecord(pl->copy_ev[b], pl->copy_stream));
-    CK(cudaStreamWaitEvent(st, pl->copy_ev[b], 0));
-    if (elem == 4) {
-      const int64_t work = n * (int64_t)fstride;
-      const unsigned grid = (unsigned)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
-      k_ingest_f32<<<grid, 256, 0, st>>>((const float *)pl->d_stage_src[b], h_idx ? pl->d_idx : nullptr, natoms_src, p.natoms_total, n,
-                                          scale, pl->d_stage_coords2[b]);
-      ++launches;
+  CK(cudaMemsetAsync(pl->d_stage_status, 0, (size_t)nframes * sizeof(int32_t), st));
+  int64_t launches = 0, c = 0;
+  pl->last_launches = 0;
+  for (int64_t f0 = 0; f0 < nframes; f0 += pl->max_chunk) {
+    const int nf = (int)((nframes - f0) < pl->max_chunk ? (nframes - f0) : pl->max_chunk);
+    for (int64_t s0 = 0; s0 < nf; ++c) {
+      const int b = (int)(c & 1);
+      const int64_t want = (f0 == 0 && s0 == 0) ? first : slice;
+      const int64_t n = (nf - s0) < want ? (nf - s0) : want;
+      if (c >= 2) CK(cudaStreamWaitEvent(pl->copy_stream, pl->copy_ev[2 + b], 0));      // buffer b has been consumed
+      void *dst = elem == 4 ? pl->d_stage_src[b] : (void *)pl->d_stage_coords2[b];
+      CK(cudaMemcpyAsync(dst, (const char *)h_src + (size_t)(f0 + s0) * src_frame_bytes, (size_t)n * src_frame_bytes,
+                         cudaMemcpyHostToDevice, pl->copy_stream));
+      CK(cudaEventRecord(pl->copy_ev[b], pl->copy_stream));
+      CK(cudaStreamWaitEvent(st, pl->copy_ev[b], 0));
+      if (elem == 4) {
+        const int64_t work = n * (int64_t)fstride;
+        const unsigned grid = (unsigned)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
+        k_ingest_f32<<<grid, 256, 0, st>>>((const float *)pl->d_stage_src[b], h_idx ? pl->d_idx : nullptr, natoms_src, p.natoms_total, n,
+                                            scale, pl->d_stage_coords2[b]);
+        ++launches;
+      }
+      int rc = launch_elect(pl, pl->d_stage_coords2[b], 0, f0 + s0, (int)s0, (int)n, pl->d_stage_out, st);
+      if (rc) return rc;
+      CK(cudaEventRecord(pl->copy_ev[2 + b], st));
+      s0 += n;
     }
-    int rc = slvgpu_eval_frames(pl, pl->d_stage_coords2[b], n, pl->d_stage_out + f0 * SLVGPU_NOUT, pl->d_stage_status + f0, st);
+    int rc = launch_rest(pl, f0, nf, pl->d_stage_out, pl->d_stage_status, st);
     if (rc) return rc;
-    CK(cudaEventRecord(pl->copy_ev[2 + b], st));
-    launches += pl->last_launches;
-    f0 += n;
   }
+  k_status<<<(unsigned)((nframes + 255) / 256), 256, 0, st>>>(pl->d_stage_out, pl->d_stage_status, nframes);
+  launches += pl->last_launches + 1;
   pl->last_launches = launches;
   CK(cudaMemcpyAsync(h_out, pl->d_stage_out, (size_t)nframes * SLVGPU_NOUT * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(h_status, pl->d_stage_status, (size_t)nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
