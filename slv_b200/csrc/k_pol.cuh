@@ -305,9 +305,11 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
             const int ca = (b << POL_BSH) + lane, cb = ca + 32;
             const bool acta = ca < ncent, actb = POL_ROWS == 2 && cb < ncent;
             const bool anyb = POL_ROWS == 2 && __any_sync(0xffffffffu, actb);
-            double ra[3] = {0, 0, 0}, rb[3] = {0, 0, 0}, ma = -1.0, mb = -1.0;      // molecule ids are small integers held as doubles
-            if (acta) { ra[0] = s_tile[ca * 10]; ra[1] = s_tile[ca * 10 + 1]; ra[2] = s_tile[ca * 10 + 2]; ma = s_tile[ca * 10 + 9]; }
-            if (actb) { rb[0] = s_tile[cb * 10]; rb[1] = s_tile[cb * 10 + 1]; rb[2] = s_tile[cb * 10 + 2]; mb = s_tile[cb * 10 + 9]; }
+            double ra[3] = {0, 0, 0}, rb[3] = {0, 0, 0};
+            int ma = -1, mb = -1;          // molecule ids: small integers held as doubles in the tile, compared through their high words
+                                           // (an integer compare: a double compare would take a slot of the FP64 pipe per pair)
+            if (acta) { ra[0] = s_tile[ca * 10]; ra[1] = s_tile[ca * 10 + 1]; ra[2] = s_tile[ca * 10 + 2]; ma = __double2hiint(s_tile[ca * 10 + 9]); }
+            if (actb) { rb[0] = s_tile[cb * 10]; rb[1] = s_tile[cb * 10 + 1]; rb[2] = s_tile[cb * 10 + 2]; mb = __double2hiint(s_tile[cb * 10 + 9]); }
             double axa[3] = {0, 0, 0}, aya[3] = {0, 0, 0}, axb[3] = {0, 0, 0}, ayb[3] = {0, 0, 0};
             if (anyb) {
 #pragma unroll 2
@@ -315,8 +317,9 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
                 const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
                 const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
                 const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
-                sweep_pair(ra, q4.y == ma, tt, axa, aya);
-                sweep_pair(rb, q4.y == mb, tt, axb, ayb);
+                const int mj = __double2hiint(q4.y);
+                sweep_pair(ra, mj == ma, tt, axa, aya);
+                sweep_pair(rb, mj == mb, tt, axb, ayb);
               }
             } else if (acta) {
 #pragma unroll 4
@@ -324,7 +327,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
                 const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
                 const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
                 const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
-                sweep_pair(ra, q4.y == ma, tt, axa, aya);
+                sweep_pair(ra, __double2hiint(q4.y) == ma, tt, axa, aya);
               }
             }
             if (ja == 0 && jb == ncent) {                       // the whole block: finish its rows here
@@ -358,8 +361,8 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
           for (int c0 = 0; c0 < ncent; c0 += NT) {
             const int ca = c0 + tid;
             const bool acta = ca < ncent;
-            double ra[3] = {0, 0, 0}, ma = -1.0;
-            if (acta) { ra[0] = wk.cent_pos[(size_t)ca * 3]; ra[1] = wk.cent_pos[(size_t)ca * 3 + 1]; ra[2] = wk.cent_pos[(size_t)ca * 3 + 2]; ma = (double)wk.cent_mol[ca]; }
+            double ra[3] = {0, 0, 0}; int ma = -1;
+            if (acta) { ra[0] = wk.cent_pos[(size_t)ca * 3]; ra[1] = wk.cent_pos[(size_t)ca * 3 + 1]; ra[2] = wk.cent_pos[(size_t)ca * 3 + 2]; ma = __double2hiint((double)wk.cent_mol[ca]); }
             double axa[3] = {0, 0, 0}, aya[3] = {0, 0, 0};
             for (int j0 = 0; j0 < ncent; j0 += POL_TILE) {
               __syncthreads();
@@ -381,7 +384,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
                   const double2 *t2 = reinterpret_cast<const double2 *>(s_tile + jj * 10);
                   const double2 q0 = t2[0], q1 = t2[1], q2 = t2[2], q3 = t2[3], q4 = t2[4];
                   const double tt[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
-                  sweep_pair(ra, q4.y == ma, tt, axa, aya);
+                  sweep_pair(ra, __double2hiint(q4.y) == ma, tt, axa, aya);
                 }
               }
             }

@@ -40,6 +40,9 @@ __host__ __device__ inline int gws_of(int natA, int natB) { return (natA * 6 + n
 __host__ __device__ inline size_t rep_ints_smem(int threads, int natA, int max_natB) {
   return ((size_t)(threads / 32) * 2 * gws_of(natA, max_natB) + (size_t)threads * REP_INT_SREC * 6) * sizeof(double);
 }
+#ifndef SLV_REP_INT_PBLOCKS
+#define SLV_REP_INT_PBLOCKS 4     // resident blocks per SM the p-shell classes are compiled for
+#endif
 #ifndef SLV_REP_INT_DBLOCKS
 #define SLV_REP_INT_DBLOCKS 3     // resident blocks per SM the d-shell classes of the integral kernel are compiled for
 #endif
@@ -327,7 +330,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 // shared-memory buffer with cp.async while the current pair is evaluated.  (One thread per (pair, item) paid the chain of
 // five dependent global loads for ~500 instructions of arithmetic.)
 template <int LA, int LB, int IA>
-__global__ void __launch_bounds__(REP_INT_THREADS, (LB == 2 || (LA == 2 && LB == 0)) ? SLV_REP_INT_DBLOCKS : (LA + LB == 0 ? 6 : 4))
+__global__ void __launch_bounds__(REP_INT_THREADS, (LB == 2 || (LA == 2 && LB == 0)) ? SLV_REP_INT_DBLOCKS : (LA + LB == 0 ? 6 : SLV_REP_INT_PBLOCKS))
 k_rep_ints(const DevPlan p, int type, int lo, int n_items, int ppb, RepPool rp) {
   extern __shared__ double s_geo[];                        // [warps][2][gws]
   constexpr int NA = IA < 0 ? cart_ncomp(LA) : 1, NB = cart_ncomp(LB);

@@ -1,5 +1,5 @@
 #!/bin/bash
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q -k "pol or golden or cluster or clash" 2>&1 | tail -3
 run() {
   cfg=$1; shift
   env "$@" python bench.py --config $cfg --only --no-cpu --steps 5 --warmup 3 2>/dev/null | python -c "
@@ -8,5 +8,3 @@ d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$*', $cfg, round
 }
 run 3 A=0
 run 2 A=0
-run 5 A=0
-run 4 A=0

@@ -7,5 +7,4 @@ d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$lib', $cfg, rou
 }
 for lib in build_variants/*.so; do
   run $PWD/$lib 3
-  run $PWD/$lib 2
 done
