@@ -297,10 +297,18 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
           // slot 1); after one barrier they are added in ascending warp order -- deterministic.
           const int warp = tid >> 5, lane = tid & 31, nwarp = NT >> 5;
           const int nb2 = (ncent + (1 << POL_BSH) - 1) >> POL_BSH;
-          const int W = nb2 * ncent, Q = (W + nwarp - 1) / nwarp;
-          const bool split = (Q % ncent) != 0;
-          const int u1 = min(W, (warp + 1) * Q);
-          for (int u = warp * Q; u < u1;) {
+          // cost-weighted ranges: a (block, column) unit costs 2 (two rows per lane) except in a last block whose second
+          // row half is empty (one-row loop, cost 1); positions in cost space are even, so they map back to whole units
+          const int nfull = nb2 - 1, ufull = nfull * ncent;
+          const int clast = (POL_ROWS == 2 && ncent - (nfull << POL_BSH) <= 32) ? 1 : 2;
+          const int F = 2 * ufull, W2 = F + clast * ncent;
+          int Qc = (W2 + nwarp - 1) / nwarp; Qc += Qc & 1;
+          auto unit_of = [&](int x) { x = min(x, W2); return x <= F ? x >> 1 : ufull + (x - F) / clast; };
+          auto warp_of = [&](int u) { return (u < ufull ? 2 * u : F + (u - ufull) * clast) / Qc; };
+          bool split = false;
+          for (int w2 = 1; w2 < nwarp; ++w2) split |= (unit_of(w2 * Qc) % ncent) != 0;
+          const int u1 = unit_of((warp + 1) * Qc);
+          for (int u = unit_of(warp * Qc); u < u1;) {
             const int b = u / ncent, ja = u - b * ncent, jb = min(ncent, ja + (u1 - u));
             const int ca = (b << POL_BSH) + lane, cb = ca + 32;
             const bool acta = ca < ncent, actb = POL_ROWS == 2 && cb < ncent;
@@ -343,11 +351,11 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
           if (split) {                                            // CTA-uniform
             __syncthreads();
             for (int b = warp; b < nb2; b += nwarp) {
-              const int wf = (b * ncent) / Q, wl = (b * ncent + ncent - 1) / Q;
+              const int wf = warp_of(b * ncent), wl = warp_of(b * ncent + ncent - 1);
               if (wf == wl) continue;                             // one warp had the whole block
               double axa[3] = {0, 0, 0}, aya[3] = {0, 0, 0}, axb[3] = {0, 0, 0}, ayb[3] = {0, 0, 0};
               for (int w2 = wf; w2 <= wl; ++w2) {
-                const double *pp = wk.part + ((size_t)(w2 * 2 + (b * ncent < w2 * Q ? 0 : 1)) * 64 + lane) * 6;
+                const double *pp = wk.part + ((size_t)(w2 * 2 + (b * ncent < unit_of(w2 * Qc) ? 0 : 1)) * 64 + lane) * 6;
                 for (int d = 0; d < 3; ++d) { axa[d] += pp[d]; aya[d] += pp[3 + d]; }
                 if (POL_ROWS == 2) for (int d = 0; d < 3; ++d) { axb[d] += pp[192 + d]; ayb[d] += pp[195 + d]; }
               }
