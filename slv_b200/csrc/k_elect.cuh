@@ -15,6 +15,10 @@ namespace slv {
 
 constexpr int ELECT_THREADS = 256;
 constexpr int SOLROW = 52;   // doubles per solute site in shared memory: pos3, smea20, sea20, cmea3, cea3 (+3 pad)
+// dynamic shared memory: solute rows, then per pass the transforms, unit offsets and types of blockDim.x instances
+inline size_t elect_smem(int ndmac) {
+  return ((size_t)ndmac * SOLROW + (size_t)ELECT_THREADS * 12) * sizeof(double) + (2 * (size_t)ELECT_THREADS + 2) * sizeof(int);
+}
 
 __global__ void __launch_bounds__(ELECT_THREADS, 2)
 k_frame_elect(const DevPlan p, const double *__restrict__ coords /* first frame of this launch */, int frame0 /* its row in out */,
@@ -23,7 +27,7 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords /* first frame 
   double *s_sol = sm;                                   // [ndma_c][SOLROW]
   __shared__ double s_xf[16];                           // solute rot(9) transl(3) rms, centroid(3)
   __shared__ double s_red[32];
-  __shared__ int s_cnt[ELECT_THREADS / 32 + 1];
+  __shared__ int s_cnt[ELECT_THREADS / 32 + 1], s_usum[ELECT_THREADS / 32 + 1];
   __shared__ int s_base;
 
   const int fi = blockIdx.x;                            // frame within chunk
@@ -84,9 +88,17 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords /* first frame 
   const int nsolv = p.ninst - 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+  // Two steps per pass of blockDim.x instances.  (1) One thread per instance: cut-off test, superimposition, hand-over
+  // list.  (2) The multipole sites of the pass's instances inside ccut form one flat list of (instance, site) units
+  // that all threads share evenly: fragment types with different site counts, instances outside the cut-off and a
+  // partly filled last pass would otherwise leave most lanes of a warp idle in the pair loop.
+  double *s_inst = s_sol + (size_t)ndmac * SOLROW;        // [blockDim.x][12]  rot, transl of the pass's instances
+  int *s_uoff = reinterpret_cast<int *>(s_inst + (size_t)blockDim.x * 12);   // [blockDim.x + 1] first unit of each instance
+  int *s_ityp = s_uoff + blockDim.x + 1;                  // [blockDim.x] fragment type
+  const bool do_el = (p.flags & SLVGPU_ELECT) && !global;
   for (int base = 0; base < nsolv; base += blockDim.x) {
     const int i = base + threadIdx.x + 1;                // instance index
-    int flag = 0;
+    int flag = 0, nd = 0;
     double rot[9], tr[3], rms = 0.0;
     if (i < p.ninst) {
       const int a0 = p.inst_atom0[i], nat = p.inst_atom0[i + 1] - a0;
@@ -98,7 +110,8 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords /* first frame 
       const double dx = cx - mx, dy = cy - my, dz = cz - mz;
       const double rr = sqrt(dx * dx + dy * dy + dz * dz);
       flag = (rr < p.ccut ? 4 : 0) | (rr < p.pcut ? 1 : 0) | (rr < p.ecut ? 2 : 0);
-      const int *tm = tmeta(p, p.inst_type[i]);
+      const int ty = p.inst_type[i];
+      const int *tm = tmeta(p, ty);
       const bool env = tm[SLVGPU_M_REMOVABLE] == 2;       // environment of eval_dma: no cut-off, electrostatics only
       if (env) flag = 4;
       if (global) flag = 5;                               // no cut-offs: every fragment is in the electrostatic and polarisation layers
@@ -106,41 +119,35 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords /* first frame 
         fit_instance(p, tm, xi, rot, tr, rms);
         if (flag & 4) {
           if (!env) { ++n_c; rms_sum += rms; rms_max = fmax(rms_max, rms); }
-          if ((p.flags & SLVGPU_ELECT) && !global) {
-            const int nd = tm[SLVGPU_M_NDMA];
-            const double *rd = p.dtab + tm[SLVGPU_M_O_RDMA], *mom = p.dtab + tm[SLVGPU_M_O_MOM];
-            for (int s = 0; s < nd; ++s) {
-              double rB[3], mB[20];
-              rot_vec(rot, rd + s * 3, rB);
-              rB[0] += tr[0]; rB[1] += tr[1]; rB[2] += tr[2];
-              rot_mom20(rot, mom + s * 20, mB);
-              for (int a = 0; a < ndmac; ++a) {
-                const double *row = s_sol + a * SOLROW;
-                double P[23];
-                pair_potentials(row, rB, mB, P);
-                double e1 = 0.0, e2 = 0.0;
+          if (do_el) {
+            nd = tm[SLVGPU_M_NDMA];
+            double *si = s_inst + (size_t)threadIdx.x * 12;
 #pragma unroll
-                for (int k = 0; k < 20; ++k) { e1 += row[3 + k] * P[k]; e2 += row[23 + k] * P[k]; }
-                const double c1 = row[43] * P[20] + row[44] * P[21] + row[45] * P[22];
-                const double c2 = row[46] * P[20] + row[47] * P[21] + row[48] * P[22];
-                if (env) { v_mea += e1; v_ea += e2; w_mea += c1; w_ea += c2; }
-                else { e_mea += e1; e_ea += e2; c_mea += c1; c_ea += c2; }
-              }
-            }
+            for (int d = 0; d < 9; ++d) si[d] = rot[d];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) si[9 + d] = tr[d];
+            s_ityp[threadIdx.x] = ty;
           }
         }
         if (flag & 1) ++n_p;
         if (flag & 2) ++n_e;
       }
     }
-    // ordered compaction of the instances the later kernels need (inside pcut or ecut)
+    // ordered compaction of the instances the later kernels need (inside pcut or ecut), and the exclusive scan of the
+    // site counts (both through one pass of warp scans)
     const int keep = (flag & 3) != 0;
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    int incl = nd;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
     if (lane == 0) s_cnt[warp] = __popc(bal);
+    if (lane == 31) s_usum[warp] = incl;
     __syncthreads();
-    int off = s_base;
-    for (int w = 0; w < warp; ++w) off += s_cnt[w];
+    int off = s_base, ubase = 0;
+    for (int w = 0; w < warp; ++w) { off += s_cnt[w]; ubase += s_usum[w]; }
     off += __popc(bal & ((1u << lane) - 1u));
+    s_uoff[threadIdx.x] = ubase + incl - nd;
+    if (threadIdx.x == blockDim.x - 1) s_uoff[blockDim.x] = ubase + incl;
     if (keep && off < p.list_cap) {
       const size_t e = (size_t)fi * p.list_cap + off;
       fl.list_inst[e] = i; fl.list_flag[e] = flag & 3;
@@ -155,6 +162,38 @@ k_frame_elect(const DevPlan p, const double *__restrict__ coords /* first frame 
       int tot = 0;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_cnt[w];
       s_base += tot;
+    }
+    if (do_el) {
+      const int nunit = s_uoff[blockDim.x];
+      for (int u = threadIdx.x; u < nunit; u += blockDim.x) {
+        int lo = 0, hi = blockDim.x;                     // owner: largest t with s_uoff[t] <= u (instances without sites share their successor's offset)
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_uoff[mid] <= u) lo = mid; else hi = mid; }
+        const int sidx = u - s_uoff[lo];
+        const int *tm = tmeta(p, s_ityp[lo]);
+        const bool env = tm[SLVGPU_M_REMOVABLE] == 2;
+        const double *si = s_inst + (size_t)lo * 12;
+        double R[9];
+#pragma unroll
+        for (int d = 0; d < 9; ++d) R[d] = si[d];
+        double rB[3], mB[20];
+        rot_vec(R, p.dtab + tm[SLVGPU_M_O_RDMA] + sidx * 3, rB);
+        rB[0] += si[9]; rB[1] += si[10]; rB[2] += si[11];
+        rot_mom20(R, p.dtab + tm[SLVGPU_M_O_MOM] + sidx * 20, mB);
+        double e1s = 0.0, e2s = 0.0, c1s = 0.0, c2s = 0.0;
+        for (int a = 0; a < ndmac; ++a) {
+          const double *row = s_sol + a * SOLROW;
+          double P[23];
+          pair_potentials(row, rB, mB, P);
+          double e1 = 0.0, e2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < 20; ++k) { e1 += row[3 + k] * P[k]; e2 += row[23 + k] * P[k]; }
+          e1s += e1; e2s += e2;
+          c1s += row[43] * P[20] + row[44] * P[21] + row[45] * P[22];
+          c2s += row[46] * P[20] + row[47] * P[21] + row[48] * P[22];
+        }
+        if (env) { v_mea += e1s; v_ea += e2s; w_mea += c1s; w_ea += c2s; }
+        else { e_mea += e1s; e_ea += e2s; c_mea += c1s; c_ea += c2s; }
+      }
     }
     __syncthreads();
   }

@@ -374,7 +374,7 @@ __global__ void k_status(const double *__restrict__ out, int *__restrict__ statu
 static int launch_elect(slvgpu_plan *pl, const double *d_coords, int64_t cframe0, int64_t oframe0, int lframe0, int n, double *d_out,
                         cudaStream_t st) {
   const DevPlan &p = pl->dp;
-  const size_t sm_el = (size_t)pl->ndmac * SOLROW * sizeof(double);
+  const size_t sm_el = elect_smem(pl->ndmac);
   FrameLists fl = pl->fl;
   fl.sol_xf += (size_t)lframe0 * 12; fl.nlist += lframe0;
   fl.list_inst += (size_t)lframe0 * p.list_cap; fl.list_flag += (size_t)lframe0 * p.list_cap; fl.list_xf += (size_t)lframe0 * p.list_cap * 12;
