@@ -474,7 +474,7 @@ def run_config(cfg, a, steps, warmup, world, rank, dev, with_cpu, sampler=None):
         tr, trs = ncu_traffic('k_pol', cfg)
         rec['roofline'] = dict(bound='fp64', kernel='k_pol', achieved=ach, peak=peak, unit='TFLOP/s', frac=ach / peak,
                                traffic=(tr * nf if tr else None), traffic_source=trs, peak_source=peak_src,
-                               ceiling=dict(achieved_by='tools/sweep_peak.cu: the sweep body alone (no solver phases) at the kernel launch shape',
+                               ceiling=dict(achieved_by='tools/sweep_peak.cu: the sweep body alone (resident tile, no solver phases), two 256-thread CTAs per SM',
                                             alg_tflops=SWEEP_BODY_TFLOPS, frac_of_ceiling=ach / SWEEP_BODY_TFLOPS),
                                flops_per_step=pol_flops, ms_per_step=kms['k_pol'], share_of_step=kms['k_pol'] / step_ms)
     ndma_c = int(bsm[0].get()['ndma'])

@@ -1,20 +1,33 @@
 #!/bin/bash
-# Round-2 closing measurements on one B200 (run through gpurun from the repo root; outputs under gpurun_out/).
+# Round-2 closing measurements on one B200 (run through gpurun from the repo root; outputs under gpurun_out/, at most
+# 64 MiB per call come back: the three parts run as separate gpurun calls).   usage: tools/final_gpu_r02.sh prof|lists|bench
+T=${TAG:-r02b}
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02_final.json 2> gpurun_out/bench_r02_final.err
-tail -c 600 gpurun_out/bench_r02_final.json
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r02_final_reference.json 2>/dev/null
-cat gpurun_out/bench_r02_final_reference.json | cut -c1-300
-python bench.py --config 4 --only --steps 5 --warmup 3 > gpurun_out/bench_r02_final_config4.json 2>/dev/null
-for c in 3 2 5; do
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_r02_config$c.csv \
-      python bench.py --config $c --only --no-cpu --frames 2000 --steps 2 --warmup 3 > gpurun_out/ncu_launch_$c.log 2>&1
-  python tools/launch_summary.py gpurun_out/launches_r02_config$c.csv > gpurun_out/launches_r02_config${c}_summary.txt
-  head -8 gpurun_out/launches_r02_config${c}_summary.txt
-done
-ncu --set full --import-source on --clock-control none -k regex:k_pol -s 3 -c 1 -f -o gpurun_out/k_pol_r02 \
-    python bench.py --config 2 --only --no-cpu --frames 1184 --steps 1 --warmup 3 > gpurun_out/ncu_pol.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:"k_rep_pair|k_frame_elect|k_disp" -s 12 -c 6 -f -o gpurun_out/k_rep_pair_r02 \
-    python bench.py --config 3 --only --no-cpu --frames 1000 --steps 1 --warmup 3 > gpurun_out/ncu_rep.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+case "$1" in
+prof)   # ncu --set full of the dominant kernel on the headline workload and on config 2, and of the other per-frame kernels
+  ncu --set full --import-source on --clock-control none -k regex:k_pol -s 3 -c 1 -f -o gpurun_out/k_pol_${T}_c3 \
+      python bench.py --config 3 --only --no-cpu --frames 2220 --steps 1 --warmup 3 > gpurun_out/ncu_pol3.log 2>&1
+  ncu --set full --import-source on --clock-control none -k regex:k_pol -s 3 -c 1 -f -o gpurun_out/k_pol_${T}_c2 \
+      python bench.py --config 2 --only --no-cpu --frames 2220 --steps 1 --warmup 3 > gpurun_out/ncu_pol2.log 2>&1
+  ncu --set full --import-source on --clock-control none -k regex:"k_rep_pair|k_frame_elect|k_disp" -s 8 -c 4 -f -o gpurun_out/k_others_${T} \
+      python bench.py --config 3 --only --no-cpu --frames 1000 --steps 1 --warmup 3 > gpurun_out/ncu_others.log 2>&1
+  ls -la gpurun_out/*${T}*.ncu-rep ;;
+lists)  # the integral kernels of one batch (no source: size), then the launch lists of the bench command
+  ncu --set full --clock-control none -k regex:k_rep_ints -s 0 -c 46 -f -o gpurun_out/k_rep_ints_${T} \
+      python bench.py --config 3 --only --no-cpu --frames 1000 --steps 1 --warmup 3 > gpurun_out/ncu_ints.log 2>&1
+  ls -la gpurun_out/*${T}*.ncu-rep
+  for c in 3 2; do
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_${T}_config$c.csv \
+        python bench.py --config $c --only --no-cpu --frames 2000 --steps 1 --warmup 3 > gpurun_out/ncu_launch_$c.log 2>&1
+    python tools/launch_summary.py gpurun_out/launches_${T}_config$c.csv > gpurun_out/launches_${T}_config${c}_summary.txt
+    head -8 gpurun_out/launches_${T}_config${c}_summary.txt
+  done ;;
+bench)
+  python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+  python bench.py --steps 20 --warmup 5 > gpurun_out/bench_${T}.json 2> gpurun_out/bench_${T}.err
+  tail -c 600 gpurun_out/bench_${T}.json
+  python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_${T}_reference.json 2>/dev/null
+  cut -c1-300 gpurun_out/bench_${T}_reference.json
+  python bench.py --config 4 --only --steps 5 --warmup 3 > gpurun_out/bench_${T}_config4.json 2>/dev/null
+  cut -c1-300 gpurun_out/bench_${T}_config4.json ;;
+esac

@@ -1,5 +1,5 @@
 #!/bin/bash
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q -k "dis or golden or cluster or full or smoke or protein" 2>&1 | tail -3
 run() {
   cfg=$1; shift
   env "$@" python bench.py --config $cfg --only --no-cpu --steps 5 --warmup 3 2>/dev/null | python -c "
@@ -7,6 +7,4 @@ import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$*', $cfg, round(d['value']), round(d['e2e']['value']), d['e2e'].get('rows_identical_to_device_path'), {k: round(v,2) for k,v in d['detail']['kernel_ms_per_step'].items()}, d['detail']['status_max'], round(d['roofline']['frac'],4), round(d['roofline_elect']['frac'],3))"
 }
 run 3 A=0
-run 2 A=0
 run 5 A=0
-run 4 A=0
