@@ -26,7 +26,6 @@ namespace slv {
 #endif
 constexpr int POL_THREADS = SLV_POL_THREADS;
 constexpr int POL_CTAS_PER_SM = SLV_POL_CTAS_PER_SM;
-constexpr int POL_CTAS_SHARED_PER_SM = 2;   // k_pol CTAs per SM while dispersion / exchange-repulsion kernels run beside it
 #ifndef SLV_POL_TILE
 #define SLV_POL_TILE 768
 #endif

@@ -79,14 +79,15 @@ struct RepLimits { size_t max_pairs = 0; };
 
 inline int rep_alloc(RepPool rp[2], RepLimits &lim, std::vector<void *> &allocs, std::string &err, int nmosc, int nbasc,
                      int natc, int max_nbas, int max_nat, int max_chunk, int list_cap, int ntypes) {
-  // integral pools: together up to 8 GiB and at most a quarter of the free memory, never more than the worst case
+  // integral pools: together up to 24 GiB (SLVGPU_REP_POOL_GIB) and at most a quarter of the free memory, never more than the worst case
   const int nbsA16 = (nbasc + 15) & ~15, IP = REP_IP;
   (void)nmosc;
   const size_t sV = (size_t)nbsA16 * 4 * rep_lp(max_nbas);
   const size_t sCA = (size_t)(nbsA16 / 8) * 2 * IP * REP_CS;
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
-  size_t budget = (size_t)8 << 30;
+  size_t budget = (size_t)24 << 30;
+  if (const char *ev = getenv("SLVGPU_REP_POOL_GIB")) { const long v = atol(ev); if (v > 0 && v <= 128) budget = (size_t)v << 30; }
   if (budget > free_b / 4) budget = free_b / 4;
   size_t cap = budget / 2 / (sV * sizeof(double));
   const size_t want = (size_t)max_chunk * (size_t)list_cap;

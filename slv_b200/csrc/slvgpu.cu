@@ -38,16 +38,16 @@ struct slvgpu_plan {
   PolWork pw{};
   RepPool rp[2] = {};
   RepLimits rep_lim;
-  cudaStream_t side[2] = {nullptr, nullptr};  // plan-owned streams: dispersion and exchange repulsion run beside k_pol
-  cudaEvent_t ev_elect = nullptr, ev_side[2] = {nullptr, nullptr}, ev_pol = nullptr;
+  cudaStream_t side = nullptr;                // plan-owned stream: every second exchange-repulsion batch runs on it
+  cudaStream_t fan[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // per batch stream: extra streams the integral classes fan out over
+  cudaEvent_t ev_side = nullptr, ev_fork[2] = {nullptr, nullptr}, ev_join[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  int rep_fan = -1;                           // extra streams per batch the integral kernels use (SLVGPU_REP_FAN, 0..2; -1: by type count)
   std::vector<int> rep_types;                 // fragment types that carry the wave-function tables
   std::vector<std::vector<int>> rep_cls;      // per such type: the 24 class offsets of its integral work list
   std::vector<RepSmem> rep_sm;                // per such type: shared-memory plan of k_rep_pair
   std::vector<int> h_pair0;
-  int pol_ctas_shared = 0;                    // k_pol grid when other kernels share the SMs with it
   double *d_glob_sites = nullptr; int glob_ctas = 0;   // energy mode: per-CTA site tables of k_global_elect
   int rep_ppb = 0, rep_bt = 128;              // integral kernels: pairs per block (0 = by batch size) and block size (testing knobs)
-  int overlap = 0;                            // SLVGPU_OVERLAP=1: dispersion / exchange repulsion beside k_pol (experimental)
   double *d_detail = nullptr;
   int *d_queue = nullptr;
   int detail_frames = 0;
@@ -135,9 +135,12 @@ extern "C" void slvgpu_plan_destroy(slvgpu_plan *pl) {
   if (pl->d_stage_status) cudaFree(pl->d_stage_status);
   if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
   if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
-  for (int b = 0; b < 2; ++b) { if (pl->side[b]) cudaStreamDestroy(pl->side[b]); if (pl->ev_side[b]) cudaEventDestroy(pl->ev_side[b]); }
-  if (pl->ev_elect) cudaEventDestroy(pl->ev_elect);
-  if (pl->ev_pol) cudaEventDestroy(pl->ev_pol);
+  if (pl->side) cudaStreamDestroy(pl->side);
+  if (pl->ev_side) cudaEventDestroy(pl->ev_side);
+  for (int b = 0; b < 2; ++b) {
+    if (pl->ev_fork[b]) cudaEventDestroy(pl->ev_fork[b]);
+    for (int k = 0; k < 2; ++k) { if (pl->fan[b][k]) cudaStreamDestroy(pl->fan[b][k]); if (pl->ev_join[b][k]) cudaEventDestroy(pl->ev_join[b][k]); }
+  }
   for (cudaEvent_t e : pl->copy_ev) cudaEventDestroy(e);
   delete pl;
 }
@@ -345,13 +348,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
 #define X(ID, LA, LB, IA) cudaFuncSetAttribute(k_rep_ints<LA, LB, IA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   SLV_SUBSHELL_CLASSES(X)
 #undef X
-  // With dispersion or exchange repulsion in the plan, k_pol leaves part of every SM to their kernels (they run on the
-  // plan's side streams at the same time); SLVGPU_POL_CTAS overrides the grid for experiments.
-  pl->pol_ctas_shared = pl->pol_ctas;
-  if (d->flags & (SLVGPU_REP | SLVGPU_DISP)) pl->pol_ctas_shared = pl->sm_count * POL_CTAS_SHARED_PER_SM;
-  if (const char *ev = getenv("SLVGPU_POL_CTAS")) { const int v = atoi(ev); if (v > 0) pl->pol_ctas_shared = v; }
-  if (pl->pol_ctas_shared > pl->pol_ctas) pl->pol_ctas_shared = pl->pol_ctas;     // the workspace is sized for pol_ctas CTAs
-  if (const char *ev = getenv("SLVGPU_OVERLAP")) pl->overlap = atoi(ev) != 0;
+  if (const char *ev = getenv("SLVGPU_REP_FAN")) { const int v = atoi(ev); if (v >= 0 && v <= 2) pl->rep_fan = v; }
   if (const char *ev = getenv("SLVGPU_REP_PPB")) { const int v = atoi(ev); if (v >= 1 && v <= 32) pl->rep_ppb = v; }
   if (const char *ev = getenv("SLVGPU_REP_BT")) { const int v = atoi(ev); if (v == 32 || v == 64 || v == 128) pl->rep_bt = v; }
   *out = pl;
@@ -394,27 +391,24 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
   sm_po = (sm_po > sm_po_sol ? sm_po : sm_po_sol) * sizeof(double);
   const bool do_disp = (p.flags & SLVGPU_DISP) && p.ninst > 1, do_pol = (p.flags & SLVGPU_POL) && p.ninst > 1;
   const bool do_rep = (p.flags & SLVGPU_REP) && p.ninst > 1;
-  if ((do_disp || do_rep) && !pl->side[0]) {
+  if (do_rep && !pl->side) {
+    CK(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&pl->ev_side, cudaEventDisableTiming));
     for (int b = 0; b < 2; ++b) {
-      CK(cudaStreamCreateWithFlags(&pl->side[b], cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&pl->ev_side[b], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&pl->ev_fork[b], cudaEventDisableTiming));
+      for (int k = 0; k < 2; ++k) {
+        CK(cudaStreamCreateWithFlags(&pl->fan[b][k], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&pl->ev_join[b][k], cudaEventDisableTiming));
+      }
     }
-    CK(cudaEventCreateWithFlags(&pl->ev_elect, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&pl->ev_pol, cudaEventDisableTiming));
   }
-  // Schedule of a chunk.  Default: k_frame_elect, k_disp, k_pol on the caller's stream, then the exchange-repulsion
-  // batches alternating between it and a plan-owned stream (two integral pools, so the integral kernels of one batch run
-  // beside the transform kernel of the other).  With SLVGPU_OVERLAP=1 dispersion and exchange repulsion run on the two
-  // side streams at the same time as k_pol -- measured and not the default: k_pol at two CTAs per SM holds the whole
-  // register file, at one CTA per SM it loses more than the side kernels gain, and the FP64 tensor-core instructions of
-  // k_rep_pair share the FP64 pipe with k_pol's DFMAs (profiles/overlap_pol_ctas_r02.jsonl, profiles/dmma_mix_r02.json).
-  const bool overlap = pl->overlap && do_pol && (do_disp || do_rep);
+  // Schedule of a chunk: k_disp and k_pol on the caller's stream, then the exchange-repulsion batches alternating between
+  // it and a plan-owned stream (two integral pools: the integral kernels of one batch run beside the transform kernel of
+  // the other), the integral classes of a batch fanned out over two more streams each (their grids are small: the tail of
+  // one class fills with the next).  Running dispersion / exchange repulsion BESIDE k_pol was measured and dropped: k_pol
+  // holds the whole register file of every SM, and with fewer CTAs it loses more than the side kernels gain
+  // (profiles/overlap_pol_ctas_r02.jsonl); FP64 tensor-core and DFMA instructions share one pipe (profiles/dmma_mix_r02.json).
   {
-    if (overlap) {
-      CK(cudaEventRecord(pl->ev_elect, st));
-      CK(cudaStreamWaitEvent(pl->side[0], pl->ev_elect, 0));
-      CK(cudaStreamWaitEvent(pl->side[1], pl->ev_elect, 0));
-    }
     if ((p.flags & SLVGPU_GLOBAL) && (p.flags & SLVGPU_ELECT) && p.ninst > 1) {
       const int g = nf < pl->glob_ctas ? nf : pl->glob_ctas;
       ev_begin(pl, 1, st);
@@ -422,16 +416,14 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
       ev_end(pl, st);
       ++pl->last_launches;
     }
-    cudaStream_t s_disp = overlap ? pl->side[0] : st;
     if (do_disp) {
-      ev_begin(pl, 1, s_disp);
-      k_disp<<<nf, DISP_THREADS, sm_di, s_disp>>>(p, (int)f0, pl->fl, d_out);
-      ev_end(pl, s_disp);
+      ev_begin(pl, 1, st);
+      k_disp<<<nf, DISP_THREADS, sm_di, st>>>(p, (int)f0, pl->fl, d_out);
+      ev_end(pl, st);
       ++pl->last_launches;
     }
     if (do_pol) {
-      const int cap = overlap ? pl->pol_ctas_shared : pl->pol_ctas;
-      const int g = nf < cap ? nf : cap;
+      const int g = nf < pl->pol_ctas ? nf : pl->pol_ctas;
       ev_begin(pl, 2, st);
       CK(cudaMemsetAsync(pl->d_queue, 0, sizeof(int), st));
       k_pol<<<g, POL_THREADS, sm_po, st>>>(p, (int)f0, nf, pl->fl, pl->pw, d_out, d_status, pl->d_detail, pl->d_queue);
@@ -441,7 +433,7 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
     if (do_rep) {
       // Exchange repulsion runs in batches of frames sized by the integral pool.  The batch boundaries need the
       // per-frame fragment counts on the host: one small copy and a stream synchronisation per chunk.
-      cudaStream_t s0 = overlap ? pl->side[1] : st, s1 = overlap ? pl->side[0] : pl->side[1];
+      cudaStream_t s0 = st, s1 = pl->side;
       ev_begin(pl, 3, s0);
       k_rep_scan<<<1, 1024, 0, s0>>>(d_out, (int)f0, nf, pl->rp[0].pair0);
       ++pl->last_launches;
@@ -480,19 +472,32 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
           // type's pair count lives on the device; groups past it leave at once)
           const int ppb = pl->rep_ppb > 0 ? pl->rep_ppb : (4);
           const unsigned gy = (unsigned)((npairs + ppb - 1) / ppb);
+          // many fragment types (protein side chains) mean many small launches per batch: those gain from the fan-out
+          // (config 4: 7.1 -> 5.7 ms), two big types do not (config 3: 37.0 -> 37.6 ms)
+          const int bi = batch & 1, nfan = pl->rep_fan >= 0 ? pl->rep_fan : (pl->rep_types.size() > 2 ? 2 : 0);
+          cudaStream_t fs3[3] = {sb, pl->fan[bi][0], pl->fan[bi][1]};
+          if (nfan > 0) {
+            CK(cudaEventRecord(pl->ev_fork[bi], sb));
+            for (int k = 0; k < nfan; ++k) CK(cudaStreamWaitEvent(pl->fan[bi][k], pl->ev_fork[bi], 0));
+          }
+          int turn = 0;
+          const size_t sm_geo = rep_ints_smem(pl->rep_bt, pl->natc, pl->max_nat);
           for (size_t ti = 0; ti < pl->rep_types.size(); ++ti) {
             const int ty = pl->rep_types[ti];
             const std::vector<int> &co = pl->rep_cls[ti];
-            const size_t sm_geo = rep_ints_smem(pl->rep_bt, pl->natc, pl->max_nat);
 #define X(ID, LA, LB, IA)                                                                                         \
             if (co[ID + 1] > co[ID]) {                                                                              \
               const int n_items = co[ID + 1] - co[ID];                                                              \
-              k_rep_ints<LA, LB, IA><<<dim3((unsigned)((n_items + pl->rep_bt - 1) / pl->rep_bt), gy), pl->rep_bt, sm_geo, sb>>>( \
-                  p, ty, co[ID], n_items, ppb, rp);                                                                 \
+              k_rep_ints<LA, LB, IA><<<dim3((unsigned)((n_items + pl->rep_bt - 1) / pl->rep_bt), gy), pl->rep_bt, sm_geo,  \
+                                       fs3[turn++ % (nfan + 1)]>>>(p, ty, co[ID], n_items, ppb, rp);                   \
               ++pl->last_launches;                                                                                  \
             }
             SLV_SUBSHELL_CLASSES(X)
 #undef X
+          }
+          for (int k = 0; k < nfan; ++k) {
+            CK(cudaEventRecord(pl->ev_join[bi][k], pl->fan[bi][k]));
+            CK(cudaStreamWaitEvent(sb, pl->ev_join[bi][k], 0));
           }
           for (size_t ti = 0; ti < pl->rep_types.size(); ++ti) {
             const int ty = pl->rep_types[ti];
@@ -508,16 +513,10 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
         fs = fe;
       }
       if (batch > 1) {                                          // the first stream closes the timing bracket after both finished
-        CK(cudaEventRecord(pl->ev_side[0], s1));
-        CK(cudaStreamWaitEvent(s0, pl->ev_side[0], 0));
+        CK(cudaEventRecord(pl->ev_side, s1));
+        CK(cudaStreamWaitEvent(s0, pl->ev_side, 0));
       }
       ev_end(pl, s0);
-    }
-    if (overlap) {                                              // join the side streams
-      CK(cudaEventRecord(pl->ev_side[0], pl->side[0]));
-      CK(cudaEventRecord(pl->ev_side[1], pl->side[1]));
-      CK(cudaStreamWaitEvent(st, pl->ev_side[0], 0));
-      CK(cudaStreamWaitEvent(st, pl->ev_side[1], 0));
     }
   }
   CK(cudaGetLastError());

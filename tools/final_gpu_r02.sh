@@ -12,13 +12,15 @@ prof)   # ncu --set full of the dominant kernel on the headline workload and on 
   ncu --set full --import-source on --clock-control none -k regex:"k_rep_pair|k_frame_elect|k_disp" -s 8 -c 4 -f -o gpurun_out/k_others_${T} \
       python bench.py --config 3 --only --no-cpu --frames 1000 --steps 1 --warmup 3 > gpurun_out/ncu_others.log 2>&1
   ls -la gpurun_out/*${T}*.ncu-rep ;;
-lists)  # the integral kernels of one batch (no source: size), then the launch lists of the bench command
-  ncu --set full --clock-control none -k regex:k_rep_ints -s 0 -c 46 -f -o gpurun_out/k_rep_ints_${T} \
+lists)  # the integral kernels of one batch and fragment type (no source, 23 launches: the reports of a call must stay under 64 MiB), k_frame_elect / k_disp, then the launch lists of the bench command
+  ncu --set full --clock-control none -k regex:k_rep_ints -s 23 -c 23 -f -o gpurun_out/k_rep_ints_${T} \
       python bench.py --config 3 --only --no-cpu --frames 1000 --steps 1 --warmup 3 > gpurun_out/ncu_ints.log 2>&1
+  ncu --set full --import-source on --clock-control none -k regex:"k_frame_elect|k_disp" -s 4 -c 2 -f -o gpurun_out/k_elect_disp_${T} \
+      python bench.py --config 3 --only --no-cpu --frames 1000 --steps 1 --warmup 3 > gpurun_out/ncu_ed.log 2>&1
   ls -la gpurun_out/*${T}*.ncu-rep
   for c in 3 2; do
-    ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_${T}_config$c.csv \
-        python bench.py --config $c --only --no-cpu --frames 2000 --steps 1 --warmup 3 > gpurun_out/ncu_launch_$c.log 2>&1
+    ncu --metrics gpu__time_duration.sum --clock-control none -c $([ $c = 3 ] && echo 700 || echo 40) --csv --log-file gpurun_out/launches_${T}_config$c.csv \
+        python bench.py --config $c --only --no-cpu --steps 1 --warmup 3 > gpurun_out/ncu_launch_$c.log 2>&1
     python tools/launch_summary.py gpurun_out/launches_${T}_config$c.csv > gpurun_out/launches_${T}_config${c}_summary.txt
     head -8 gpurun_out/launches_${T}_config${c}_summary.txt
   done ;;
