@@ -573,6 +573,7 @@ static int eval_frames_host_any(slvgpu_plan *pl, const void *h_src, int elem, in
   const size_t fstride = (size_t)p.natoms_total * 3;
   int64_t slice = (int64_t)(48.0e6 / (double)src_frame_bytes);
   slice = slice < 296 ? 296 : slice;
+  if (const char *ev = getenv("SLVGPU_STAGE_SLICE")) { const long v = atol(ev); if (v > 0) slice = v; }   // testing knob: small slices
   if (slice > pl->max_chunk) slice = pl->max_chunk;
   int64_t first = slice / 4 < 64 ? (slice < 64 ? slice : 64) : slice / 4;     // a short first slice: its copy is the exposed one
   if (pl->stage_slice < slice) {

@@ -449,11 +449,12 @@ def test_full_solefp_batch_properties(frags):
     assert ru[0, 13] == ref['n_rep']
 
 
-@pytest.mark.parametrize('nw', [77, 130, 230])
+@pytest.mark.parametrize('nw', [77, 84, 130, 160, 230])
 def test_large_polarisation_system_multi_tile(frags, nw):
     """No pcut, polarisation and dispersion against the dense LU oracle: 77 waters -> 405 centres (7 row blocks cut
-    into 8 uneven warp ranges of the balanced sweep), 130 -> 670 (more row blocks than warps: ranges span blocks, head
-    and tail partial sums), 230 -> 1170 (NDIM 3510: more than the 1024-centre resident tile, tiled fallback)."""
+    into 8 uneven warp ranges of the balanced sweep; the last block has an empty second row half: cost-weighted ranges),
+    84 -> 440 (last block with both halves), 130 -> 670 (more row blocks than warps: ranges span blocks, head and tail
+    partial sums), 160 -> 820 and 230 -> 1170 (more than the 768-centre resident tile: tiled fallback)."""
     from slv_b200 import synth
     from oracle import solefp_oracle as O
     sol, wat = frags('nma'), frags('water')
@@ -512,9 +513,31 @@ def test_float32_ingest_is_bit_identical_to_float64_ingest(frags):
     r64, s64 = efp.eval_frames(x64)
     assert np.array_equal(r32, r64) and np.array_equal(s32, s64) and int(s32.max()) == 0
     assert np.abs(r32[:, :8]).max() > 0
-    efp.max_chunk = 8                                                # several slices through the double-buffered staging
+    efp.max_chunk = 8                                                # several chunks through the double-buffered staging
     r32b, _ = efp.eval_frames(rec32, scale=AngstromToBohr, idx=idx)
     assert np.array_equal(r32b, r64)
+
+
+def test_slice_fed_chunks_equal_the_device_path(frags, monkeypatch):
+    """The host entries feed a chunk slice by slice into k_frame_elect (hand-over lists at the slice's offset) and run the
+    list-driven kernels once per chunk: rows must equal the device-resident path bit for bit when a chunk takes several
+    slices, when the last slice of a chunk is short, and when the call takes several chunks."""
+    import torch
+    from slv_b200 import synth
+    sol, wat = frags('nma'), frags('water')
+    nw = 30
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos()], np.zeros(nw, int), 45, seed=72)
+    ind = [0] + [1] * nw; nmol = [12] + [3] * nw
+    monkeypatch.setenv('SLVGPU_STAGE_SLICE', '7')
+    efp = _efp(rep=True, ccut=30.0, pcut=14.0, ecut=11.0)
+    efp.max_chunk = 16                                               # chunks of 16 frames = slices of 7 (first: 4), 7, 2
+    rows_dev, st_dev = efp.eval_frames(torch.from_numpy(X).cuda(), ind, nmol, [sol, wat], [None, None], [None, None])
+    rows_dev = rows_dev.cpu().numpy()
+    rows_host, st_host = efp.eval_frames(X)
+    assert np.array_equal(rows_host, rows_dev) and int(st_host.max()) == 0
+    rows32, _ = efp.eval_frames(np.ascontiguousarray(X, np.float32), scale=1.0)
+    rows64, _ = efp.eval_frames(np.ascontiguousarray(X, np.float32).astype(np.float64))
+    assert np.array_equal(rows32, rows64)
 
 
 def test_mdrun_reads_xtc_like_the_same_coordinates_as_an_array(frags, golden, tmp_path):

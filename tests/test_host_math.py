@@ -151,3 +151,38 @@ def test_subshell_pair_integrals_match_oracle(L, frags, na, nb):
     assert np.isnan(Vp[:, len(bB):]).all()            # and nothing beyond the fragment's last basis function
     scale = np.abs(ref).max((0, 1))
     assert (np.abs(V - ref).max((0, 1)) < 1e-12 * np.maximum(scale, 1.0)).all(), np.abs(V - ref).max((0, 1))
+
+
+@pytest.mark.parametrize('na,nb', [('mescn', 'dmso'), ('nma', 'water')])
+def test_primitive_pair_records_are_a_sorted_screening_table(frags, na, nb):
+    """The plan's tables behind the integral kernels (slv_b200/plan.py primitive_pair_records): every work item points at
+    the records of its sub-shell pair; records carry (thr, mu, c_a c_b (pi/p)^1.5, 1/p, a, b), thresholds descend, and at
+    any distance the primitive pairs the screening rule a b AB^2 <= 46 (a + b) keeps are exactly a prefix of the list."""
+    from slv_b200.basis import BasisSet
+    from slv_b200.plan import subshell_work_list, primitive_pair_records, SUBSHELL_CLASSES, PP_REC
+    pa, pb = frags(na).get(), frags(nb).get()
+    bA, bB = BasisSet(pa['atno'], pa['pos']), BasisSet(pb['atno'], pb['pos'])
+    offs, items = subshell_work_list(bA.subshells, bB.subshells)
+    irec, ptab = primitive_pair_records(bA, bB, items)
+    assert irec.shape == (len(items), 8) and ptab.shape[1] == PP_REC == 6 and offs[-1] == len(items)
+    rng = np.random.default_rng(9)
+    nB = len(bB.subshells)
+    for ci, (LA, LB, IA) in enumerate(SUBSHELL_CLASSES):
+        for it in range(offs[ci], offs[ci + 1]):
+            a, b = items[it] // nB, items[it] % nB
+            sa, sb = bA.subshells[a], bB.subshells[b]
+            assert (sa[2], sb[2]) == (LA, LB)
+            assert tuple(irec[it, :4]) == (3 * sa[0], sa[1], 3 * sb[0], sb[1]) and irec[it, 5] == sa[3] * sb[3]
+            r = ptab[irec[it, 4]:irec[it, 4] + irec[it, 5]]
+            assert (np.diff(r[:, 0]) <= 0).all()
+            ea, eb = bA.exps[sa[1], :sa[3]], bB.exps[sb[1], :sb[3]]
+            ca, cb = bA.coefs[sa[1], :sa[3]], bB.coefs[sb[1], :sb[3]]
+            A, B = np.repeat(ea, sb[3]), np.tile(eb, sa[3])
+            want = np.stack([46.0 * (A + B) / (A * B), A * B / (A + B), np.repeat(ca, sb[3]) * np.tile(cb, sa[3]) * (np.pi / (A + B)) ** 1.5,
+                             1.0 / (A + B), A, B], 1)
+            o1, o2 = np.lexsort(r.T[::-1]), np.lexsort(want.T[::-1])
+            assert np.allclose(r[o1], want[o2], rtol=1e-15, atol=0)            # the same set of primitive pairs
+            for ab2 in rng.uniform(0.5, 200.0, 3):
+                keep = r[:, 4] * r[:, 5] * ab2 <= 46.0 * (r[:, 4] + r[:, 5])
+                n = int(keep.sum())
+                assert keep[:n].all() and not keep[n:].any()
