@@ -39,6 +39,9 @@ struct slvgpu_plan {
   RepPool rp[2] = {};
   RepLimits rep_lim;
   cudaStream_t side = nullptr;                // plan-owned stream: every second exchange-repulsion batch runs on it
+  cudaStream_t hp = nullptr, rep0 = nullptr;  // tail fill: k_pol on a high-priority stream, the other batches on a stream of their own
+  cudaEvent_t ev_a = nullptr, ev_pol = nullptr, ev_rep0 = nullptr;
+  int tailfill = 1;                           // SLVGPU_TAILFILL=0: k_pol and the first batch stream stay on the caller's stream
   cudaStream_t fan[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // per batch stream: extra streams the integral classes fan out over
   cudaEvent_t ev_side = nullptr, ev_fork[2] = {nullptr, nullptr}, ev_join[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   int rep_fan = -1;                           // extra streams per batch the integral kernels use (SLVGPU_REP_FAN, 0..2; -1: by type count)
@@ -136,7 +139,12 @@ extern "C" void slvgpu_plan_destroy(slvgpu_plan *pl) {
   if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
   if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
   if (pl->side) cudaStreamDestroy(pl->side);
+  if (pl->hp) cudaStreamDestroy(pl->hp);
+  if (pl->rep0) cudaStreamDestroy(pl->rep0);
   if (pl->ev_side) cudaEventDestroy(pl->ev_side);
+  if (pl->ev_a) cudaEventDestroy(pl->ev_a);
+  if (pl->ev_pol) cudaEventDestroy(pl->ev_pol);
+  if (pl->ev_rep0) cudaEventDestroy(pl->ev_rep0);
   for (int b = 0; b < 2; ++b) {
     if (pl->ev_fork[b]) cudaEventDestroy(pl->ev_fork[b]);
     for (int k = 0; k < 2; ++k) { if (pl->fan[b][k]) cudaStreamDestroy(pl->fan[b][k]); if (pl->ev_join[b][k]) cudaEventDestroy(pl->ev_join[b][k]); }
@@ -348,6 +356,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
 #define X(ID, LA, LB, IA) cudaFuncSetAttribute(k_rep_ints<LA, LB, IA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   SLV_SUBSHELL_CLASSES(X)
 #undef X
+  if (const char *ev = getenv("SLVGPU_TAILFILL")) pl->tailfill = atoi(ev) != 0;
   if (const char *ev = getenv("SLVGPU_REP_FAN")) { const int v = atoi(ev); if (v >= 0 && v <= 2) pl->rep_fan = v; }
   if (const char *ev = getenv("SLVGPU_REP_PPB")) { const int v = atoi(ev); if (v >= 1 && v <= 32) pl->rep_ppb = v; }
   if (const char *ev = getenv("SLVGPU_REP_BT")) { const int v = atoi(ev); if (v == 32 || v == 64 || v == 128) pl->rep_bt = v; }
@@ -394,6 +403,13 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
   if (do_rep && !pl->side) {
     CK(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&pl->ev_side, cudaEventDisableTiming));
+    int lo_pri = 0, hi_pri = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    CK(cudaStreamCreateWithPriority(&pl->hp, cudaStreamNonBlocking, hi_pri));
+    CK(cudaStreamCreateWithFlags(&pl->rep0, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&pl->ev_a, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&pl->ev_pol, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&pl->ev_rep0, cudaEventDisableTiming));
     for (int b = 0; b < 2; ++b) {
       CK(cudaEventCreateWithFlags(&pl->ev_fork[b], cudaEventDisableTiming));
       for (int k = 0; k < 2; ++k) {
@@ -409,6 +425,28 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
   // holds the whole register file of every SM, and with fewer CTAs it loses more than the side kernels gain
   // (profiles/overlap_pol_ctas_r02.jsonl); FP64 tensor-core and DFMA instructions share one pipe (profiles/dmma_mix_r02.json).
   {
+    // The exchange-repulsion batch boundaries need the per-frame fragment counts on the host: one small copy and one
+    // synchronisation of the caller's stream per chunk, taken here (k_frame_elect has written the counts) so that
+    // everything after it is enqueued without another host stall.
+    const bool tail = do_rep && do_pol && pl->tailfill;
+    cudaStream_t s0 = tail ? pl->rep0 : st, s1 = pl->side;
+    if (do_rep) {
+      k_rep_scan<<<1, 1024, 0, st>>>(d_out, (int)f0, nf, pl->rp[0].pair0);
+      ++pl->last_launches;
+      CK(cudaMemcpyAsync(pl->h_pair0.data(), pl->rp[0].pair0, ((size_t)nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      const int *pair0 = pl->h_pair0.data();
+      // pools sized for two concurrent batches covering the chunk, and for the largest single frame
+      int fmax = 0;
+      for (int f = 0; f < nf; ++f) fmax = pair0[f + 1] - pair0[f] > fmax ? pair0[f + 1] - pair0[f] : fmax;
+      size_t need = ((size_t)pair0[nf] + 1) / 2;
+      if (need < (size_t)fmax) need = (size_t)fmax;
+      if (need > (size_t)pl->rp[0].pair_cap && (size_t)pl->rp[0].pair_cap < pl->rep_lim.max_pairs) {
+        CK(cudaStreamSynchronize(s1)); CK(cudaStreamSynchronize(pl->rep0));     // nothing of an earlier chunk may still use the pools
+        const int rc = rep_reserve(pl->rp, pl->rep_lim, need, g_err);
+        if (rc) return rc;
+      }
+    }
     if ((p.flags & SLVGPU_GLOBAL) && (p.flags & SLVGPU_ELECT) && p.ninst > 1) {
       const int g = nf < pl->glob_ctas ? nf : pl->glob_ctas;
       ev_begin(pl, 1, st);
@@ -422,36 +460,34 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
       ev_end(pl, st);
       ++pl->last_launches;
     }
+    // Tail fill: k_pol's persistent CTAs hold every register of the SMs, so nothing runs beside them -- until the frame queue
+    // is empty and they retire one by one (the last ~2 ms of the launch).  With k_pol on a high-priority stream of the plan
+    // and the exchange-repulsion batches on streams that become runnable at the same moment, the integral kernels take the
+    // SMs as they fall idle instead of waiting for the last CTA.
+    cudaStream_t sp = tail ? pl->hp : st;
+    if (tail) {
+      CK(cudaEventRecord(pl->ev_a, st));
+      CK(cudaStreamWaitEvent(pl->hp, pl->ev_a, 0));
+      CK(cudaStreamWaitEvent(s0, pl->ev_a, 0));
+      CK(cudaStreamWaitEvent(s1, pl->ev_a, 0));
+    }
     if (do_pol) {
       const int g = nf < pl->pol_ctas ? nf : pl->pol_ctas;
-      ev_begin(pl, 2, st);
-      CK(cudaMemsetAsync(pl->d_queue, 0, sizeof(int), st));
-      k_pol<<<g, POL_THREADS, sm_po, st>>>(p, (int)f0, nf, pl->fl, pl->pw, d_out, d_status, pl->d_detail, pl->d_queue);
-      ev_end(pl, st);
+      ev_begin(pl, 2, sp);
+      CK(cudaMemsetAsync(pl->d_queue, 0, sizeof(int), sp));
+      k_pol<<<g, POL_THREADS, sm_po, sp>>>(p, (int)f0, nf, pl->fl, pl->pw, d_out, d_status, pl->d_detail, pl->d_queue);
+      ev_end(pl, sp);
       ++pl->last_launches;
     }
     if (do_rep) {
-      // Exchange repulsion runs in batches of frames sized by the integral pool.  The batch boundaries need the
-      // per-frame fragment counts on the host: one small copy and a stream synchronisation per chunk.
-      cudaStream_t s0 = st, s1 = pl->side;
-      ev_begin(pl, 3, s0);
-      k_rep_scan<<<1, 1024, 0, s0>>>(d_out, (int)f0, nf, pl->rp[0].pair0);
-      ++pl->last_launches;
-      CK(cudaMemcpyAsync(pl->h_pair0.data(), pl->rp[0].pair0, ((size_t)nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, s0));
-      CK(cudaStreamSynchronize(s0));                            // serial schedule: everything the batches read is complete from here on
-      const int *pair0 = pl->h_pair0.data();
-      {
-        // pools sized for two concurrent batches covering the chunk, and for the largest single frame
-        int fmax = 0;
-        for (int f = 0; f < nf; ++f) fmax = pair0[f + 1] - pair0[f] > fmax ? pair0[f + 1] - pair0[f] : fmax;
-        size_t need = ((size_t)pair0[nf] + 1) / 2;
-        if (need < (size_t)fmax) need = (size_t)fmax;
-        if (need > (size_t)pl->rp[0].pair_cap && (size_t)pl->rp[0].pair_cap < pl->rep_lim.max_pairs) {
-          CK(cudaStreamSynchronize(s1));                          // nothing of an earlier chunk may still use the pools
-          const int rc = rep_reserve(pl->rp, pl->rep_lim, need, g_err);
-          if (rc) { ev_end(pl, s0); return rc; }
-        }
+      ev_begin(pl, 3, sp);                                       // the bracket of the exchange repulsion opens where k_pol ends:
+                                                                 // it times what the step pays for it
+      if (!tail) {                                               // serial schedule: the second batch stream starts after k_pol too
+        CK(cudaEventRecord(pl->ev_a, st));
+        CK(cudaStreamWaitEvent(s1, pl->ev_a, 0));
       }
+      // Exchange repulsion runs in batches of frames sized by the integral pool.
+      const int *pair0 = pl->h_pair0.data();
       int batch = 0;
       for (int fs = 0; fs < nf; ++batch) {
         const RepPool &rp = pl->rp[batch & 1];
@@ -512,11 +548,17 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
         ++pl->last_launches;
         fs = fe;
       }
-      if (batch > 1) {                                          // the first stream closes the timing bracket after both finished
+      if (batch > 1) {                                          // the first batch stream waits for the second
         CK(cudaEventRecord(pl->ev_side, s1));
         CK(cudaStreamWaitEvent(s0, pl->ev_side, 0));
       }
-      ev_end(pl, s0);
+      if (tail) {                                               // the caller's stream joins k_pol and the batches
+        CK(cudaEventRecord(pl->ev_rep0, s0));
+        CK(cudaStreamWaitEvent(st, pl->ev_rep0, 0));
+        CK(cudaEventRecord(pl->ev_pol, pl->hp));
+        CK(cudaStreamWaitEvent(st, pl->ev_pol, 0));
+        ev_end(pl, st);
+      } else ev_end(pl, s0);
     }
   }
   CK(cudaGetLastError());
