@@ -298,7 +298,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
   TRY(dalloc(pl, &pl->fl.list_flag, ch * p.list_cap));
   TRY(dalloc(pl, &pl->fl.list_xf, ch * p.list_cap * 12));
   if (d->flags & SLVGPU_POL) {
-    pl->pol_ctas = pl->sm_count * POL_CTAS_PER_SM;    // two persistent 256-thread CTAs per SM: one frame each, their barrier phases interleave (4 x 128 measured: better
+    pl->pol_ctas = pl->sm_count * POL_CTAS_PER_SM;    // three persistent 256-thread CTAs per SM: one frame each, their barrier phases interleave (4 x 128 measured: better
     // for ~400 centres, worse at ~500 and a longer tail -- DESIGN.md)
     const size_t nc = (size_t)pl->pol_ctas, cc = (size_t)p.cent_cap;
     TRY(dalloc(pl, &pl->pw.cent_pos, nc * cc * 3));
@@ -374,9 +374,9 @@ __global__ void k_status(const double *__restrict__ out, int *__restrict__ statu
 }
 
 // Stage 1 of a chunk: superimposition + electrostatics of `n` frames whose coordinates start at frame `cframe0` of
-// d_coords; results go to rows oframe0.. of d_out, the hand-over lists to slots lframe0.. of the chunk's lists.  The host
-// entry feeds a chunk slice by slice (each slice's copy hides behind the previous slice's kernel); coordinates are not
-// read again after this stage.
+// d_coords, then their dispersion (per frame, from the hand-over lists just written); results go to rows oframe0.. of
+// d_out, the lists to slots lframe0.. of the chunk's lists.  The host entry feeds a chunk slice by slice (each slice's copy
+// hides behind the previous slice's two kernels); coordinates are not read again after k_frame_elect.
 static int launch_elect(slvgpu_plan *pl, const double *d_coords, int64_t cframe0, int64_t oframe0, int lframe0, int n, double *d_out,
                         cudaStream_t st) {
   const DevPlan &p = pl->dp;
@@ -388,6 +388,13 @@ static int launch_elect(slvgpu_plan *pl, const double *d_coords, int64_t cframe0
   k_frame_elect<<<n, ELECT_THREADS, sm_el, st>>>(p, d_coords + (size_t)cframe0 * p.natoms_total * 3, (int)oframe0, fl, d_out);
   ev_end(pl, st);
   ++pl->last_launches;
+  if ((p.flags & SLVGPU_DISP) && p.ninst > 1) {
+    const size_t sm_di = ((size_t)pl->npolc * DISP_SOLROW + (108 + 4) * DISP_TJ) * sizeof(double) + ((size_t)p.list_cap + 2) * sizeof(int);
+    ev_begin(pl, 1, st);
+    k_disp<<<n, DISP_THREADS, sm_di, st>>>(p, (int)oframe0, fl, d_out);
+    ev_end(pl, st);
+    ++pl->last_launches;
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -395,10 +402,9 @@ static int launch_elect(slvgpu_plan *pl, const double *d_coords, int64_t cframe0
 // Stage 2 of a chunk: everything that works from the hand-over lists of its nf frames (rows f0.. of d_out).
 static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32_t *d_status, cudaStream_t st) {
   const DevPlan &p = pl->dp;
-  const size_t sm_di = ((size_t)pl->npolc * DISP_SOLROW + (108 + 4) * DISP_TJ) * sizeof(double) + ((size_t)p.list_cap + 2) * sizeof(int);
   size_t sm_po = (size_t)POL_TILE * 10, sm_po_sol = (size_t)pl->npolc * 21 + (size_t)pl->ndmac * 46;   // tile; solute tables alias it
   sm_po = (sm_po > sm_po_sol ? sm_po : sm_po_sol) * sizeof(double);
-  const bool do_disp = (p.flags & SLVGPU_DISP) && p.ninst > 1, do_pol = (p.flags & SLVGPU_POL) && p.ninst > 1;
+  const bool do_pol = (p.flags & SLVGPU_POL) && p.ninst > 1;
   const bool do_rep = (p.flags & SLVGPU_REP) && p.ninst > 1;
   if (do_rep && !pl->side) {
     CK(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
@@ -451,12 +457,6 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
       const int g = nf < pl->glob_ctas ? nf : pl->glob_ctas;
       ev_begin(pl, 1, st);
       k_global_elect<<<g, GLOB_THREADS, 0, st>>>(p, (int)f0, nf, pl->fl, pl->d_glob_sites, d_out);
-      ev_end(pl, st);
-      ++pl->last_launches;
-    }
-    if (do_disp) {
-      ev_begin(pl, 1, st);
-      k_disp<<<nf, DISP_THREADS, sm_di, st>>>(p, (int)f0, pl->fl, d_out);
       ev_end(pl, st);
       ++pl->last_launches;
     }
@@ -613,11 +613,13 @@ static int eval_frames_host_any(slvgpu_plan *pl, const void *h_src, int elem, in
   // -- the step costs what the device-resident path costs plus the first slice's copy.
   const size_t src_frame_bytes = (size_t)natoms_src * 3 * elem;
   const size_t fstride = (size_t)p.natoms_total * 3;
-  int64_t slice = (int64_t)(48.0e6 / (double)src_frame_bytes);
-  slice = slice < 296 ? 296 : slice;
+  // slices are whole waves of the per-frame kernels (one CTA per frame, two CTAs per SM): a slice of 1.1 waves costs two
+  const int64_t wave = 2 * (int64_t)pl->sm_count;
+  int64_t slice = (int64_t)(48.0e6 / (double)src_frame_bytes) / wave * wave;
+  slice = slice < wave ? wave : slice;
   if (const char *ev = getenv("SLVGPU_STAGE_SLICE")) { const long v = atol(ev); if (v > 0) slice = v; }   // testing knob: small slices
   if (slice > pl->max_chunk) slice = pl->max_chunk;
-  int64_t first = slice / 4 < 64 ? (slice < 64 ? slice : 64) : slice / 4;     // a short first slice: its copy is the exposed one
+  const int64_t first = slice < wave / 2 ? slice : (slice < wave ? slice : wave / 2);     // a short first slice: its copy is the exposed one
   if (pl->stage_slice < slice) {
     for (int b = 0; b < 2; ++b) { if (pl->d_stage_coords2[b]) cudaFree(pl->d_stage_coords2[b]); pl->d_stage_coords2[b] = nullptr; }
     pl->stage_slice = 0;
