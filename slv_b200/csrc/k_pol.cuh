@@ -69,7 +69,7 @@ __device__ __forceinline__ void sweep_pair(const double rc[3], const bool same, 
 __global__ void __launch_bounds__(POL_THREADS, POL_CTAS_PER_SM)
 k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, double *__restrict__ out, int *__restrict__ status,
       double *__restrict__ detail /* optional [nframes][cent_cap][9]: dipind, flds, rpol */, int *__restrict__ queue) {
-  __shared__ double s_red[64];
+  __shared__ double s_red[64], s_redA[32], s_redB[64];   // A / B: the two reductions of a BiCG iteration (one barrier each)
   __shared__ int s_fi;
   __shared__ unsigned long long s_scan[POL_THREADS / 32];
   __shared__ int s_n[4];
@@ -398,7 +398,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
             if (acta) finish(ca, axa, aya);
           }
         }
-        pq = block_sum(pq, s_red);
+        pq = block_sum_1b(pq, s_redA);
         ++iters;
         if (!(fabs(pq) > 0.0) || !isfinite(pq)) { broke = true; break; }
         const double al = rho / pq;
@@ -413,7 +413,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
           }
         }
         double rho1 = prho, rmax = pr;
-        block_sum_max(rho1, rmax, s_red);
+        block_sum_max_1b(rho1, rmax, s_redB);
         resid = rmax / bnorm;
         if (!(resid > p.pol_tol)) break;
         if (!(fabs(rho) > 0.0) || !isfinite(rho1)) { broke = true; break; }

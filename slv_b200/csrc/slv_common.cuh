@@ -71,6 +71,28 @@ __device__ __forceinline__ double block_max(double v, double *scratch) {
   return r;
 }
 
+// Single-barrier variants for reductions that alternate between two scratch arrays inside a loop: the barrier that
+// protects `scratch` from the readers of its previous use is whatever barrier the caller has between the two uses
+// (k_pol's BiCG iteration: pq -> A, (rho, max) -> B, with the other reduction's barrier in between).
+__device__ __forceinline__ double block_sum_1b(double v, double *scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < nw; ++i) r += scratch[i];
+  return r;
+}
+__device__ __forceinline__ void block_sum_max_1b(double &s, double &m, double *scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  s = warp_sum(s); m = warp_max(m);
+  if (lane == 0) { scratch[w] = s; scratch[32 + w] = m; }
+  __syncthreads();
+  double rs = 0.0, rm = scratch[32];
+  for (int i = 0; i < nw; ++i) { rs += scratch[i]; rm = fmax(rm, scratch[32 + i]); }
+  s = rs; m = rm;
+}
+
 // one sum and one max in a single pass (two barriers); `scratch` must hold >= 64 doubles
 __device__ __forceinline__ void block_sum_max(double &s, double &m, double *scratch) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;

@@ -1,5 +1,5 @@
 #!/bin/bash
-python -m pytest tests -m gpu -x -q -k "slice or float32 or mdrun or full" 2>&1 | tail -2
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
 run() {
   cfg=$1; shift
   env "$@" python bench.py --config $cfg --only --no-cpu --steps 5 --warmup 3 2>/dev/null | python -c "
