@@ -331,7 +331,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 // shared-memory buffer with cp.async while the current pair is evaluated.  (One thread per (pair, item) paid the chain of
 // five dependent global loads for ~500 instructions of arithmetic.)
 template <int LA, int LB, int IA>
-__global__ void __launch_bounds__(REP_INT_THREADS, (LB == 2 || (LA == 2 && LB == 0)) ? SLV_REP_INT_DBLOCKS : (LA + LB == 0 ? 6 : SLV_REP_INT_PBLOCKS))
+__global__ void __launch_bounds__(REP_INT_THREADS, (LB == 2 || (LA == 2 && LB == 0)) ? SLV_REP_INT_DBLOCKS : (LA + LB == 0 ? 10 : SLV_REP_INT_PBLOCKS))
 k_rep_ints(const DevPlan p, int type, int lo, int n_items, int ppb, RepPool rp) {
   extern __shared__ double s_geo[];                        // [warps][2][gws]
   constexpr int NA = IA < 0 ? cart_ncomp(LA) : 1, NB = cart_ncomp(LB);

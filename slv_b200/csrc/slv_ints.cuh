@@ -93,7 +93,7 @@ struct AxisVals {
 // thread walks ITS survivors and stops at the first record whose threshold the distance exceeds -- no division, square
 // root or screening loop per evaluation.
 constexpr int PP_REC = 6;
-constexpr int PP_SREC = 4;    // leading records of an item the integral kernel keeps in shared memory
+constexpr int PP_SREC = 2;    // leading records of an item the integral kernel keeps in shared memory
 
 // acc[(ca * NB + cb) * 4 + q] += contributions of all primitive pairs; q = S, T, L.dS/dA, L.dT/dA.
 // ca = bra component slot (component index when IA < 0, else 0), cb = ket component.
@@ -115,8 +115,18 @@ SLV_HD void subshell_pair_t(const double A[3], const double B[3], const double L
     if (!(AB2 <= r[0])) break;
     {
       const double mu = r[st], pref0 = r[2 * st], ip = r[3 * st], a = r[4 * st], b = r[5 * st];
-      const double h = 0.5 * ip;
       const double pref = pref0 * exp(-mu * AB2);
+      if constexpr (LA == 0 && LB == 0) {
+        // s|s in closed form (a fifth of all items): S = pref, T = mu (3 - 2 mu AB^2) S, dS/dA = -2 mu (A - B) S,
+        // dT/dA = -2 mu (A - B) (T + 2 mu S) -- a dozen live values instead of the three 1-D tables, so twice as many
+        // warps fit an SM
+        const double LAB = L[0] * ABx + L[1] * ABy + L[2] * ABz;
+        const double T = mu * (3.0 - 2.0 * mu * AB2) * pref, g = -2.0 * mu * LAB;
+        acc[0] += pref; acc[1] += T; acc[2] += g * pref; acc[3] += g * (T + 2.0 * mu * pref);
+        (void)ip; (void)a; (void)b;
+        continue;
+      }
+      const double h = 0.5 * ip;
       const double fa = -b * ip, fb = a * ip;
       AxisVals<MX, LB, ALL> X; AxisVals<MY, LB, ALL> Y; AxisVals<MZ, LB, ALL> Z;
       X.build(fa * ABx, fb * ABx, h, a, b); X.scale(pref);       // every term below carries exactly one x factor
@@ -164,11 +174,19 @@ SLV_HD void subshell_pair_write(const double *acc, int f0a, int f0b, int LP, dou
       const int l = f0b + c2;
       const double f = cart_norm_ratio(LA, ka) * cart_norm_ratio(LB, c2);
       double *v = V + ((size_t)k * LP + l) * 4;                   // V[k][l][q], LP records per row
+      double x[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const double x = (f == 1.0) ? acc[(c1 * NB + c2) * 4 + q] : f * acc[(c1 * NB + c2) * 4 + q];
-        v[q] = (x - x == 0.0) ? x : 0.0;                            // non-finite -> 0: the pool is recycled and its cells are
+        const double y = (f == 1.0) ? acc[(c1 * NB + c2) * 4 + q] : f * acc[(c1 * NB + c2) * 4 + q];
+        x[q] = (y - y == 0.0) ? y : 0.0;                            // non-finite -> 0: the pool is recycled and its cells are
       }                                                             // read (times zero) by later batches
+#ifdef __CUDA_ARCH__
+      // one 256-bit store per record (a whole 32-byte sector): the stores of a warp go to 32 different sectors, four
+      // 64-bit stores per record quadrupled the requests the memory pipeline had to take
+      asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(v), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
+#else
+      v[0] = x[0]; v[1] = x[1]; v[2] = x[2]; v[3] = x[3];
+#endif
     }
   }
 }
