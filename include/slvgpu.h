@@ -91,6 +91,9 @@ enum {
                        * solute function, 3 * fragment atom, first fragment function, first record in O_PPTAB, records   */
   SLVGPU_M_O_PPTAB,   /* dtab (16-byte aligned): [records][6] primitive pairs of every (solute sub-shell, sub-shell) pair,
                        * thr = 46 (a+b)/(ab), mu, c_a c_b (pi/(a+b))^1.5, 1/(a+b), a, b; thr descending within a pair    */
+  SLVGPU_M_IO_BFBLK,  /* itab: [nbfblk][2] first function and angular momentum of every s / p / d block of the basis (the units
+                       * VECROT rotates the AO->LMO coefficient rows in)                                                  */
+  SLVGPU_M_NBFBLK,
   SLVGPU_NMETA = 32
 };
 

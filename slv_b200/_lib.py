@@ -20,7 +20,7 @@ OUT = dict(ele_mea=0, ele_ea=1, cor_mea=2, cor_ea=3, pol_mea=4, rep_mea=5, dis_m
            env_ele_mea=20, env_ele_ea=21, env_cor_mea=22, env_cor_ea=23)
 M = dict(NATOMS=0, NDMA=1, NPOL=2, NMOS=3, NBASIS=4, NSUPL=5, IO_SUPL=6, IO_REORD=7, O_POS=8, O_RDMA=9, O_MOM=10,
          O_RPOL=11, O_POL=12, O_POLINV=13, O_DPOLI=14, O_LMOC=15, O_FOCK=16, O_VECL=17, O_ZNUC=18, IO_BFC=19,
-         IO_BFL=20, IO_BFNP=21, O_BFEXP=22, O_BFCOEF=23, REMOVABLE=24, NSUBSH=25, IO_SUBSH=26, IO_SHPAIR=27, IO_SHITEM=28, O_PPTAB=29)
+         IO_BFL=20, IO_BFNP=21, O_BFEXP=22, O_BFCOEF=23, REMOVABLE=24, NSUBSH=25, IO_SUBSH=26, IO_SHPAIR=27, IO_SHITEM=28, O_PPTAB=29, IO_BFBLK=30, NBFBLK=31)
 S = dict(SMEA=0, SEA=1, CMEA=2, CEA=3, DPOLI1=4, LMOC1=5, DPOL1=6, LVEC=7, DMA1=8, FOCK1=9, VECL1=10)
 ST_NONFINITE, ST_POL_NOCONV, ST_SINGULAR, ST_OVERFLOW = 1, 2, 4, 8
 

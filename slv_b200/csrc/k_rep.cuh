@@ -217,15 +217,16 @@ __global__ void __launch_bounds__(1024) k_rep_scan(const double *__restrict__ ou
 // symmetric tensors; one thread per leading element of a block; element (i, k) goes to dst[index(i, k)]
 template <class Index>
 __device__ inline void rotate_vecl_rows(const DevPlan &p, const int *tm, const double *src, int nrows, const double R[9], double *dst, Index index) {
-  const int nb = tm[SLVGPU_M_NBASIS];
-  const int *bl = p.itab + tm[SLVGPU_M_IO_BFL];
-  for (int w = threadIdx.x; w < nrows * nb; w += blockDim.x) {
-    const int i = w / nb, k = w % nb;
-    const int lx = bl[k * 3], ly = bl[k * 3 + 1], lz = bl[k * 3 + 2], Ls = lx + ly + lz;
+  const int nb = tm[SLVGPU_M_NBASIS], nblk = tm[SLVGPU_M_NBFBLK];
+  const int2 *blk = reinterpret_cast<const int2 *>(p.itab + tm[SLVGPU_M_IO_BFBLK]);     // (first function, L) of every block
+  for (int w = threadIdx.x; w < nrows * nblk; w += blockDim.x) {
+    const int i = w / nblk;
+    const int2 bk = blk[w - i * nblk];
+    const int k = bk.x;
     const double *c = src + (size_t)i * nb + k;
-    if (Ls == 0) dst[index(i, k)] = c[0];
-    else if (Ls == 1 && lx == 1) { double v[3] = {c[0], c[1], c[2]}, o[3]; rot_vec(R, v, o); for (int t = 0; t < 3; ++t) dst[index(i, k + t)] = o[t]; }
-    else if (Ls == 2 && lx == 2) { double v[6] = {c[0], c[1], c[2], c[3], c[4], c[5]}, o[6]; rot_quad(R, v, o); for (int t = 0; t < 6; ++t) dst[index(i, k + t)] = o[t]; }
+    if (bk.y == 0) dst[index(i, k)] = c[0];
+    else if (bk.y == 1) { double v[3] = {c[0], c[1], c[2]}, o[3]; rot_vec(R, v, o); for (int t = 0; t < 3; ++t) dst[index(i, k + t)] = o[t]; }
+    else { double v[6] = {c[0], c[1], c[2], c[3], c[4], c[5]}, o[6]; rot_quad(R, v, o); for (int t = 0; t < 6; ++t) dst[index(i, k + t)] = o[t]; }
   }
 }
 
@@ -446,9 +447,10 @@ k_rep_pair(const DevPlan p, int type, FrameLists fl, RepPool rp, RepSmem L) {
     rot_vec(R, p.dtab + tm[SLVGPU_M_O_LMOC] + j * 3, y);
     riB[j * 3] = y[0] + tr[0]; riB[j * 3 + 1] = y[1] + tr[1]; riB[j * 3 + 2] = y[2] + tr[2];
   }
-  for (int w = tid; w < L.LK * JS; w += NT) CBs[w] = 0.0;
-  __syncthreads();
+  // pad rows / columns of the coefficient tile are zero; the rotation writes every other element (disjoint: no barrier)
+  for (int w = tid; w < L.LK * JS; w += NT) { const int l = w / JS, j = w - l * JS; if (l >= nbsB || j >= nmosB) CBs[w] = 0.0; }
   rotate_vecl_rows(p, tm, p.dtab + tm[SLVGPU_M_O_VECL], nmosB, R, CBs, [](int j, int l) { return l * JS + j; });   // CBs[l][j]
+  __syncthreads();                                       // geometry tables complete
   for (int w = tid; w < nij; w += NT) {
     const int i = w / nmosB, j = w - i * nmosB;
     const double dx = riA[i * 3] - riB[j * 3], dy = riA[i * 3 + 1] - riB[j * 3 + 1], dz = riA[i * 3 + 2] - riB[j * 3 + 2];

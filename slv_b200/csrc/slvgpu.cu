@@ -44,6 +44,7 @@ struct slvgpu_plan {
   int tailfill = 1;                           // SLVGPU_TAILFILL=0: k_pol and the first batch stream stay on the caller's stream
   cudaStream_t fan[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // per batch stream: extra streams the integral classes fan out over
   cudaEvent_t ev_side = nullptr, ev_fork[2] = {nullptr, nullptr}, ev_join[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  int rep_skip = 0;                           // experiments: SLVGPU_REP_SKIP=1 no integral kernels, 2 no transform kernels (results are then wrong)
   int rep_fan = -1;                           // extra streams per batch the integral kernels use (SLVGPU_REP_FAN, 0..2; -1: by type count)
   std::vector<int> rep_types;                 // fragment types that carry the wave-function tables
   std::vector<std::vector<int>> rep_cls;      // per such type: the 24 class offsets of its integral work list
@@ -356,6 +357,7 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
 #define X(ID, LA, LB, IA) cudaFuncSetAttribute(k_rep_ints<LA, LB, IA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   SLV_SUBSHELL_CLASSES(X)
 #undef X
+  if (const char *ev = getenv("SLVGPU_REP_SKIP")) pl->rep_skip = atoi(ev);
   if (const char *ev = getenv("SLVGPU_TAILFILL")) pl->tailfill = atoi(ev) != 0;
   if (const char *ev = getenv("SLVGPU_REP_FAN")) { const int v = atoi(ev); if (v >= 0 && v <= 2) pl->rep_fan = v; }
   if (const char *ev = getenv("SLVGPU_REP_PPB")) { const int v = atoi(ev); if (v >= 1 && v <= 32) pl->rep_ppb = v; }
@@ -522,7 +524,7 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
             const int ty = pl->rep_types[ti];
             const std::vector<int> &co = pl->rep_cls[ti];
 #define X(ID, LA, LB, IA)                                                                                         \
-            if (co[ID + 1] > co[ID]) {                                                                              \
+            if (co[ID + 1] > co[ID] && pl->rep_skip != 1) {                                                         \
               const int n_items = co[ID + 1] - co[ID];                                                              \
               k_rep_ints<LA, LB, IA><<<dim3((unsigned)((n_items + pl->rep_bt - 1) / pl->rep_bt), gy), pl->rep_bt, sm_geo,  \
                                        fs3[turn++ % (nfan + 1)]>>>(p, ty, co[ID], n_items, ppb, rp);                   \
@@ -538,7 +540,7 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
           for (size_t ti = 0; ti < pl->rep_types.size(); ++ti) {
             const int ty = pl->rep_types[ti];
             const RepSmem &rs = pl->rep_sm[ti];
-#define RP(KT_, NNT_) if (rs.KT == KT_ && rs.NNT == NNT_) k_rep_pair<KT_, NNT_><<<npairs, REP_THREADS, rs.bytes, sb>>>(p, ty, pl->fl, rp, rs);
+#define RP(KT_, NNT_) if (rs.KT == KT_ && rs.NNT == NNT_ && pl->rep_skip != 2) k_rep_pair<KT_, NNT_><<<npairs, REP_THREADS, rs.bytes, sb>>>(p, ty, pl->fl, rp, rs);
             RP(8, 1) RP(8, 2) RP(8, 3) RP(8, 4) RP(8, 5) RP(16, 1) RP(16, 2) RP(16, 3) RP(16, 4) RP(16, 5)
 #undef RP
             ++pl->last_launches;

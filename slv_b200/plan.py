@@ -164,6 +164,9 @@ class Plan(object):
                 m[M['IO_BFC']] = it.add(bfs.center); m[M['IO_BFL']] = it.add(bfs.powers); m[M['IO_BFNP']] = it.add(bfs.nprim)
                 m[M['O_BFEXP']] = dt.add(bfs.exps); m[M['O_BFCOEF']] = dt.add(bfs.coefs)
                 m[M['NSUBSH']] = len(bfs.subshells); m[M['IO_SUBSH']] = it.add(bfs.subshells)
+                # rotation blocks of the AO->LMO coefficient rows (VECROT): (first function, angular momentum) per sub-shell
+                it.pad(2)
+                m[M['NBFBLK']] = len(bfs.subshells); m[M['IO_BFBLK']] = it.add(bfs.subshells[:, [1, 2]])
                 self._bfs[t] = bfs
         # ---- every table a requested term reads must exist: the reference fails with KeyError on the missing parameter
         #      (solefp.py:1429 par['dpoli'], 1305 par['dpol'], 1531 par['fock']); here a missing table would be a bad address
