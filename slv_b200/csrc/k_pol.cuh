@@ -37,7 +37,9 @@ constexpr int POL_TILE = SLV_POL_TILE;   // centres the resident sweep tile hold
 constexpr int POL_ROWS = SLV_POL_ROWS;   // rows per lane in the resident sweep (2: the tile entry of a column is read once for two rows)
 constexpr int POL_BSH = POL_ROWS == 2 ? 6 : 5;   // log2 of the rows of a sweep block
 constexpr int SITE_ROW = 24;     // pos3, mom20, molecule id
-constexpr int PST = 30;          // BiCG state per centre: x xt r rt p pt u ut q qt (3 each)
+constexpr int PST = 32;          // BiCG state per centre: x xt r rt p pt u ut q qt (3 each) + 2 pad: rows are 32-byte aligned, the
+                                 // vector phases move them with 256-bit loads / stores (a third of the memory requests)
+constexpr int AST = 12;          // row stride of the centre polarisabilities (9 used)
 
 struct PolWork {                 // per-CTA workspace (device pointers already offset per CTA by the kernel)
   double *cent_pos;   // [cent_cap][3]
@@ -51,6 +53,15 @@ struct PolWork {                 // per-CTA workspace (device pointers already o
   int *ent_coff;      // [list_cap] first centre of a list entry
   int *ent_soff;      // [list_cap] first site of a list entry
 };
+
+// 256-bit accesses to the L2-resident workspace (32-byte aligned rows); volatile + memory clobber: the rows are shared
+// between the phases of the solver through barriers
+__device__ __forceinline__ void ld4(const double *p, double *o) {
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st4(double *p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 
 // One ordered centre pair of the BiCG sweep: dipole tensor of R = rc - r_j applied to the two search directions
 // held in the tile entry tt = {r_j(3), p_j(3), ut_j(3), molecule_j}; same-molecule pairs (incl. self) are masked branch-free.
@@ -80,7 +91,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
   {
     const size_t cb = blockIdx.x;
     const size_t cc = (size_t)p.cent_cap;
-    wk.cent_pos += cb * cc * 3; wk.cent_alpha += cb * cc * 9; wk.fld += cb * cc * 3; wk.xy += cb * cc * (PST + 6);
+    wk.cent_pos += cb * cc * 3; wk.cent_alpha += cb * cc * AST; wk.fld += cb * cc * 3; wk.xy += cb * cc * (PST + 8);
     wk.site += cb * (size_t)p.site_cap * SITE_ROW; wk.cent_mol += cb * cc; wk.aux += cb * cc * 6;
     wk.ent_coff += cb * (size_t)p.list_cap; wk.ent_soff += cb * (size_t)p.list_cap;
     wk.part += cb * (size_t)(POL_THREADS / 32) * 2 * 64 * 6;
@@ -172,7 +183,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
         rot_vec(R, p.dtab + tm[SLVGPU_M_O_RPOL] + l * 3, y);
         rot_mat(R, p.dtab + tm[SLVGPU_M_O_POL] + l * 9, a);
         for (int d = 0; d < 3; ++d) wk.cent_pos[(size_t)(c0 + l) * 3 + d] = y[d] + t[d];
-        for (int d = 0; d < 9; ++d) wk.cent_alpha[(size_t)(c0 + l) * 9 + d] = a[d];
+        for (int d = 0; d < 9; ++d) wk.cent_alpha[(size_t)(c0 + l) * AST + d] = a[d];
         wk.cent_mol[c0 + l] = mol;
       }
       for (int s = 0; s < nd; ++s) {
@@ -213,7 +224,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
           }
         }
         if (act) {
-          const double *a = wk.cent_alpha + (size_t)c * 9;
+          const double *a = wk.cent_alpha + (size_t)c * AST;
           wk.fld[(size_t)c * 3] = F[0]; wk.fld[(size_t)c * 3 + 1] = F[1]; wk.fld[(size_t)c * 3 + 2] = F[2];
           double *v = wk.xy + (size_t)c * PST;               // state slot 0..2 <- b = alpha F
           for (int i = 0; i < 3; ++i) v[i] = a[i * 3] * F[0] + a[i * 3 + 1] * F[1] + a[i * 3 + 2] * F[2];
@@ -265,7 +276,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       // sweep operands of the first iteration: u = p, ut = alpha^T pt (later iterations write them where p, pt are updated)
       for (int c = tid; c < ncent; c += NT) {
         double *s_ = stt + (size_t)c * PST;
-        const double *a = wk.cent_alpha + (size_t)c * 9;
+        const double *a = wk.cent_alpha + (size_t)c * AST;
         double *dst = resident ? s_tile + c * 10 + 3 : s_ + 18;
         for (int i = 0; i < 3; ++i) {
           dst[i] = s_[12 + i];
@@ -278,13 +289,16 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
         // q = p + alpha (T p), qt = pt + T ut for one row, from the accumulated tensor applications
         auto finish = [&](int c, const double *ax, const double *ay) {
           double *s_ = stt + (size_t)c * PST;
-          const double *a = wk.cent_alpha + (size_t)c * 9;
+          double v[8], a[12], q[3], qt[3];                    // v = p(3) pt(3) u(2)
+          ld4(s_ + 12, v); ld4(s_ + 16, v + 4);
+          const double *ag = wk.cent_alpha + (size_t)c * AST;
+          ld4(ag, a); ld4(ag + 4, a + 4); ld4(ag + 8, a + 8);
           for (int i = 0; i < 3; ++i) {
-            const double q = s_[12 + i] + a[i * 3] * ax[0] + a[i * 3 + 1] * ax[1] + a[i * 3 + 2] * ax[2];
-            const double qt = s_[15 + i] + ay[i];
-            pq += s_[15 + i] * q;
-            s_[24 + i] = q; s_[27 + i] = qt;
+            q[i] = v[i] + a[i * 3] * ax[0] + a[i * 3 + 1] * ax[1] + a[i * 3 + 2] * ax[2];
+            qt[i] = v[3 + i] + ay[i];
+            pq += v[3 + i] * q[i];
           }
+          st4(s_ + 24, q[0], q[1], q[2], qt[0]); st4(s_ + 28, qt[1], qt[2], 0.0, 0.0);
         };
         if (resident) {
           // Balanced sweep.  Rows are taken in blocks of 64 (two per lane: the tile entry of column j is read from
@@ -405,12 +419,16 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
         double prho = 0.0, pr = 0.0;
         for (int c = tid; c < ncent; c += NT) {
           double *s_ = stt + (size_t)c * PST;
+          double v[20], w[8];                                  // v = x xt r rt p pt u(2), w = q qt pad(2)
+          ld4(s_, v); ld4(s_ + 4, v + 4); ld4(s_ + 8, v + 8); ld4(s_ + 12, v + 12); ld4(s_ + 16, v + 16);
+          ld4(s_ + 24, w); ld4(s_ + 28, w + 4);
           for (int i = 0; i < 3; ++i) {
-            s_[i] += al * s_[12 + i]; s_[3 + i] += al * s_[15 + i];
-            const double r = s_[6 + i] - al * s_[24 + i], rt = s_[9 + i] - al * s_[27 + i];
-            s_[6 + i] = r; s_[9 + i] = rt;
+            v[i] += al * v[12 + i]; v[3 + i] += al * v[15 + i];
+            const double r = v[6 + i] - al * w[i], rt = v[9 + i] - al * w[3 + i];
+            v[6 + i] = r; v[9 + i] = rt;
             prho += rt * r; pr = fmax(pr, fmax(fabs(r), fabs(rt)));
           }
+          st4(s_, v[0], v[1], v[2], v[3]); st4(s_ + 4, v[4], v[5], v[6], v[7]); st4(s_ + 8, v[8], v[9], v[10], v[11]);
         }
         double rho1 = prho, rmax = pr;
         block_sum_max_1b(rho1, rmax, s_redB);
@@ -421,13 +439,13 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
         rho = rho1;
         for (int c = tid; c < ncent; c += NT) {                 // new search directions, and the next sweep's operands
           double *s_ = stt + (size_t)c * PST;
-          const double *a = wk.cent_alpha + (size_t)c * 9;
           double *dst = resident ? s_tile + c * 10 + 3 : s_ + 18;
-          double pn[3], ptn[3];
-          for (int i = 0; i < 3; ++i) {
-            pn[i] = s_[6 + i] + be * s_[12 + i]; ptn[i] = s_[9 + i] + be * s_[15 + i];
-            s_[12 + i] = pn[i]; s_[15 + i] = ptn[i];
-          }
+          double v[16], a[12], pn[3], ptn[3];                  // v = s_[4..19]: xt(2) r rt p pt u(2)
+          ld4(s_ + 4, v); ld4(s_ + 8, v + 4); ld4(s_ + 12, v + 8); ld4(s_ + 16, v + 12);
+          const double *ag = wk.cent_alpha + (size_t)c * AST;
+          ld4(ag, a); ld4(ag + 4, a + 4); ld4(ag + 8, a + 8);
+          for (int i = 0; i < 3; ++i) { pn[i] = v[2 + i] + be * v[8 + i]; ptn[i] = v[5 + i] + be * v[11 + i]; }
+          st4(s_ + 12, pn[0], pn[1], pn[2], ptn[0]); st4(s_ + 16, ptn[1], ptn[2], v[14], v[15]);
           for (int i = 0; i < 3; ++i) {
             dst[i] = pn[i];
             dst[3 + i] = a[i] * ptn[0] + a[3 + i] * ptn[1] + a[6 + i] * ptn[2];
@@ -437,7 +455,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
     } else resid = 0.0;
     for (int c = tid; c < ncent; c += NT) {       // x, and y = alpha^T xt
       const double *s_ = stt + (size_t)c * PST;
-      const double *a = wk.cent_alpha + (size_t)c * 9;
+      const double *a = wk.cent_alpha + (size_t)c * AST;
       double *v = vfin + (size_t)c * 6;
       for (int i = 0; i < 3; ++i) {
         v[i] = s_[i];
@@ -586,7 +604,7 @@ k_pol(const DevPlan p, int frame0, int nframes, FrameLists fl, PolWork wk0, doub
       }
       __syncthreads();
       for (int c = tid; c < ncent; c += NT) {                          // preconditioned rhs b = alpha dF
-        const double *a = wk.cent_alpha + (size_t)c * 9, *F = dFv + (size_t)c * 3;
+        const double *a = wk.cent_alpha + (size_t)c * AST, *F = dFv + (size_t)c * 3;
         double *v = wk.xy + (size_t)c * PST;
         for (int i = 0; i < 3; ++i) v[i] = a[i * 3] * F[0] + a[i * 3 + 1] * F[1] + a[i * 3 + 2] * F[2];
       }

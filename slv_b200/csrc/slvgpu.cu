@@ -303,9 +303,9 @@ extern "C" int slvgpu_plan_create(const slvgpu_plan_desc *d, slvgpu_plan **out) 
     // for ~400 centres, worse at ~500 and a longer tail -- DESIGN.md)
     const size_t nc = (size_t)pl->pol_ctas, cc = (size_t)p.cent_cap;
     TRY(dalloc(pl, &pl->pw.cent_pos, nc * cc * 3));
-    TRY(dalloc(pl, &pl->pw.cent_alpha, nc * cc * 9));
+    TRY(dalloc(pl, &pl->pw.cent_alpha, nc * cc * AST));
     TRY(dalloc(pl, &pl->pw.fld, nc * cc * 3));
-    TRY(dalloc(pl, &pl->pw.xy, nc * cc * (PST + 6)));
+    TRY(dalloc(pl, &pl->pw.xy, nc * cc * (PST + 8)));
     TRY(dalloc(pl, &pl->pw.site, nc * (size_t)p.site_cap * SITE_ROW));
     TRY(dalloc(pl, &pl->pw.aux, nc * cc * 6));
     TRY(dalloc(pl, &pl->pw.part, nc * (size_t)(POL_THREADS / 32) * 2 * 64 * 6));
