@@ -109,12 +109,16 @@ SLV_HD void subshell_pair_t(const double A[3], const double B[3], const double L
   for (int w = 0; w < NA * NB * 4; ++w) acc[w] = 0.0;
   // records k < PP_SREC come from srec[(k * PP_REC + field) * sstride] (the kernel's shared-memory copy), the rest from rec
   for (int k = 0; k < npp; ++k) {
-    const bool sh = srec != nullptr && k < PP_SREC;
-    const double *r = sh ? srec + (size_t)k * PP_REC * sstride : rec + (size_t)k * PP_REC;
-    const int st = sh ? sstride : 1;
-    if (!(AB2 <= r[0])) break;
+    double thr, mu, pref0, ip, a, b;
+    if (srec != nullptr && k < PP_SREC) {                  // two separate paths: a pointer select would turn both into generic loads
+      const double *r = srec + (size_t)k * PP_REC * sstride;
+      thr = r[0]; mu = r[sstride]; pref0 = r[2 * sstride]; ip = r[3 * sstride]; a = r[4 * sstride]; b = r[5 * sstride];
+    } else {
+      const double *r = rec + (size_t)k * PP_REC;
+      thr = r[0]; mu = r[1]; pref0 = r[2]; ip = r[3]; a = r[4]; b = r[5];
+    }
+    if (!(AB2 <= thr)) break;
     {
-      const double mu = r[st], pref0 = r[2 * st], ip = r[3 * st], a = r[4 * st], b = r[5 * st];
       const double pref = pref0 * exp(-mu * AB2);
       if constexpr (LA == 0 && LB == 0) {
         // s|s in closed form (a fifth of all items): S = pref, T = mu (3 - 2 mu AB^2) S, dS/dA = -2 mu (A - B) S,

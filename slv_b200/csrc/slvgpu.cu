@@ -508,7 +508,7 @@ static int launch_rest(slvgpu_plan *pl, int64_t f0, int nf, double *d_out, int32
           ++pl->last_launches;
           // integral kernels: grid.x covers the items of a class, grid.y the pairs of the type in groups of ppb (the
           // type's pair count lives on the device; groups past it leave at once)
-          const int ppb = pl->rep_ppb > 0 ? pl->rep_ppb : (4);
+          const int ppb = pl->rep_ppb > 0 ? pl->rep_ppb : (npairs >= 8192 ? 16 : 8);
           const unsigned gy = (unsigned)((npairs + ppb - 1) / ppb);
           // many fragment types (protein side chains) mean many small launches per batch: those gain from the fan-out
           // (config 4: 7.1 -> 5.7 ms), two big types do not (config 3: 37.0 -> 37.6 ms)
