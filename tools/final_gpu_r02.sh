@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 closing measurements on one B200 (run through gpurun from the repo root; outputs under gpurun_out/, at most
 # 64 MiB per call come back: the three parts run as separate gpurun calls).   usage: tools/final_gpu_r02.sh prof|lists|bench
-T=${TAG:-r02c}
+T=${TAG:-r02d}
 set -x
 case "$1" in
 prof)   # ncu --set full of the dominant kernel on the headline workload and on config 2, and of the other per-frame kernels
