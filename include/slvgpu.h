@@ -147,8 +147,9 @@ void slvgpu_plan_destroy(slvgpu_plan *plan);
  * sdmtpm/sdmtpe/dmtcor/sdisp6/tdisp6, shftex.f SHFTEX, PyQuante getSAB/getTAB/getSA1B/getTA1B).
  * Work is enqueued on `stream` and the call returns without waiting for it, except when the plan has
  * SLVGPU_REP: the exchange-repulsion batches are sized from per-frame fragment counts read back on the host, so
- * the call synchronises `stream` once per chunk of max_chunk frames (and is therefore not graph-capturable); its
- * batches also use a plan-owned side stream that is joined back into `stream` before the call returns. */
+ * the call synchronises `stream` once per chunk of max_chunk frames (right after the per-frame kernels of the chunk; it is
+ * therefore not graph-capturable); the polarisation kernel and the batches also use plan-owned streams (one of high
+ * priority), all joined back into `stream` before the call returns. */
 int slvgpu_eval_frames(slvgpu_plan *plan, const double *d_coords, int64_t nframes,
                        double *d_out, int32_t *d_status, void *stream);
 

@@ -11,8 +11,9 @@
 //   k_rep_prep   per frame: lab-frame solute atoms and displacement vectors, the solute's rotated AO->LMO coefficients
 //                in k-octet tiles; per (frame, fragment) pair: the fragment's atoms and the pair -> (frame, entry, type) map
 //   k_rep_ints   AO integrals V[pair][k][l][q] (q = S, T, L.dS, L.dT; l padded to a multiple of 4): one launch per (fragment
-//                type, sub-shell class), one thread per (pair, sub-shell-pair item), grid-wide -- every warp runs one
-//                specialisation of slv_ints.cuh with near-equal loop lengths
+//                type, sub-shell class); a thread owns one (sub-shell pair) item of the class and walks 8 or 16 pairs of the
+//                type's pair list (geometry staged per warp with cp.async, primitive pairs from the plan's sorted records,
+//                one 256-bit store per record) -- every warp runs one specialisation of slv_ints.cuh with near-equal loops
 //   k_rep_pair   one CTA per (frame, fragment) pair, one launch per fragment type.  The pair's integrals stream through
 //                shared memory in tiles of KT solute basis functions (one cp.async.bulk per tile, completion on an
 //                mbarrier, the next tile in flight while the current one is consumed); per tile
