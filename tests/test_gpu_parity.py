@@ -530,7 +530,7 @@ def test_slice_fed_chunks_equal_the_device_path(frags, monkeypatch):
     ind = [0] + [1] * nw; nmol = [12] + [3] * nw
     monkeypatch.setenv('SLVGPU_STAGE_SLICE', '7')
     efp = _efp(rep=True, ccut=30.0, pcut=14.0, ecut=11.0)
-    efp.max_chunk = 16                                               # chunks of 16 frames = slices of 7 (first: 4), 7, 2
+    efp.max_chunk = 16                                               # chunks of 16 frames = slices of 7, 7, 2
     rows_dev, st_dev = efp.eval_frames(torch.from_numpy(X).cuda(), ind, nmol, [sol, wat], [None, None], [None, None])
     rows_dev = rows_dev.cpu().numpy()
     rows_host, st_host = efp.eval_frames(X)
