@@ -540,6 +540,32 @@ def test_slice_fed_chunks_equal_the_device_path(frags, monkeypatch):
     assert np.array_equal(rows32, rows64)
 
 
+def test_chunk_schedule_does_not_change_the_rows(frags, monkeypatch):
+    """k_pol on the plan's high-priority stream with the exchange-repulsion batches filling the tail of its frame queue
+    (the default), the strictly serial schedule (SLVGPU_TAILFILL=0) and the integral classes fanned out over extra
+    streams must give the same rows bit for bit: the schedule only moves kernels in time."""
+    import torch
+    from slv_b200 import synth
+    sol, wat, dmso = frags('mescn'), frags('water'), frags('dmso')
+    types = np.random.default_rng(8).integers(0, 2, 40)
+    X = synth.make_trajectory(sol.get_pos(), [wat.get_pos(), dmso.get_pos()], types, 24, seed=73, spacing=8.5)
+    ind = [0] + [1 + int(t) for t in types]; nmol = [7] + [3 if t == 0 else 10 for t in types]
+    d = torch.from_numpy(X).cuda()
+    rows = []
+    for env in ({}, {'SLVGPU_TAILFILL': '0'}, {'SLVGPU_REP_FAN': '2'}, {'SLVGPU_REP_PPB': '3'}):
+        for k in ('SLVGPU_TAILFILL', 'SLVGPU_REP_FAN', 'SLVGPU_REP_PPB'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        efp = _efp(mode=4, rep=True, ccut=40.0, pcut=17.0, ecut=12.0)      # a new plan reads the environment
+        r, st = efp.eval_frames(d, ind, nmol, [sol, wat, dmso], [None] * 3, [None] * 3)
+        assert int(st.max()) == 0
+        rows.append(r.cpu().numpy())
+    for r in rows[1:]:
+        assert np.array_equal(r, rows[0])
+    assert np.abs(rows[0][:, 5]).max() > 0 and np.abs(rows[0][:, 4]).max() > 0
+
+
 def test_mdrun_reads_xtc_like_the_same_coordinates_as_an_array(frags, golden, tmp_path):
     """N1: the frame loop on a GROMACS XTC file (nm, float32, decoded by the library, gathered and converted on the
     device) writes the report it writes for the same float32 coordinates handed over as an array in Angstrom."""
