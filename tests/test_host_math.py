@@ -186,3 +186,20 @@ def test_primitive_pair_records_are_a_sorted_screening_table(frags, na, nb):
                 keep = r[:, 4] * r[:, 5] * ab2 <= 46.0 * (r[:, 4] + r[:, 5])
                 n = int(keep.sum())
                 assert keep[:n].all() and not keep[n:].any()
+
+
+def test_d_component_norm_ratio_is_sqrt3_for_every_bundled_basis(frags):
+    """slv_ints.cuh contracts a d sub-shell with the coefficients of its first component and rescales d_xy, d_xz, d_yz by
+    the compile-time constant sqrt(3) (cart_norm_ratio).  That holds because primitive norms differ by exactly sqrt(3)
+    between xx- and xy-type components while the contracted norms are equal: check it on the tables of every element the
+    bundled basis set knows, for every primitive."""
+    from slv_b200.basis import BasisSet
+    for z in (1, 3, 6, 7, 8, 9, 11, 16, 17):
+        b = BasisSet([z], np.zeros((1, 3)))
+        for atom, f0, L, npr in b.subshells:
+            if L != 2:
+                continue
+            c = b.coefs[f0:f0 + 6, :npr]
+            assert np.allclose(c[1:3] / c[0], 1.0, rtol=1e-14, atol=0)
+            assert np.allclose(c[3:6] / c[0], np.sqrt(3.0), rtol=1e-14, atol=0)
+            assert (b.exps[f0:f0 + 6, :npr] == b.exps[f0, :npr]).all()
